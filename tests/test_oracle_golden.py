@@ -1,0 +1,144 @@
+"""Pins the oracle (numpy + C restatements) to the reference: known-answer vectors of the reference's own
+tests and the fixtures generated from the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden_index, load_golden
+from oracle import c_oracle, numpy_oracle as no
+
+KS = (1, 3, 5, 16, 31)
+
+
+# ---- known answers copied from the reference's tests (tests/test_kmer_hashing.py) -------------------
+def test_known_answer_hashes():
+    assert no.sequence_to_kmer_hash("ACTG") == 0 * 1 + 1 * 4 + 3 * 16 + 2 * 64          # :10-11
+    assert no.sequence_to_kmer_hash("T" * 31) == 4611686018427387903                      # :27
+    for s in ["CAtgAACAtttggtAATCTACAtgAACAttt", "ACAtgAACAtttggtAATCTACAtgAACAtt"]:      # :13-24
+        assert no.sequence_to_kmer_hash(s) == int(np.sum(no.reverse_power_array(31) * no.letter_sequence_to_numeric(s)))
+    for s in ["atg", "Acacatacgactacg", "CAtgAACAtttggtAATCTACAtgAACAttt", "G"]:          # :30-35
+        assert no.kmer_hash_to_sequence(no.sequence_to_kmer_hash(s), len(s)) == s.lower()
+
+
+def test_known_answer_revcomp():
+    comp = str.maketrans("ACGTacgt", "TGCAtgca")
+    for s in ["AcATaCAG", "AGACATTA", "GGGGAAAACCCCTTTTAAAACCCCTTTTGGG", "G" * 31, "ACT"]:  # :38-54
+        k = len(s)
+        h = np.array([no.sequence_to_kmer_hash(s)], dtype=np.uint64)
+        for impl in (no.revcomp_hashes, c_oracle.revcomp_hashes):
+            rc = impl(h, k)
+            assert impl(rc, k)[0] == h[0]
+            assert no.kmer_hash_to_sequence(rc[0], k) == s[::-1].translate(comp).lower()
+    bases = no.kmer_hashes_to_bases(np.array([no.sequence_to_kmer_hash(s) for s in ["ACTG", "TGGC"]], dtype=np.uint64), 4)
+    assert ["".join(no.numeric_to_letter_sequence(b)).upper() for b in bases] == ["ACTG", "TGGC"]   # :69-75
+
+
+def test_known_answer_tiny_index():
+    """tests/test_collision_free_kmer_index.py:6-27 + SURVEY appendix A tables."""
+    kmers = np.array([1, 1, 2, 2, 4, 5, 3], dtype=np.uint64)
+    nodes = np.array([5, 6, 7, 8, 10, 11, 100])
+    ref = np.array([1, 1, 2, 3, 10, 11, 100])
+    af = np.ones(7, dtype=np.float32)
+    idx = no.build_index(kmers, nodes, ref, af, modulo=4)
+    assert list(idx["_hashes_to_index"]) == [0, 1, 4, 6] and list(idx["_n_kmers"]) == [1, 3, 2, 1]
+    assert list(no.index_get(idx, 1)[0]) == [5, 6] and list(no.index_get(idx, 1)[1]) == [1, 1]
+    assert list(no.index_get(idx, 5)[0]) == [11]
+    q = np.array([1, 2, 3, 10, 10, 12, 100, 101, 102, 5], dtype=np.uint64)                 # :30-34
+    assert list(no.has_kmers(idx, q)) == [True, True, True, False, False, False, False, False, False, True]
+    g = load_golden("tiny_index")
+    for key in ("hashes_to_index", "n_kmers", "kmers", "nodes", "ref_offsets", "frequencies", "allele_frequencies"):
+        assert np.array_equal(idx["_" + key], g["stable_" + key]), key
+        assert idx["_" + key].dtype == g["stable_" + key].dtype, key
+    cidx = c_oracle.build_index(kmers, nodes, ref, af, 4)
+    for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_frequencies"):
+        assert np.array_equal(cidx[key], idx[key]), key
+
+
+# ---- fixtures generated from the reference ----------------------------------------------------------
+def test_hashing_golden():
+    g = load_golden("hashing")
+    reads = g["reads"]
+    assert np.array_equal(no.letter_sequence_to_numeric(g["encode_in"]), g["encode_out"])
+    for k in KS:
+        fwd, rc = no.hash_reads(reads, k)
+        assert np.array_equal(fwd, g["fwd_k%d" % k]) and np.array_equal(rc, g["rc_k%d" % k]), k
+        cf, cr = c_oracle.hash_reads(reads, k)
+        assert np.array_equal(cf, fwd) and np.array_equal(cr, rc), k
+        for r in (0, 5, 17):
+            assert np.array_equal(no.read_kmer_hashes(reads[r], k), fwd[r])
+
+
+def test_revcomp_golden():
+    g = load_golden("revcomp")
+    for k in (1, 2, 4, 9, 16, 30, 31):
+        h = g["in_k%d" % k]
+        for impl_rc, impl_c in ((no.revcomp_hashes, no.complement_hashes),
+                                (c_oracle.revcomp_hashes, c_oracle.complement_hashes)):
+            assert np.array_equal(impl_rc(h, k), g["rc_k%d" % k]), k
+            assert np.array_equal(impl_c(h, k), g["comp_k%d" % k]), k
+        assert np.array_equal(no.kmer_hashes_to_bases(h, k), g["bases_k%d" % k])
+    for s, h, back in zip(g["seqs"], g["seq_hashes"], g["seq_back"]):
+        assert no.sequence_to_kmer_hash(str(s)) == int(h)
+        assert no.kmer_hash_to_sequence(h, len(str(s))) == str(back)
+
+
+@pytest.mark.parametrize("name", ["index_small", "index_sparse"])
+def test_build_golden(name):
+    g = load_golden(name)
+    with_freq = bool(g["stable_frequencies"].any())
+    idx = no.build_index(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"],
+                         int(g["stable_modulo"]), skip_frequencies=not with_freq)
+    cidx = c_oracle.build_index(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"],
+                                int(g["stable_modulo"]), skip_frequencies=not with_freq)
+    for key in ("hashes_to_index", "n_kmers", "kmers", "nodes", "ref_offsets", "frequencies", "allele_frequencies"):
+        assert np.array_equal(idx["_" + key], g["stable_" + key]), key          # (ii) canonical order
+        assert idx["_" + key].dtype == g["stable_" + key].dtype, key
+        assert np.array_equal(cidx["_" + key], g["stable_" + key]), key
+    for key in ("hashes_to_index", "n_kmers"):                                   # (i) tables vs as-run
+        assert np.array_equal(idx["_" + key], g["asrun_" + key]), key
+    # (iii) per-bucket multiset equality vs the as-run (unstable argsort) reference
+    def canon(prefix):
+        b = g[prefix + "kmers"] % np.uint64(int(g["stable_modulo"]))
+        rec = np.rec.fromarrays([b, g[prefix + "kmers"], g[prefix + "nodes"], g[prefix + "ref_offsets"],
+                                 g[prefix + "allele_frequencies"], g[prefix + "frequencies"]])
+        return np.sort(rec)
+    assert np.array_equal(canon("stable_"), canon("asrun_"))
+
+
+@pytest.mark.parametrize("name", ["index_small", "index_sparse"])
+def test_lookup_and_counts_golden(name):
+    g = load_golden(name)
+    idx = golden_index(g)
+    q = g["queries"]
+    # single get (cfki:303-315)
+    nodes, offs, ns = [], [], []
+    for kmer in q[:200]:
+        r = no.index_get(idx, kmer, max_hits=10 ** 9)
+        ns.append(0 if r[0] is None else len(r[0]))
+        if r[0] is not None:
+            nodes.extend(r[0]); offs.extend(r[1])
+    assert ns == list(g["get_n"]) and nodes == list(g["get_nodes"]) and offs == list(g["get_ref_offsets"])
+    # CounterKmerIndex.count_kmers x2 + get_node_counts (cfki:33-40)
+    qq = np.concatenate([q, q[:100]])
+    assert np.array_equal(no.node_counts(idx, qq), g["node_counts_min0"])
+    nc = no.node_counts(idx, qq, int(g["n_nodes"]) + 17)
+    assert np.array_equal(nc, g["node_counts_min_big"]) and nc.dtype == np.float64
+    ec = c_oracle.count_kmers(idx, qq)
+    assert np.array_equal(c_oracle.node_counts_from_entry_counts(idx, ec, int(g["n_nodes"]) + 17), nc)
+    # compiled reference Cython probe (pyx:47-109), gates as in the .pyx
+    if "cython_get" in g.files:
+        assert np.array_equal(no.lookup_hits(idx, q), g["cython_get"])
+        assert np.array_equal(c_oracle.lookup_hits(idx, q), g["cython_get"])
+    assert np.array_equal(no.lookup_hits(idx, q, False, None, None), c_oracle.lookup_hits(idx, q, False, None, None))
+    # map_kmers == per-entry counting when nothing is gated
+    assert np.array_equal(no.map_kmers(idx, qq, len(nc)).astype(np.float64), nc)
+    # reads -> node counts through ReadKmers + CounterKmerIndex
+    k = int(g["k"])
+    want = g["read_node_counts"]
+    assert np.array_equal(no.read_node_counts(idx, g["reads"], k, int(g["n_nodes"])), want)
+    assert np.array_equal(c_oracle.read_node_counts(idx, g["reads"], k, int(g["n_nodes"])), want)
+
+
+def test_without_singletons():
+    h = np.array([5, 7, 5, 9, 7, 5], dtype=np.uint64)
+    out = no.without_singletons(h, np.arange(6), np.arange(6) * 10, np.ones(6, np.float32))
+    assert list(out[0]) == [5, 7, 5] and list(out[1]) == [2, 4, 5]      # flat_kmers.py:98-125
