@@ -1,0 +1,376 @@
+// build.cu -- K2: CollisionFreeKmerIndex construction on the device.
+//
+// Reference: collision_free_kmer_index.py:422-467 (from_flat_kmers) and :267-293 (set_frequencies):
+//   hashes = kmers % modulo; sorting = argsort(hashes); gather 5 columns; run heads -> hashes_to_index,
+//   run lengths -> n_kmers; frequencies = #distinct ref_offsets per k-mer.
+// Here: bucket keys (u32) -> STABLE LSD radix sort of (key, index) pairs, 8 bits per pass, only as many
+// passes as modulo-1 has bits -> run heads / tails written straight into the zeroed dense tables ->
+// one fused gather of the payload columns through the permutation -> frequencies by bucket-local scans.
+// The sort is stable so the payload order inside a bucket is the input order (the canonical order of
+// SURVEY.md section 8c(ii)); numpy's default argsort is not stable, so the reference's own payload order is
+// only defined up to a permutation inside each bucket.
+//
+// Roofline: HBM streaming.  Compulsory traffic 50*N + 8*modulo bytes; this implementation moves
+// 12 (keys) + P*(4 hist + 16 scatter) + 8 (tables) + ~24 gather-in (sector-amplified) + 24 out per entry.
+#include "common.cuh"
+
+namespace gki {
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RADIX = 256;
+
+__global__ void bucket_keys_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, uint32_t *__restrict__ keys) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        keys[i] = fastmod(__ldg(kmers + i), fm);
+}
+
+// per-tile digit histogram, stored digit-major: hist[d * n_tiles + tile]
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift,
+                                                                uint32_t *__restrict__ hist, int64_t n_tiles) {
+    __shared__ uint32_t h[RADIX];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        int64_t i = base + it * RS_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[(__ldg(keys + i) >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+// stable scatter of one tile.  Key order inside a tile: warp-major, then item, then lane -- i.e. memory order.
+// first_pass: values are the identity (not read).
+__global__ void __launch_bounds__(RS_THREADS)
+    radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, int64_t n, int shift,
+                         const uint32_t *__restrict__ offsets, int64_t n_tiles, uint32_t *__restrict__ keys_out,
+                         uint32_t *__restrict__ vals_out, bool first_pass) {
+    __shared__ uint32_t warp_hist[RS_WARPS][RADIX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int64_t warp_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_ITEMS * 32);
+    uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        int64_t i = warp_base + it * 32 + lane;
+        bool ok = i < n;
+        key[it] = ok ? __ldg(keys_in + i) : 0u;
+        uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+        rank[it] = 0;
+        if (ok) {
+            uint32_t d = (key[it] >> shift) & 0xFFu;
+            uint32_t peers = __match_any_sync(okmask, d);
+            uint32_t before = __popc(peers & ((1u << lane) - 1u));
+            int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) {
+                base = warp_hist[warp][d];
+                warp_hist[warp][d] = base + __popc(peers);
+            }
+            base = __shfl_sync(peers, base, leader);
+            rank[it] = base + before;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // digit = threadIdx.x: turn the per-warp counts into start positions in the output
+        uint32_t run = offsets[(int64_t)threadIdx.x * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; w++) {
+            uint32_t c = warp_hist[w][threadIdx.x];
+            warp_hist[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {
+        int64_t i = warp_base + it * 32 + lane;
+        if (i < n) {
+            uint32_t d = (key[it] >> shift) & 0xFFu;
+            uint32_t pos = warp_hist[warp][d] + rank[it];
+            keys_out[pos] = key[it];
+            vals_out[pos] = first_pass ? (uint32_t)i : __ldg(vals_in + i);
+        }
+    }
+}
+
+__global__ void iota_kernel(uint32_t *__restrict__ v, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+
+// Stable sort of (keys, identity) by the low `bits` bits.  On return *keys_sorted / *perm point into the
+// scratch buffers owned by `bufs`.
+struct SortBuffers {
+    Scratch keys[2], vals[2], hist;
+};
+
+static int radix_sort_pairs(SortBuffers &bufs, int64_t n, int bits, const uint32_t **keys_sorted, const uint32_t **perm,
+                            cudaStream_t s) {
+    // bufs.keys[0] holds the input keys
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    int passes = (bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    GKI_TRY(bufs.keys[1].alloc((size_t)n * 4, s));
+    GKI_TRY(bufs.vals[0].alloc((size_t)n * 4, s));
+    GKI_TRY(bufs.vals[1].alloc((size_t)n * 4, s));
+    GKI_TRY(bufs.hist.alloc((size_t)RADIX * n_tiles * 4, s));
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        int shift = 8 * p;
+        radix_hist_kernel<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(bufs.keys[cur].as<uint32_t>(), n, shift, bufs.hist.as<uint32_t>(), n_tiles);
+        GKI_CHECK_LAUNCH();
+        GKI_TRY(exclusive_scan_u32(bufs.hist.as<uint32_t>(), bufs.hist.as<uint32_t>(), (int64_t)RADIX * n_tiles, nullptr, s));
+        radix_scatter_kernel<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(bufs.keys[cur].as<uint32_t>(), bufs.vals[cur].as<uint32_t>(), n, shift,
+                                                                      bufs.hist.as<uint32_t>(), n_tiles, bufs.keys[cur ^ 1].as<uint32_t>(),
+                                                                      bufs.vals[cur ^ 1].as<uint32_t>(), p == 0);
+        GKI_CHECK_LAUNCH();
+        cur ^= 1;
+    }
+    *keys_sorted = bufs.keys[cur].as<uint32_t>();
+    *perm = bufs.vals[cur].as<uint32_t>();
+    return GKI_OK;
+}
+
+// run heads: hashes_to_index[bucket] = first sorted position (cfki:444-454)
+__global__ void run_heads_kernel(const uint32_t *__restrict__ keys, int64_t n, int32_t *__restrict__ h2i) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t k = __ldg(keys + i);
+        if (i == 0 || __ldg(keys + i - 1) != k) h2i[k] = (int32_t)i;
+    }
+}
+// run tails: n_kmers[bucket] = run length (cfki:455-457)
+__global__ void run_tails_kernel(const uint32_t *__restrict__ keys, int64_t n, const int32_t *__restrict__ h2i,
+                                 uint32_t *__restrict__ nk) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t k = __ldg(keys + i);
+        if (i == n - 1 || __ldg(keys + i + 1) != k) nk[k] = (uint32_t)(i + 1 - h2i[k]);
+    }
+}
+
+// cfki:436-440: the payload columns follow the sort
+__global__ void gather_payload_kernel(const uint32_t *__restrict__ perm, int64_t n, const uint64_t *__restrict__ kmers,
+                                      const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
+                                      const float *__restrict__ af, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o,
+                                      uint64_t *__restrict__ ref_o, float *__restrict__ af_o) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t p = __ldg(perm + i);
+        if (kmers_o) kmers_o[i] = __ldg(kmers + p);
+        if (nodes_o) nodes_o[i] = __ldg(nodes + p);
+        if (ref_o) ref_o[i] = __ldg(ref + p);
+        if (af_o) af_o[i] = __ldg(af + p);
+    }
+}
+
+template <typename T> __global__ void gather_kernel(const T *__restrict__ src, const uint32_t *__restrict__ perm, int64_t n, T *__restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __ldg(src + __ldg(perm + i));
+}
+
+// set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
+// (k-mer, ref_offset) pair
+__global__ void freq_first_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kmers,
+                                  const uint64_t *__restrict__ ref, const int32_t *__restrict__ h2i, int64_t n,
+                                  uint8_t *__restrict__ first) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = h2i[__ldg(keys + e)];
+        uint64_t km = __ldg(kmers + e);
+        uint64_t ro = ref ? __ldg(ref + e) : 0ull;
+        uint8_t f = 1;
+        for (int64_t c = e - 1; c >= s; c--) {
+            if (__ldg(kmers + c) == km && (!ref || __ldg(ref + c) == ro)) {
+                f = 0;
+                break;
+            }
+        }
+        first[e] = f;
+    }
+}
+// pass 2: frequency[e] = number of first-flagged entries of the bucket with the same k-mer (uint16, wraps)
+__global__ void freq_count_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kmers,
+                                  const int32_t *__restrict__ h2i, const uint32_t *__restrict__ nk, const uint8_t *__restrict__ first,
+                                  int64_t n, uint16_t *__restrict__ freq) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t b = __ldg(keys + e);
+        int64_t s = h2i[b], t = s + nk[b];
+        uint64_t km = __ldg(kmers + e);
+        uint32_t c = 0;
+        for (int64_t a = s; a < t; a++) c += (__ldg(kmers + a) == km) & first[a];
+        freq[e] = (uint16_t)c;
+    }
+}
+
+// flat_kmers.py:98-125: keep[i] = 0 for the first occurrence of a hash.  After the stable sort by
+// (hash % M) an earlier occurrence of the same hash sits earlier in the same key run.
+__global__ void non_first_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
+                                 const uint64_t *__restrict__ hashes, int64_t n, uint8_t *__restrict__ keep) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t key = __ldg(keys + p);
+        uint32_t me = __ldg(perm + p);
+        uint64_t h = __ldg(hashes + me);
+        uint8_t seen = 0;
+        for (int64_t c = p - 1; c >= 0 && __ldg(keys + c) == key; c--) {
+            if (__ldg(hashes + __ldg(perm + c)) == h) {
+                seen = 1;
+                break;
+            }
+        }
+        keep[me] = seen;
+    }
+}
+
+static int bit_length(uint64_t v) {
+    int b = 0;
+    while (v) {
+        b++;
+        v >>= 1;
+    }
+    return b;
+}
+
+static int sort_by_bucket(const uint64_t *d_kmers, int64_t n, uint64_t modulo, SortBuffers &bufs, const uint32_t **keys_sorted,
+                          const uint32_t **perm, cudaStream_t s) {
+    GKI_TRY(bufs.keys[0].alloc((size_t)n * 4, s));
+    int grid = grid_for(n, 256 * 4, device_info().sms * 16);
+    bucket_keys_kernel<<<grid, 256, 0, s>>>(d_kmers, n, make_fastmod(modulo), bufs.keys[0].as<uint32_t>());
+    GKI_CHECK_LAUNCH();
+    return radix_sort_pairs(bufs, n, bit_length(modulo - 1), keys_sorted, perm, s);
+}
+
+}  // namespace gki
+
+using namespace gki;
+
+extern "C" {
+
+int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
+                    uint64_t modulo, int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,
+                    uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out, uint32_t *perm_out,
+                    gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    GKI_REQUIRE(n >= 1, GKI_ERR_INVALID, "gki_index_build: empty FlatKmers (the reference raises IndexError, cfki:455)");
+    GKI_REQUIRE(n < (1ll << 31), GKI_ERR_UNSUPPORTED, "gki_index_build: n must be < 2^31 (int32 hashes_to_index, cfki:453)");
+    GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build: need 1 <= modulo < 2^32");
+    GKI_REQUIRE(kmers && hashes_to_index && n_kmers, GKI_ERR_INVALID, "gki_index_build: kmers / table outputs are NULL");
+    GKI_REQUIRE((!nodes_out || nodes) && (!ref_out || ref_offsets) && (!af_out || af), GKI_ERR_INVALID,
+                "gki_index_build: output column requested without its input");
+    const bool want_freq = freq_out && !(flags & GKI_BUILD_SKIP_FREQUENCIES);
+
+    DevIn d_kmers, d_nodes, d_ref, d_af;
+    GKI_TRY(d_kmers.stage(kmers, (size_t)n * 8, s));
+    GKI_TRY(d_nodes.stage(nodes_out ? nodes : nullptr, (size_t)n * 4, s));
+    GKI_TRY(d_ref.stage((ref_out || want_freq) ? ref_offsets : nullptr, (size_t)n * 8, s));
+    GKI_TRY(d_af.stage(af_out ? af : nullptr, (size_t)n * 4, s));
+    DevOut o_h2i, o_nk, o_kmers, o_nodes, o_ref, o_af, o_freq, o_perm;
+    GKI_TRY(o_h2i.prepare(hashes_to_index, (size_t)modulo * 4, s));
+    GKI_TRY(o_nk.prepare(n_kmers, (size_t)modulo * 4, s));
+    GKI_TRY(o_kmers.prepare(kmers_out, (size_t)n * 8, s));
+    GKI_TRY(o_nodes.prepare(nodes_out, (size_t)n * 4, s));
+    GKI_TRY(o_ref.prepare(ref_out, (size_t)n * 8, s));
+    GKI_TRY(o_af.prepare(af_out, (size_t)n * 4, s));
+    GKI_TRY(o_freq.prepare(freq_out, (size_t)n * 2, s));
+    GKI_TRY(o_perm.prepare(perm_out, (size_t)n * 4, s));
+
+    SortBuffers bufs;
+    const uint32_t *keys_sorted, *perm;
+    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, bufs, &keys_sorted, &perm, s));
+
+    const int grid_n = grid_for(n, 256 * 4, device_info().sms * 16);
+    GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)modulo * 4, s));
+    GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)modulo * 4, s));
+    run_heads_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, n, o_h2i.as<int32_t>());
+    GKI_CHECK_LAUNCH();
+    run_tails_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>());
+    GKI_CHECK_LAUNCH();
+
+    // the frequency pass needs sorted k-mers (and ref offsets) even if the caller did not ask for them
+    Scratch tmp_kmers, tmp_ref;
+    uint64_t *kmers_sorted = o_kmers.as<uint64_t>();
+    uint64_t *ref_sorted = o_ref.as<uint64_t>();
+    if (want_freq && !kmers_sorted) {
+        GKI_TRY(tmp_kmers.alloc((size_t)n * 8, s));
+        kmers_sorted = tmp_kmers.as<uint64_t>();
+    }
+    if (want_freq && !ref_sorted && d_ref.dptr) {
+        GKI_TRY(tmp_ref.alloc((size_t)n * 8, s));
+        ref_sorted = tmp_ref.as<uint64_t>();
+    }
+    gather_payload_kernel<<<grid_n, 256, 0, s>>>(perm, n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(),
+                                                 d_af.as<float>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>());
+    GKI_CHECK_LAUNCH();
+    if (o_perm.dptr) GKI_CUDA(cudaMemcpyAsync(o_perm.dptr, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+
+    if (freq_out) {
+        if (!want_freq) {
+            GKI_CUDA(cudaMemsetAsync(o_freq.dptr, 0, (size_t)n * 2, s));   // cfki:270-274
+        } else {
+            Scratch first;
+            GKI_TRY(first.alloc((size_t)n, s));
+            freq_first_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>());
+            GKI_CHECK_LAUNCH();
+            freq_count_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, kmers_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), first.as<uint8_t>(), n,
+                                                     o_freq.as<uint16_t>());
+            GKI_CHECK_LAUNCH();
+        }
+    }
+    GKI_TRY(o_h2i.finish(s));
+    GKI_TRY(o_nk.finish(s));
+    GKI_TRY(o_kmers.finish(s));
+    GKI_TRY(o_nodes.finish(s));
+    GKI_TRY(o_ref.finish(s));
+    GKI_TRY(o_af.finish(s));
+    GKI_TRY(o_freq.finish(s));
+    GKI_TRY(o_perm.finish(s));
+    return call.finish();
+}
+
+int gki_gather(const void *src, int32_t item_size, const uint32_t *perm, int64_t n, void *out, gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    GKI_REQUIRE(n >= 0 && (n == 0 || (src && perm && out)), GKI_ERR_INVALID, "gki_gather: bad arguments");
+    GKI_REQUIRE(item_size == 1 || item_size == 2 || item_size == 4 || item_size == 8, GKI_ERR_INVALID, "gki_gather: item_size must be 1, 2, 4 or 8");
+    if (n == 0) return GKI_OK;
+    DevIn d_src, d_perm;
+    DevOut o;
+    GKI_TRY(d_src.stage(src, (size_t)n * item_size, s));
+    GKI_TRY(d_perm.stage(perm, (size_t)n * 4, s));
+    GKI_TRY(o.prepare(out, (size_t)n * item_size, s));
+    int grid = grid_for(n, 256 * 4, device_info().sms * 16);
+    switch (item_size) {
+        case 1: gather_kernel<uint8_t><<<grid, 256, 0, s>>>(d_src.as<uint8_t>(), d_perm.as<uint32_t>(), n, o.as<uint8_t>()); break;
+        case 2: gather_kernel<uint16_t><<<grid, 256, 0, s>>>(d_src.as<uint16_t>(), d_perm.as<uint32_t>(), n, o.as<uint16_t>()); break;
+        case 4: gather_kernel<uint32_t><<<grid, 256, 0, s>>>(d_src.as<uint32_t>(), d_perm.as<uint32_t>(), n, o.as<uint32_t>()); break;
+        default: gather_kernel<uint64_t><<<grid, 256, 0, s>>>(d_src.as<uint64_t>(), d_perm.as<uint32_t>(), n, o.as<uint64_t>()); break;
+    }
+    GKI_CHECK_LAUNCH();
+    GKI_TRY(o.finish(s));
+    return call.finish();
+}
+
+int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *keep, gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    GKI_REQUIRE(n >= 0 && n < (1ll << 31) && (n == 0 || (hashes && keep)), GKI_ERR_INVALID, "gki_mark_non_first_occurrences: bad arguments");
+    if (n == 0) return GKI_OK;
+    DevIn d_h;
+    DevOut o;
+    GKI_TRY(d_h.stage(hashes, (size_t)n * 8, s));
+    GKI_TRY(o.prepare(keep, (size_t)n, s));
+    uint64_t m = (uint64_t)(2 * n + 1025) | 1ull;   // sparse odd table size: runs of distinct hashes stay short
+    if (m >= (1ull << 32)) m = (1ull << 32) - 1;
+    SortBuffers bufs;
+    const uint32_t *keys_sorted, *perm;
+    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, bufs, &keys_sorted, &perm, s));
+    non_first_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(keys_sorted, perm, d_h.as<uint64_t>(), n, o.as<uint8_t>());
+    GKI_CHECK_LAUNCH();
+    GKI_TRY(o.finish(s));
+    return call.finish();
+}
+
+}  // extern "C"

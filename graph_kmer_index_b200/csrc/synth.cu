@@ -1,0 +1,200 @@
+// synth.cu -- deterministic synthetic workloads (bit-identical to graph_kmer_index_b200/synthetic.py) and
+// the calibration micro-benchmarks (random-gather ceiling for K3, streaming copy for K1/K2).
+#include "common.cuh"
+
+namespace gki {
+
+constexpr uint64_t SEED_GENOME = 1, SEED_NODES = 2, SEED_AF = 3, SEED_READS = 4, SEED_BASES = 5, SEED_NS = 6;
+constexpr uint64_t PERM_MULT = 2654435761ull, PERM_ADD = 12345ull;
+
+__device__ __forceinline__ uint32_t packed_base(uint64_t seed, uint64_t idx) {
+    return (uint32_t)(rnd(seed, idx >> 5) >> ((idx & 31) << 1)) & 3u;
+}
+
+__global__ void synth_genome_kernel(uint8_t *__restrict__ codes, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        codes[i] = (uint8_t)packed_base(SEED_GENOME, (uint64_t)i);
+}
+
+__global__ void synth_flat_kmers_kernel(const uint8_t *__restrict__ g, int64_t n, uint64_t n_nodes, int k,
+                                        uint64_t *__restrict__ hashes, uint32_t *__restrict__ nodes,
+                                        uint64_t *__restrict__ ref, float *__restrict__ af) {
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t p = ((uint64_t)j * PERM_MULT + PERM_ADD) % (uint64_t)n;
+        uint64_t u = p >> 1;
+        uint64_t h = 0;
+        for (int b = 0; b < k; b++) h |= (uint64_t)__ldg(g + u + b) << (2 * b);
+        hashes[j] = h;
+        if (nodes) nodes[j] = (uint32_t)(rnd(SEED_NODES, p) % n_nodes);
+        if (ref) ref[j] = u;
+        if (af) af[j] = (float)((rnd(SEED_AF, p) & 1023ull) + 1ull) * (1.0f / 1024.0f);
+    }
+}
+
+__global__ void synth_reads_kernel(const uint8_t *__restrict__ g, int64_t glen, int64_t first_read, int64_t n_reads, int L,
+                                   uint32_t p_hit, uint32_t n_rate, uint8_t *__restrict__ out) {
+    const int64_t total = n_reads * L;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t rl = i / L;
+        int m = (int)(i - rl * L);
+        uint64_t r = (uint64_t)(first_read + rl);
+        uint64_t h = rnd(SEED_READS, r);
+        bool from_genome = (h % 1000ull) < p_hit && glen >= L;
+        uint64_t flat = r * (uint64_t)L + (uint64_t)m;
+        uint32_t code;
+        if (from_genome) {
+            uint64_t span = (uint64_t)(glen - L + 1);
+            int64_t start = (int64_t)((h >> 16) % span);
+            bool strand = (h >> 12) & 1ull;
+            code = strand ? 3u - __ldg(g + start + (L - 1 - m)) : __ldg(g + start + m);
+        } else {
+            code = packed_base(SEED_BASES, flat);
+        }
+        uint8_t c = (uint8_t)("ACGT"[code]);
+        if (n_rate && (rnd(SEED_NS, flat) % 1000ull) < n_rate) c = 'N';
+        out[i] = c;
+    }
+}
+
+// dependent == 0: each thread issues independent gathers; dependent == 1: each gather's address depends on the
+// previous value (2-deep chain like cell -> chain).
+__global__ void random_gather_kernel(const uint64_t *__restrict__ table, uint64_t n_words, int64_t n_gathers, int dependent,
+                                     uint64_t *__restrict__ sink) {
+    uint64_t acc = 0;
+    const int64_t T = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_gathers; i += 4 * T) {
+        uint64_t v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int64_t idx = i + j * T;
+            v[j] = idx < n_gathers ? __ldg(table + splitmix64((uint64_t)idx) % n_words) : 0;
+        }
+        if (dependent) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) v[j] = __ldg(table + (v[j] ^ splitmix64(v[j] + j)) % n_words);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc += v[j];
+    }
+    if (acc == 0x123456789abcdefull) *sink = acc;
+}
+
+__global__ void fill_kernel(uint64_t *__restrict__ t, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t[i] = splitmix64(i);
+}
+
+__global__ void copy_kernel(const uint4 *__restrict__ in, uint4 *__restrict__ out, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = in[i];
+}
+
+}  // namespace gki
+
+using namespace gki;
+
+extern "C" {
+
+int gki_synth_genome(uint8_t *codes, int64_t length, gki_stream_t stream) {
+    CallScope call(stream);
+    GKI_REQUIRE(length >= 0 && (length == 0 || codes), GKI_ERR_INVALID, "gki_synth_genome: bad arguments");
+    if (length == 0) return GKI_OK;
+    DevOut o;
+    GKI_TRY(o.prepare(codes, (size_t)length, call.stream));
+    synth_genome_kernel<<<grid_for(length, 256 * 4, device_info().sms * 16), 256, 0, call.stream>>>(o.as<uint8_t>(), length);
+    GKI_CHECK_LAUNCH();
+    GKI_TRY(o.finish(call.stream));
+    return call.finish();
+}
+
+int gki_synth_flat_kmers(const uint8_t *genome_codes, int64_t n_entries, int64_t n_nodes, int32_t k, uint64_t *hashes,
+                         uint32_t *nodes, uint64_t *ref_offsets, float *af, gki_stream_t stream) {
+    CallScope call(stream);
+    GKI_REQUIRE(genome_codes && hashes && n_entries >= 1 && n_nodes >= 1 && k >= 1 && k <= 31, GKI_ERR_INVALID, "gki_synth_flat_kmers: bad arguments");
+    cudaStream_t s = call.stream;
+    DevIn g;
+    GKI_TRY(g.stage(genome_codes, (size_t)((n_entries + 1) / 2 + k - 1), s));
+    DevOut oh, on, orf, oa;
+    GKI_TRY(oh.prepare(hashes, (size_t)n_entries * 8, s));
+    GKI_TRY(on.prepare(nodes, (size_t)n_entries * 4, s));
+    GKI_TRY(orf.prepare(ref_offsets, (size_t)n_entries * 8, s));
+    GKI_TRY(oa.prepare(af, (size_t)n_entries * 4, s));
+    synth_flat_kmers_kernel<<<grid_for(n_entries, 256 * 2, device_info().sms * 16), 256, 0, s>>>(
+        g.as<uint8_t>(), n_entries, (uint64_t)n_nodes, k, oh.as<uint64_t>(), on.as<uint32_t>(), orf.as<uint64_t>(), oa.as<float>());
+    GKI_CHECK_LAUNCH();
+    GKI_TRY(oh.finish(s));
+    GKI_TRY(on.finish(s));
+    GKI_TRY(orf.finish(s));
+    GKI_TRY(oa.finish(s));
+    return call.finish();
+}
+
+int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t first_read, int64_t n_reads, int32_t read_len,
+                    int32_t p_hit_permille, int32_t n_permille, uint8_t *reads, gki_stream_t stream) {
+    CallScope call(stream);
+    GKI_REQUIRE(genome_codes && reads && n_reads >= 0 && read_len >= 1 && genome_len >= 1, GKI_ERR_INVALID, "gki_synth_reads: bad arguments");
+    if (n_reads == 0) return GKI_OK;
+    cudaStream_t s = call.stream;
+    DevIn g;
+    GKI_TRY(g.stage(genome_codes, (size_t)genome_len, s));
+    DevOut o;
+    GKI_TRY(o.prepare(reads, (size_t)n_reads * read_len, s));
+    synth_reads_kernel<<<grid_for(n_reads * read_len, 256 * 4, device_info().sms * 16), 256, 0, s>>>(
+        g.as<uint8_t>(), genome_len, first_read, n_reads, read_len, (uint32_t)p_hit_permille, (uint32_t)n_permille, o.as<uint8_t>());
+    GKI_CHECK_LAUNCH();
+    GKI_TRY(o.finish(s));
+    return call.finish();
+}
+
+int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms) {
+    GKI_REQUIRE(table_bytes >= 8 && n_gathers >= 1 && ms, GKI_ERR_INVALID, "gki_calibrate_random_gather: bad arguments");
+    uint64_t n_words = (uint64_t)table_bytes / 8;
+    uint64_t *table = nullptr, *sink = nullptr;
+    GKI_CUDA(cudaMalloc((void **)&table, n_words * 8));
+    GKI_CUDA(cudaMalloc((void **)&sink, 8));
+    int grid = device_info().sms * 8;
+    fill_kernel<<<grid, 256>>>(table, n_words);
+    GKI_CHECK_LAUNCH();
+    cudaEvent_t a, b;
+    GKI_CUDA(cudaEventCreate(&a));
+    GKI_CUDA(cudaEventCreate(&b));
+    random_gather_kernel<<<grid, 256>>>(table, n_words, n_gathers / 8 + 1, dependent_loads, sink);   // warm-up
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(a));
+    random_gather_kernel<<<grid, 256>>>(table, n_words, n_gathers, dependent_loads, sink);
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(b));
+    GKI_CUDA(cudaEventSynchronize(b));
+    GKI_CUDA(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(table);
+    cudaFree(sink);
+    return GKI_OK;
+}
+
+int gki_calibrate_copy(int64_t bytes, float *ms) {
+    GKI_REQUIRE(bytes >= 16 && ms, GKI_ERR_INVALID, "gki_calibrate_copy: bad arguments");
+    int64_t n = bytes / 16;
+    uint4 *in = nullptr, *out = nullptr;
+    GKI_CUDA(cudaMalloc((void **)&in, (size_t)n * 16));
+    GKI_CUDA(cudaMalloc((void **)&out, (size_t)n * 16));
+    GKI_CUDA(cudaMemset(in, 1, (size_t)n * 16));
+    int grid = device_info().sms * 16;
+    cudaEvent_t a, b;
+    GKI_CUDA(cudaEventCreate(&a));
+    GKI_CUDA(cudaEventCreate(&b));
+    copy_kernel<<<grid, 256>>>(in, out, n);
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(a));
+    copy_kernel<<<grid, 256>>>(in, out, n);
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(b));
+    GKI_CUDA(cudaEventSynchronize(b));
+    GKI_CUDA(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(in);
+    cudaFree(out);
+    return GKI_OK;
+}
+
+}  // extern "C"

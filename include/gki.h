@@ -1,0 +1,182 @@
+/* gki.h -- C ABI of libgki.so: the B200 (sm_100a) implementation of graph_kmer_index's
+ * read-k-mer counting hot path.
+ *
+ * The reference (ivargr/graph_kmer_index) is pure Python/numpy and has no FFI of its own; its
+ * boundary is the Python API.  Each entry point below names the reference
+ * function(s) it replaces (file:line relative to the reference repository);
+ * graph_kmer_index_b200/*.py binds these through ctypes behind the reference's own class and
+ * function names, and INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative gki_status; gki_last_error() returns a
+ *     thread-local message for the last failure on the calling thread.
+ *   - Every array argument is a plain pointer that may live in DEVICE memory or in HOST memory
+ *     (pageable or pinned); the library detects which (cudaPointerGetAttributes).  Host inputs are
+ *     staged to the device (chunked and double-buffered for the streaming read batches), host
+ *     outputs are copied back before the call returns.  Calls whose arguments are all device
+ *     pointers are asynchronous on `stream` unless stated otherwise.
+ *   - Buffers are caller-owned and never freed or resized by the library; inputs are not modified.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - There is no CPU fallback: without a CUDA device every call fails with GKI_ERR_CUDA.
+ */
+#ifndef GKI_H
+#define GKI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    GKI_OK = 0,
+    GKI_ERR_INVALID = -1,     /* bad argument (k > 31, modulo == 0, NULL pointer ...)            */
+    GKI_ERR_CUDA = -2,        /* CUDA runtime error; text in gki_last_error()                    */
+    GKI_ERR_UNSUPPORTED = -3, /* outside the supported envelope (modulo >= 2^32, n >= 2^31 ...)   */
+    GKI_ERR_OVERFLOW = -4     /* caller-provided output capacity too small                       */
+} gki_status;
+
+typedef struct gki_index gki_index_t; /* opaque, device-resident CollisionFreeKmerIndex */
+typedef void *gki_stream_t;
+
+const char *gki_last_error(void);
+int gki_version(void);
+/* number of CUDA devices / current device selection (one process per GPU). */
+int gki_device_count(int *count);
+int gki_set_device(int device);
+/* number of kernel launches issued by this library so far (bench.py's gpu_launches). */
+int64_t gki_launch_count(void);
+
+/* ------------------------------------------------------------------ K1: encoding + hashing */
+
+/* flat_kmers.py:134-145 letter_sequence_to_numeric: ASCII (case-insensitive) -> a0 c1 g2 t3,
+ * every other byte -> 0.  out[n] uint64 (the reference's dtype). */
+int gki_encode_bases(const uint8_t *seq, int64_t n, uint64_t *out, gki_stream_t stream);
+
+/* read_kmers.py:67-70 ReadKmers.get_kmers_from_read_dynamic (np.convolve(read, power_array(k),
+ * 'valid')) for a batch of equal-length reads, plus read_kmers.py:21-26 (hashes of the
+ * reverse-complemented read).  reads: n_reads rows of read_len ASCII bytes, row_stride bytes apart.
+ * fwd / rc: (n_reads, read_len-k+1) uint64 row-major; either may be NULL.
+ * fwd[r][i] = sum_j code(read[i+j]) * 4^j;  rc[r][i] = the same over the reverse-complemented read.
+ * 1 <= k <= 31.  read_len < k yields no k-mers (documented deviation). */
+int gki_hash_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, int32_t k,
+                   uint64_t *fwd, uint64_t *rc, gki_stream_t stream);
+
+/* Ragged form of the above (read_kmers.py:14-49 from_fasta_file iterates reads of any length):
+ * read r occupies seq[offsets[r] .. offsets[r+1]); its max(len-k+1,0) hashes are written at
+ * fwd[out_offsets[r] ..) and rc[out_offsets[r] ..).  offsets/out_offsets have n_reads+1 entries. */
+int gki_hash_reads_ragged(const uint8_t *seq, const int64_t *offsets, const int64_t *out_offsets, int64_t n_reads,
+                          int32_t k, uint64_t *fwd, uint64_t *rc, gki_stream_t stream);
+
+/* kmer_hashing.py:24-28 kmer_hashes_to_reverse_complement_hash (+ :12-22 scalar/chunked wrappers). */
+int gki_revcomp_hashes(const uint64_t *in, int64_t n, int32_t k, uint64_t *out, gki_stream_t stream);
+/* kmer_hashing.py:31-36 kmer_hashes_to_complement_hashes. */
+int gki_complement_hashes(const uint64_t *in, int64_t n, int32_t k, uint64_t *out, gki_stream_t stream);
+/* kmer_hashing.py:53-65 kmer_hashes_to_bases: out is (n, k) uint64 row-major, column j = base j. */
+int gki_hashes_to_bases(const uint64_t *in, int64_t n, int32_t k, uint64_t *out, gki_stream_t stream);
+
+/* ------------------------------------------------------------------ K2: index construction */
+
+#define GKI_BUILD_SKIP_FREQUENCIES 1 /* from_flat_kmers(skip_frequencies=True): frequencies all 0 */
+
+/* collision_free_kmer_index.py:422-467 CollisionFreeKmerIndex.from_flat_kmers (+ :267-293
+ * set_frequencies): bucket = kmer % modulo, STABLE radix sort by bucket, run heads/lengths scattered
+ * into the dense tables, payload columns permuted by the sort.
+ *   in : kmers[n] u64, nodes[n] u32, ref_offsets[n] 8-byte items (moved bit-exactly), af[n] f32
+ *   out: hashes_to_index[modulo] i32, n_kmers[modulo] u32 (0 for empty buckets),
+ *        kmers_out/nodes_out/ref_out/af_out[n] permuted, freq_out[n] u16.
+ * Any of nodes/ref_offsets/af (and the matching output) may be NULL.  perm_out (optional, u32[n])
+ * receives the sort permutation (the reference's `sorting`, cfki:435) for columns of other dtypes.
+ * Requires 1 <= n < 2^31 and 1 <= modulo < 2^32. */
+int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af,
+                    int64_t n, uint64_t modulo, int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers,
+                    uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out,
+                    uint32_t *perm_out, gki_stream_t stream);
+
+/* out[i] = src[perm[i]] for items of item_size in {1,2,4,8} bytes (cfki:436-440 for any dtype). */
+int gki_gather(const void *src, int32_t item_size, const uint32_t *perm, int64_t n, void *out, gki_stream_t stream);
+
+/* flat_kmers.py:98-125 FlatKmers.get_new_without_singletons: keep[i] = 0 for the first occurrence
+ * of every hash, 1 otherwise (the caller compacts).  keep[n] u8. */
+int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *keep, gki_stream_t stream);
+
+/* ------------------------------------------------------------------ K3: resident index, lookup, counting */
+
+#define GKI_INDEX_NO_BITMAP 1     /* never build the L2-resident bucket-occupancy bitmap   */
+#define GKI_INDEX_FORCE_BITMAP 2  /* always build it                                       */
+
+/* Upload a CollisionFreeKmerIndex (cfki:176-189 attribute arrays; npz layout cfki:393-402) and lay it
+ * out for probing: {hashes_to_index, n_kmers} interleaved into one 8-byte cell per bucket, optional
+ * bucket-occupancy bitmap, zeroed per-entry counters.  ref_offsets/frequencies/af may be NULL (only
+ * gki_lookup_hits and the frequency gates need them). */
+int gki_index_create(const int32_t *hashes_to_index, const uint32_t *n_kmers, const uint64_t *kmers,
+                     const uint32_t *nodes, const uint64_t *ref_offsets, const uint16_t *frequencies,
+                     const float *af, int64_t n, uint64_t modulo, int32_t flags, gki_index_t **out,
+                     gki_stream_t stream);
+int gki_index_destroy(gki_index_t *index);
+/* introspection: n entries, modulo, max node id (cfki:237-238), device bytes, bitmap in use. */
+int gki_index_info(const gki_index_t *index, int64_t *n, uint64_t *modulo, int64_t *max_node,
+                   int64_t *device_bytes, int32_t *has_bitmap);
+
+/* cfki:30-31 CounterKmerIndex.reset (intended meaning: zero every counter). */
+int gki_reset_counts(gki_index_t *index, gki_stream_t stream);
+
+/* cfki:33-37 CounterKmerIndex.count_kmers: for every query k-mer present in the index add one to
+ * that k-mer's counter; absent k-mers are ignored.  queries[nq] u64. */
+int gki_count_kmers(gki_index_t *index, const uint64_t *queries, int64_t nq, gki_stream_t stream);
+
+/* Fused K1 -> K3 (read_kmers.py:14-26 then cfki:33-37): hash every k-mer of every read (forward and,
+ * if both_strands, the reverse-complemented read) and count it; hashes never touch HBM. */
+int gki_count_reads(gki_index_t *index, const uint8_t *reads, int64_t n_reads, int32_t read_len,
+                    int64_t row_stride, int32_t k, int32_t both_strands, gki_stream_t stream);
+
+#define GKI_COUNTS_WRAP_UINT16 1 /* weight = counter mod 2^16 (the reference's uint16 Counter, cfki:27) */
+
+/* cfki:39-40 CounterKmerIndex.get_node_counts: out[node] = sum over entries e with nodes[e]==node of
+ * counter[kmers[e]], as float64.  n_out must be >= max(min_nodes, max_node+1); out is overwritten. */
+int gki_node_counts(gki_index_t *index, double *out, int64_t n_out, int32_t flags, gki_stream_t stream);
+/* counter[kmers[e]] for every entry e (what `self.counter[self.kmers]` evaluates to, cfki:40). */
+int gki_entry_counts(gki_index_t *index, uint32_t *out, gki_stream_t stream);
+
+#define GKI_PROBE_SKIP_BUCKET0 1 /* cython_kmer_index.pyx:59-60, 84-85 */
+/* cfki:210-212 map_kmers (kmer_mapper.map_kmers_to_graph_index): node_counts[nodes[e]] += 1 for every
+ * (query, entry e) with kmers[e]==query [, frequencies[e] <= max_frequency if max_frequency >= 0].
+ * node_counts[n_nodes] u64 is ACCUMULATED into (caller zeroes it); entries whose node >= n_nodes are skipped. */
+int gki_map_kmers(gki_index_t *index, const uint64_t *queries, int64_t nq, uint64_t *node_counts, int64_t n_nodes,
+                  int32_t flags, int32_t max_frequency, gki_stream_t stream);
+/* cfki:214-216 has_kmers (kmer_mapper.in_graph_index): out[i] = 1 if queries[i] is in the index. */
+int gki_has_kmers(gki_index_t *index, const uint64_t *queries, int64_t nq, uint8_t *out, int32_t flags,
+                  gki_stream_t stream);
+/* cython_kmer_index.pyx:47-109 CythonKmerIndex.get: rows [node, ref_offset, query index, frequency,
+ * uint64(1000*af)] for every hit, ordered by query then entry.  out is (5, capacity) u64 row-major;
+ * *n_hits receives the total (call with out=NULL to size).  max_bucket / max_frequency < 0 disable
+ * the .pyx gates (pyx:62-63, 70-71); pass 10000 / 20 and GKI_PROBE_SKIP_BUCKET0 to reproduce them.
+ * Synchronises `stream`. */
+int gki_lookup_hits(gki_index_t *index, const uint64_t *queries, int64_t nq, int32_t flags, int64_t max_bucket,
+                    int32_t max_frequency, uint64_t *out, int64_t capacity, int64_t *n_hits, gki_stream_t stream);
+
+/* Positions form of the hit list (cfki:303-315 `hit_positions + start`, cfki:354-391 the *_from_multiple_kmers
+ * loops): entries[c] = index position of hit c, query_index[c] = its query; same order and gates as
+ * gki_lookup_hits.  The caller gathers whatever columns it needs with their own dtypes. */
+int gki_lookup_entries(gki_index_t *index, const uint64_t *queries, int64_t nq, int32_t flags, int64_t max_bucket,
+                       int32_t max_frequency, int64_t *entries, int64_t *query_index, int64_t capacity, int64_t *n_hits,
+                       gki_stream_t stream);
+/* `counter[keys]` for arbitrary keys (cfki:40): out[i] = current counter of queries[i], 0 when absent. */
+int gki_query_counts(gki_index_t *index, const uint64_t *queries, int64_t nq, uint32_t *out, gki_stream_t stream);
+
+/* ------------------------------------------------------------------ synthetic workloads + calibration
+ * (bench / test support; graph_kmer_index_b200/synthetic.py is the bit-identical host mirror) */
+int gki_synth_genome(uint8_t *codes, int64_t length, gki_stream_t stream);
+int gki_synth_flat_kmers(const uint8_t *genome_codes, int64_t n_entries, int64_t n_nodes, int32_t k, uint64_t *hashes,
+                         uint32_t *nodes, uint64_t *ref_offsets, float *af, gki_stream_t stream);
+int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t first_read, int64_t n_reads,
+                    int32_t read_len, int32_t p_hit_permille, int32_t n_permille, uint8_t *reads, gki_stream_t stream);
+/* random 8-byte gathers over a table of table_bytes (power of two not required): the measured
+ * random-access ceiling K3 is compared with.  *ms receives the kernel time. Synchronous. */
+int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms);
+int gki_calibrate_copy(int64_t bytes, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GKI_H */

@@ -1,0 +1,300 @@
+"""GPU parity of K2 (index construction) and K3 (lookup / counting / node counts) against the oracle, the
+reference's known answers and the golden fixtures generated from the unmodified reference."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_index, load_golden
+from oracle import c_oracle, numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+COLS = ("hashes_to_index", "n_kmers", "kmers", "nodes", "ref_offsets", "frequencies", "allele_frequencies")
+
+
+@pytest.fixture(scope="module")
+def gki():
+    import graph_kmer_index_b200 as g
+    return g
+
+
+def product_index(gki, idx):
+    return gki.CollisionFreeKmerIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_nodes"], idx["_ref_offsets"], idx["_kmers"],
+                                      idx["_modulo"], idx["_frequencies"], idx["_allele_frequencies"])
+
+
+def assert_index_equal(index, want, dtypes=True):
+    for key in COLS:
+        got = getattr(index, "_" + key)
+        assert np.array_equal(got, want["_" + key]), key
+        if dtypes:
+            assert got.dtype == want["_" + key].dtype, (key, got.dtype, want["_" + key].dtype)
+    assert int(index._modulo) == want["_modulo"]
+
+
+# ---- the reference's own test (tests/test_collision_free_kmer_index.py) --------------------------------
+def test_reference_collision_free_test(gki, tmp_path):
+    flat = gki.FlatKmers(np.array([1, 1, 2, 2, 4, 5, 3], dtype=np.uint64), np.array([5, 6, 7, 8, 10, 11, 100]),
+                         np.array([1, 1, 2, 3, 10, 11, 100]))
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=4)
+    assert list(index.get(1)[0]) == [5, 6]
+    assert list(index.get(1)[1]) == [1, 1]
+    index.to_file(str(tmp_path / "tmp.index"))
+    index = gki.CollisionFreeKmerIndex.from_file(str(tmp_path / "tmp.index"))
+    assert list(index.get(5)[0]) == [11]
+    assert list(index.get(3)[0]) == [100] and index.get(7)[0] is None
+    n, o, r, f = index.get_nodes_and_ref_offsets_from_multiple_kmers(np.array([1, 5]))
+    assert list(n) == [5, 6, 11] and list(o) == [1, 1, 11] and list(r) == [0, 0, 1]
+    assert 4 in index and 12 not in index
+    index.convert_to_int32()
+    kmers = np.array([1, 2, 3, 10, 10, 12, 100, 101, 102, 5], dtype=np.uint64)
+    result = index.has_kmers_parallel(kmers, n_threads=3)
+    assert np.all(result == [True, True, True, False, False, False, False, False, False, True]), result
+    g = load_golden("tiny_index")
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=4)
+    assert_index_equal(index, golden_index(g))
+
+
+@pytest.mark.parametrize("name", ["index_small", "index_sparse"])
+def test_build_golden(gki, name):
+    g = load_golden(name)
+    with_freq = bool(g["stable_frequencies"].any())
+    flat = gki.FlatKmers(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"])
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=int(g["stable_modulo"]), skip_frequencies=not with_freq)
+    assert_index_equal(index, golden_index(g))                                   # (ii) canonical (stable) order
+    for key in ("hashes_to_index", "n_kmers"):                                  # (i) tables vs the as-run reference
+        assert np.array_equal(getattr(index, "_" + key), g["asrun_" + key])
+    def canon(kmers, nodes, ref, af, fr):                                        # (iii) per-bucket multisets
+        b = kmers % np.uint64(int(g["stable_modulo"]))
+        return np.sort(np.rec.fromarrays([b, kmers, nodes, ref, af, fr]))
+    assert np.array_equal(canon(index._kmers, index._nodes, index._ref_offsets, index._allele_frequencies, index._frequencies),
+                          canon(*[g["asrun_" + k] for k in ("kmers", "nodes", "ref_offsets", "allele_frequencies", "frequencies")]))
+
+
+@pytest.mark.parametrize("n,modulo,skip", [(1, 1, False), (2, 1, False), (1000, 1, True), (5000, 2, False), (4097, 255, False),
+                                           (70000, 256, True), (70000, 257, False), (200000, 65536, False),
+                                           (200000, 1000003, False), (300001, 19999999, True), (50000, 4294967291, True)])
+def test_build_vs_oracle(gki, n, modulo, skip):
+    from graph_kmer_index_b200 import synthetic
+    if modulo > 2 ** 31:
+        pytest.skip("16 GB of host tables; covered by the device-resident build test")
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, max(n // 10, 1), 31)
+    if not skip:                                       # several ref offsets per k-mer + one heavy k-mer
+        ref = ref.copy()
+        ref[::5] += np.uint64(77)
+        hashes = hashes.copy()
+        hashes[::13] = hashes[0]
+    want = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=skip)
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(hashes, nodes, ref, af), modulo=modulo, skip_frequencies=skip)
+    assert_index_equal(index, want)
+    assert np.all(np.diff((index._kmers % np.uint64(modulo)).astype(np.int64)) >= 0)        # sortedness
+
+
+def test_build_dtypes_and_defaults(gki):
+    """payload columns keep whatever dtype the caller had (cfki:436-440 are plain fancy-indexing)"""
+    rng = np.random.default_rng(2)
+    n, modulo = 3000, 1009
+    hashes = rng.integers(0, 4 ** 31, n, dtype=np.uint64)
+    hashes[::3] = hashes[1]
+    nodes = rng.integers(0, 50, n)                      # int64 nodes
+    flat = gki.FlatKmers(hashes, nodes)                 # default ref_offsets float64 zeros, af float32 ones
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo)
+    want = no.build_index(hashes, nodes, np.zeros(n), np.ones(n, dtype=np.float32), modulo)
+    assert_index_equal(index, want)
+    for rdt, ndt in ((np.int32, np.uint16), (np.float32, np.int8), (np.uint8, np.uint32)):
+        ref = rng.integers(0, 100, n).astype(rdt)
+        nd = rng.integers(0, 100, n).astype(ndt)
+        af = rng.random(n)                              # float64 allele frequencies
+        index = gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(hashes, nd, ref, af), modulo=modulo)
+        assert_index_equal(index, no.build_index(hashes, nd, ref, af, modulo))
+    with pytest.raises(IndexError):
+        gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(np.zeros(0, np.uint64), np.zeros(0, np.uint32)), modulo=7)
+    m = gki.MinimalKmerIndex.from_flat_kmers(gki.FlatKmers(hashes, nodes.astype(np.uint32)), modulo=modulo)
+    assert m._hashes_to_index.dtype == np.int64 and np.array_equal(m._hashes_to_index, want["_hashes_to_index"])
+    assert np.array_equal(m._kmers, want["_kmers"]) and np.array_equal(m._nodes, want["_nodes"])
+
+
+def test_singletons_and_set_frequencies(gki):
+    rng = np.random.default_rng(4)
+    hashes = rng.integers(0, 500, 4000).astype(np.uint64)
+    nodes = np.arange(4000, dtype=np.uint32)
+    ref = rng.integers(0, 5, 4000).astype(np.uint64)
+    af = np.ones(4000, dtype=np.float32)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    kept = flat.get_new_without_singletons()
+    want = no.without_singletons(hashes, nodes, ref, af)
+    for a, b in zip((kept._hashes, kept._nodes, kept._ref_offsets, kept._allele_frequencies), want):
+        assert np.array_equal(a, b)
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=101, skip_singletons=True)
+    w = no.build_index(*want, 101)
+    assert np.array_equal(index._frequencies, w["_frequencies"] + 1) and np.array_equal(index._kmers, w["_kmers"])
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=101, skip_frequencies=True)
+    assert not index._frequencies.any()
+    index.set_frequencies()
+    assert np.array_equal(index._frequencies, no.build_index(hashes, nodes, ref, af, 101)["_frequencies"])
+    rc = flat.get_reverse_complement_flat_kmers(31)
+    assert np.array_equal(rc._hashes, no.revcomp_hashes(hashes, 31))
+    both = gki.FlatKmers.from_multiple_flat_kmers([flat, rc])
+    assert len(both._hashes) == 8000 and both._nodes.dtype == np.uint32 and both._ref_offsets.dtype == np.uint64
+
+
+@pytest.mark.parametrize("name", ["index_small", "index_sparse"])
+def test_lookup_and_counts_golden(gki, name):
+    g = load_golden(name)
+    idx = golden_index(g)
+    index = product_index(gki, idx)
+    q = g["queries"]
+    nodes, offs, ns = [], [], []
+    for kmer in q[:200]:
+        r = index.get(kmer, max_hits=10 ** 9)
+        ns.append(0 if r[0] is None else len(r[0]))
+        if r[0] is not None:
+            nodes.extend(r[0]); offs.extend(r[1])
+    assert ns == list(g["get_n"]) and nodes == list(g["get_nodes"]) and offs == list(g["get_ref_offsets"])
+    counter = gki.CounterKmerIndex.from_kmer_index(index)
+    counter.count_kmers(q)
+    counter.count_kmers(q[:100])
+    got = counter.get_node_counts()
+    assert got.dtype == np.float64 and np.array_equal(got, g["node_counts_min0"])
+    assert np.array_equal(counter.get_node_counts(int(g["n_nodes"]) + 17), g["node_counts_min_big"])
+    assert np.array_equal(counter.counter[counter.kmers], c_oracle.count_kmers(idx, np.concatenate([q, q[:100]])))
+    counter.count_kmers(q[:100], update_counter=False)                       # cfki:34-35: reset first
+    assert np.array_equal(counter.get_node_counts(), no.node_counts(idx, q[:100]))
+    if "cython_get" in g.files:
+        assert np.array_equal(gki.CythonKmerIndex(index).get(q), g["cython_get"])
+    assert np.array_equal(index.device_index().lookup_hits(q, False, None, None), no.lookup_hits(idx, q, False, None, None))
+    assert np.array_equal(index.has_kmers(q), no.has_kmers(idx, q))
+    n_nodes = int(g["n_nodes"])
+    assert np.array_equal(index.map_kmers(q, n_nodes), no.map_kmers(idx, q, n_nodes))
+    # reads -> node counts, fused
+    counter.reset()
+    counter.count_reads(g["reads"], int(g["k"]))
+    assert np.array_equal(counter.get_node_counts(n_nodes), g["read_node_counts"])
+
+
+@pytest.mark.parametrize("flags", ["auto", "bitmap", "nobitmap"])
+@pytest.mark.parametrize("n,modulo,n_reads,L,k", [(40000, 200003, 3000, 150, 31), (40000, 4099, 1500, 150, 31), (5000, 7, 300, 100, 15),
+                                                   (40000, 200003, 777, 64, 31)])
+def test_count_reads_vs_oracle(gki, flags, n, modulo, n_reads, L, k):
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 997, k)
+    idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=400, n_permille=10)
+    f = {"auto": 0, "bitmap": _lib.GKI_INDEX_FORCE_BITMAP, "nobitmap": _lib.GKI_INDEX_NO_BITMAP}[flags]
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo, flags=f)
+    assert dev.info()["has_bitmap"] == {"auto": dev.info()["has_bitmap"], "bitmap": True, "nobitmap": False}[flags]
+    want = c_oracle.read_node_counts(idx, reads, k, 1000)
+    assert want.sum() > 0
+    dev.count_reads(reads, k)                                   # host buffer: chunked H2D inside the call
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dreads = torch.from_numpy(reads).cuda()
+    dev.count_reads(dreads, k)                                  # device-resident
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dev.count_reads(dreads, k, both_strands=False)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads, k, 1000, both_strands=False))
+    # unfused: hashes -> count_kmers equals the fused path; linearity over two halves
+    from graph_kmer_index_b200.read_kmers import hash_read_matrix
+    fwd, rc = hash_read_matrix(reads, k)
+    dev.reset_counts()
+    half = n_reads // 2
+    dev.count_kmers(np.concatenate([fwd[:half].ravel(), rc[:half].ravel()]))
+    first = dev.node_counts(1000)
+    dev.count_kmers(torch.from_numpy(np.concatenate([fwd[half:].ravel(), rc[half:].ravel()]).view(np.int64)).cuda())
+    assert np.array_equal(dev.node_counts(1000), want)
+    assert np.array_equal(want - first, c_oracle.read_node_counts(idx, reads[half:], k, 1000))
+    # strided host rows
+    padded = np.full((n_reads, L + 10), ord("A"), dtype=np.uint8)
+    padded[:, :L] = reads
+    dev.reset_counts()
+    dev.count_reads(padded[:, :L], k)
+    assert np.array_equal(dev.node_counts(1000), want)
+    assert np.array_equal(dev.entry_counts(), c_oracle.count_reads(idx, reads, k))
+    dev.close()
+
+
+def test_uint16_wrap_flag_and_hot_kmer(gki):
+    """a k-mer hit > 65535 times: exact by default, modulo 2^16 with the reference-Counter compat flag (cfki:27)"""
+    kmers = np.array([5, 5, 9], dtype=np.uint64)
+    nodes = np.array([1, 2, 3], dtype=np.uint32)
+    idx = no.build_index(kmers, nodes, np.zeros(3, np.uint64), np.ones(3, np.float32), 11, skip_frequencies=True)
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], 11)
+    dev.count_kmers(np.full(70000, 5, dtype=np.uint64))
+    dev.count_kmers(np.array([9, 9, 4, 16], dtype=np.uint64))
+    assert list(dev.node_counts()) == [0, 70000, 70000, 2]
+    assert list(dev.node_counts(wrap_uint16=True)) == [0, 70000 - 65536, 70000 - 65536, 2]
+    assert list(dev.node_counts(6)) == [0, 70000, 70000, 2, 0, 0]
+
+
+def test_device_resident_build_and_count_full_config1(gki):
+    """BASELINE config 1 (1M entries, 100k nodes, 100k x 150bp reads) entirely on the device; the oracle checks it."""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    n, n_nodes, modulo, k, n_reads, L = 1_000_000, 100_000, 19_999_999, 31, 100_000, 150
+    glen = synthetic.genome_length(n, k)
+    dev = torch.device("cuda")
+    genome = torch.empty(glen, dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_genome", _lib.ptr(genome), glen, None)
+    hashes = torch.empty(n, dtype=torch.int64, device=dev)
+    nodes = torch.empty(n, dtype=torch.int32, device=dev)
+    ref = torch.empty(n, dtype=torch.int64, device=dev)
+    af = torch.empty(n, dtype=torch.float32, device=dev)
+    _lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), None)
+    reads = torch.empty((n_reads, L), dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_reads", _lib.ptr(genome), glen, 0, n_reads, L, 100, 0, _lib.ptr(reads), None)
+    torch.cuda.synchronize()
+    # device generators == host mirror
+    h_hashes, h_nodes, h_ref, h_af = synthetic.flat_kmers(n, n_nodes, k)
+    assert np.array_equal(hashes.cpu().numpy().view(np.uint64), h_hashes) and np.array_equal(nodes.cpu().numpy().view(np.uint32), h_nodes)
+    assert np.array_equal(ref.cpu().numpy().view(np.uint64), h_ref) and np.array_equal(af.cpu().numpy(), h_af)
+    h_reads = synthetic.reads(n_reads, L, n, k, 100)
+    assert np.array_equal(reads.cpu().numpy(), h_reads)
+    # build on the device
+    h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+    nk = torch.empty(modulo, dtype=torch.int32, device=dev)
+    o_k, o_r = torch.empty_like(hashes), torch.empty_like(ref)
+    o_n, o_a = torch.empty_like(nodes), torch.empty_like(af)
+    o_f = torch.empty(n, dtype=torch.int16, device=dev)
+    _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), n, modulo, 0, _lib.ptr(h2i), _lib.ptr(nk),
+              _lib.ptr(o_k), _lib.ptr(o_n), _lib.ptr(o_r), _lib.ptr(o_a), _lib.ptr(o_f), None, None)
+    torch.cuda.synchronize()
+    want = c_oracle.build_index(h_hashes, h_nodes, h_ref, h_af, modulo)
+    assert np.array_equal(h2i.cpu().numpy(), want["_hashes_to_index"]) and np.array_equal(nk.cpu().numpy().view(np.uint32), want["_n_kmers"])
+    assert np.array_equal(o_k.cpu().numpy().view(np.uint64), want["_kmers"]) and np.array_equal(o_n.cpu().numpy().view(np.uint32), want["_nodes"])
+    assert np.array_equal(o_r.cpu().numpy().view(np.uint64), want["_ref_offsets"]) and np.array_equal(o_a.cpu().numpy(), want["_allele_frequencies"])
+    assert np.array_equal(o_f.cpu().numpy().view(np.uint16), want["_frequencies"])
+    # count on the device
+    index = gki.DeviceIndex(h2i, nk, o_k, o_n, modulo)
+    index.count_reads(reads, k)
+    got = index.node_counts(n_nodes)
+    assert np.array_equal(got, c_oracle.read_node_counts(want, h_reads, k, n_nodes))
+    # checksum-of-checksums: total node count == sum over entries of their k-mer's hit count
+    assert got.sum() == float(index.entry_counts().astype(np.int64).sum())
+
+
+def test_large_modulo_device_build(gki):
+    """default-sized tables (modulo 452930477) stay on the device: tables checked through their invariants"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    n, modulo, k = 2_000_000, 452930477, 31
+    h_hashes, h_nodes, _, _ = synthetic.flat_kmers(n, 1000, k)
+    dev = torch.device("cuda")
+    hashes = torch.from_numpy(h_hashes.view(np.int64)).to(dev)
+    nodes = torch.from_numpy(h_nodes.view(np.int32)).to(dev)
+    h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+    nk = torch.empty(modulo, dtype=torch.int32, device=dev)
+    o_k, o_n = torch.empty_like(hashes), torch.empty_like(nodes)
+    _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, 1, _lib.ptr(h2i), _lib.ptr(nk),
+              _lib.ptr(o_k), _lib.ptr(o_n), None, None, None, None, None)
+    torch.cuda.synchronize()
+    assert int(nk.sum()) == n
+    b = (h_hashes % np.uint64(modulo)).astype(np.int64)
+    order = np.argsort(b, kind="stable")
+    assert np.array_equal(o_k.cpu().numpy().view(np.uint64), h_hashes[order]) and np.array_equal(o_n.cpu().numpy().view(np.uint32), h_nodes[order])
+    ub, first, cnt = np.unique(b[order], return_index=True, return_counts=True)
+    sel = torch.from_numpy(ub).to(dev)
+    assert np.array_equal(h2i[sel].cpu().numpy(), first) and np.array_equal(nk[sel].cpu().numpy(), cnt)
+    assert int((nk != 0).sum()) == len(ub) and int((h2i != 0).sum()) <= len(ub)

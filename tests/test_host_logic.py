@@ -1,0 +1,87 @@
+"""CPU tests of the host-side logic: synthetic generators, sharding, the world_size-2 all-reduce path (gloo)."""
+import os
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+
+from conftest import ROOT
+from graph_kmer_index_b200 import distributed, synthetic
+from oracle import c_oracle, numpy_oracle as no
+
+
+def test_synthetic_is_deterministic_and_shardable():
+    h1 = synthetic.flat_kmers(1001, 50, 31)
+    h2 = synthetic.flat_kmers(1001, 50, 31)
+    for a, b in zip(h1, h2):
+        assert np.array_equal(a, b)
+    assert h1[0].dtype == np.uint64 and h1[1].dtype == np.uint32 and h1[2].dtype == np.uint64 and h1[3].dtype == np.float32
+    # every unique k-mer appears twice (once for the odd tail), with the same ref offset
+    u, c = np.unique(h1[2], return_counts=True)
+    assert len(u) == 501 and set(c) == {1, 2}
+    r = synthetic.reads(64, 150, 1001, 31, p_hit_permille=500)
+    parts = np.concatenate([synthetic.reads(20, 150, 1001, 31, 500, first_read=0),
+                            synthetic.reads(44, 150, 1001, 31, 500, first_read=20)])
+    assert np.array_equal(r, parts)
+    assert set(np.unique(r)) <= set(b"ACGT")
+    assert ord("N") in synthetic.reads(64, 150, 1001, 31, 500, n_permille=100)
+
+
+def test_synthetic_reads_hit_the_index():
+    n = 4000
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 100, 31)
+    idx = no.build_index(hashes, nodes, ref, af, 10007, skip_frequencies=True)
+    r = synthetic.reads(200, 150, n, 31, p_hit_permille=1000)
+    fwd, rc = no.hash_reads(r, 31)
+    hit = no.has_kmers(idx, np.concatenate([fwd.ravel(), rc.ravel()]))
+    assert 0.45 < hit.mean() < 0.55          # one strand of every read comes from the indexed sequence
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000, 12345):
+        for w in (1, 2, 3, 8):
+            b = [distributed.shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(e - s for s, e in b) - min(e - s for s, e in b) <= 1
+
+
+WORKER = textwrap.dedent("""
+    import os, sys
+    import numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %r)
+    from graph_kmer_index_b200 import distributed, synthetic
+    from oracle import c_oracle, numpy_oracle as no
+    rank, world = distributed.init_process_group("gloo")
+    n = 3000
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 200, 31)
+    idx = no.build_index(hashes, nodes, ref, af, 5003, skip_frequencies=True)
+    reads = synthetic.reads(400, 100, n, 31, p_hit_permille=600)
+    lo, hi = distributed.shard_bounds(len(reads), rank, world)
+    local = c_oracle.read_node_counts(idx, reads[lo:hi], 31, 200)       # checker stands in for the GPU count
+    t = torch.from_numpy(local.copy())
+    distributed.allreduce_node_counts(t)
+    whole = c_oracle.read_node_counts(idx, reads, 31, 200)
+    assert np.array_equal(t.numpy(), whole), rank
+    assert whole.sum() > 0
+    dist.barrier()
+    if rank == 0:
+        print("OK", world, int(whole.sum()))
+""")
+
+
+def test_world_size_2_allreduce_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-3000:]
+    assert "OK 2" in out.stdout
