@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- read k-mers/s through get_node_counts (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch: reset counters -> fused hash+probe+count of the rank's read
+batch (gki_count_reads) -> get_node_counts (gki_node_counts) [-> NCCL all-reduce of the node-count vector at N>1].
+Workload at N=1: BASELINE configs[1] (chr20-scale: 60M k=31 index entries, modulo 452930477, 10M x 150 bp reads,
+both strands -> 2.4 G read k-mers per step).  At N>1 every rank holds the replicated index and its own 10M-read
+shard (weak scaling) -- configs[2]'s sharding at the per-GPU batch of configs[1].
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: entries, nodes, modulo, reads per GPU, read length, k, p_hit (permille of reads drawn from the indexed sequence)
+    "c1": dict(entries=1_000_000, nodes=100_000, modulo=19_999_999, reads=100_000, read_len=150, k=31, p_hit=100),
+    "c2": dict(entries=60_000_000, nodes=6_000_000, modulo=452_930_477, reads=10_000_000, read_len=150, k=31, p_hit=100),
+    "c3": dict(entries=1_000_000_000, nodes=50_000_000, modulo=452_930_477, reads=37_500_000, read_len=150, k=31, p_hit=100),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--entries", type=int)
+    ap.add_argument("--reads", type=int)
+    ap.add_argument("--p-hit", type=int, dest="p_hit")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline time box")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(args):
+    cfg = dict(CONFIGS[args.config])
+    if args.entries:
+        cfg["entries"] = args.entries
+        cfg["nodes"] = max(args.entries // 10, 1)
+    if args.reads:
+        cfg["reads"] = args.reads
+    if args.p_hit is not None:
+        cfg["p_hit"] = args.p_hit
+    return cfg
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_count_rate(idx, reads, k, seconds, chunk=50_000):
+    """Oracle C port (oracle/gki_oracle.c, OpenMP over all host threads) on a time-boxed sample of the same reads.
+    Returns (read k-mers/s, k-mers processed, seconds, node counts of the sample's entry counters)."""
+    from oracle import c_oracle
+    prepared = c_oracle._index_args(idx)
+    ec = np.zeros(len(prepared[2]), dtype=np.uint32)
+    nk = (reads.shape[1] - k + 1) * 2
+    c_oracle.count_reads(idx, reads[:1000], k, True, np.zeros_like(ec), prepared)      # warm
+    done, t0 = 0, time.perf_counter()
+    while done < len(reads) and time.perf_counter() - t0 < seconds:
+        c_oracle.count_reads(idx, reads[done:done + chunk], k, True, ec, prepared)
+        done += min(chunk, len(reads) - done)
+    dt = time.perf_counter() - t0
+    return done * nk / dt, done * nk, dt, done
+
+
+def run_reference(args, cfg, rank):
+    """--impl reference: the reference's CPU path for the metric (oracle port; the reference itself is pure Python
+    whose counting step lives in an absent third-party package) on the host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    from graph_kmer_index_b200 import synthetic
+    from oracle import c_oracle
+    n, k, L = cfg["entries"], cfg["k"], cfg["read_len"]
+    codes = synthetic.genome_codes(synthetic.genome_length(n, k))
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, cfg["nodes"], k, codes=codes)
+    idx = c_oracle.build_index(hashes, nodes, ref, af, cfg["modulo"], skip_frequencies=True)
+    del hashes, ref, af
+    sample_reads = min(cfg["reads"], 200_000)
+    reads = synthetic.reads(sample_reads, L, n, k, cfg["p_hit"], codes=codes)
+    prepared = c_oracle._index_args(idx)
+    nk = (L - k + 1) * 2
+    ec = np.zeros(n, dtype=np.uint32)
+    times = []
+    for step in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        ec[:] = 0
+        c_oracle.count_reads(idx, reads, k, True, ec, prepared)
+        c_oracle.node_counts_from_entry_counts(idx, ec, cfg["nodes"])
+        if step >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    value = sample_reads * nk * len(times) / total
+    threads = c_oracle.num_threads()
+    line = {"impl": "reference", "metric": "read_kmers_per_s_through_get_node_counts", "value": value, "unit": "kmers/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": bench_config(cfg, args, 1, sample_reads=sample_reads),
+            "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": threads, "kind": "port",
+                             "sample": "%d of %d reads per step, oracle/gki_oracle.c with OpenMP over %d host threads" % (sample_reads, cfg["reads"], threads)},
+            "e2e": {"value": value, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def bench_config(cfg, args, world, sample_reads=None):
+    c = {"workload": "%s: synthetic variant-graph index, %d k=%d entries (%d distinct k-mers x 2 nodes), modulo %d, %d nodes; "
+                     "%d x %d bp reads per GPU, both strands, %.0f%% of reads drawn from the indexed sequence"
+                     % (args.config, cfg["entries"], cfg["k"], (cfg["entries"] + 1) // 2, cfg["modulo"], cfg["nodes"], cfg["reads"],
+                        cfg["read_len"], cfg["p_hit"] / 10.0),
+         "index_entries": cfg["entries"], "modulo": cfg["modulo"], "n_nodes": cfg["nodes"], "reads_per_gpu": cfg["reads"],
+         "read_len": cfg["read_len"], "k": cfg["k"], "kmers_per_step_per_gpu": cfg["reads"] * (cfg["read_len"] - cfg["k"] + 1) * 2,
+         "parallelism": "reads sharded x%d, index replicated, 1 all-reduce of node counts" % world if world > 1 else "single GPU",
+         "l2": "inputs larger than L2 (reads %.2f GB, bucket cells %.2f GB per step)" % (cfg["reads"] * cfg["read_len"] / 1e9, cfg["modulo"] * 8 / 1e9)}
+    if sample_reads is not None:
+        c["reads_per_step_sampled"] = sample_reads
+    return c
+
+
+def main():
+    args = parse_args()
+    cfg = workload(args)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from graph_kmer_index_b200 import DeviceIndex, _lib, distributed, synthetic
+
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        distributed.init_process_group("nccl")
+    dev = torch.device("cuda", local_rank)
+    n, k, L, R, modulo, n_nodes = cfg["entries"], cfg["k"], cfg["read_len"], cfg["reads"], cfg["modulo"], cfg["nodes"]
+    nk_per_read = (L - k + 1) * 2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # ---------------- setup (untimed): synthetic FlatKmers + reads on the device, index built by K2 ----------------
+    glen = synthetic.genome_length(n, k)
+    genome = torch.empty(glen, dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_genome", _lib.ptr(genome), glen, stream)
+    hashes = torch.empty(n, dtype=torch.int64, device=dev)
+    nodes = torch.empty(n, dtype=torch.int32, device=dev)
+    _lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(hashes), _lib.ptr(nodes), None, None, stream)
+    h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+    nkm = torch.empty(modulo, dtype=torch.int32, device=dev)
+    s_kmers, s_nodes = torch.empty_like(hashes), torch.empty_like(nodes)
+    build_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    build_ev[0].record()
+    _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, _lib.GKI_BUILD_SKIP_FREQUENCIES,
+              _lib.ptr(h2i), _lib.ptr(nkm), _lib.ptr(s_kmers), _lib.ptr(s_nodes), None, None, None, None, stream)
+    build_ev[1].record()
+    torch.cuda.synchronize()
+    build_ms = build_ev[0].elapsed_time(build_ev[1])
+    index = DeviceIndex(h2i, nkm, s_kmers, s_nodes, modulo)
+    info = index.info()
+    del hashes, nodes
+    reads = torch.empty((R, L), dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_reads", _lib.ptr(genome), glen, rank * R, R, L, cfg["p_hit"], 0, _lib.ptr(reads), stream)
+    counts = torch.zeros(max(n_nodes, index.max_node + 1), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        index.reset_counts()
+        index.count_reads(reads, k, True)
+        index.node_counts(n_nodes, out=counts)
+        if world > 1:
+            distributed.allreduce_node_counts(counts)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev0.record()
+    for i in range(args.steps):
+        index.reset_counts()
+        kern_ev[i][0].record()
+        index.count_reads(reads, k, True)
+        kern_ev[i][1].record()
+        index.node_counts(n_nodes, out=counts)
+        if world > 1:
+            distributed.allreduce_node_counts(counts)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = ev0.elapsed_time(ev1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    total_kmers_per_step = R * nk_per_read * world
+    value = total_kmers_per_step * args.steps / (elapsed_ms / 1e3)
+
+    # hit statistics of the last step (for the algorithmic-bytes model) -- untimed
+    total_counts = float(counts.sum().item())
+    entry_hits = None
+    if rank == 0:
+        ec = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.call("gki_entry_counts", index.handle, _lib.ptr(ec), stream)
+        torch.cuda.synchronize()
+        # every distinct k-mer has its counter replicated on each of its entries; hits = sum over distinct k-mers
+        entry_hits = float(ec.to(torch.float64).sum().item())
+        del ec
+
+    # ---------------- e2e: host (pinned) reads through the same C-ABI call, node counts read back to the host -------
+    e2e = None
+    if not args.no_e2e:
+        host_reads = torch.empty((R, L), dtype=torch.uint8, pin_memory=True)
+        host_reads.copy_(reads)
+        host_counts = torch.empty(counts.shape[0], dtype=torch.float64, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def e2e_step():
+            index.reset_counts()
+            index.count_reads(host_reads, k, True)                 # H2D chunks overlap the count kernels inside the call
+            index.node_counts(n_nodes, out=counts)
+            if world > 1:
+                distributed.allreduce_node_counts(counts)
+            host_counts.copy_(counts, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_steps = max(1, min(args.steps, 5))
+        for _ in range(min(args.warmup, 2)):
+            e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        barrier()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_kmers_per_step * e2e_steps / (float(t.item()) / 1e3), "unit": "kmers/s",
+               "h2d_bytes_per_step": int(R * L), "d2h_bytes_per_step": int(counts.shape[0] * 8), "steps": e2e_steps,
+               "host_memory": "pinned", "note": "per GPU bytes; reads are ASCII, 1 byte per base"}
+        assert float(host_counts.sum().item()) == (total_counts if world == 1 else float(counts.sum().item()))
+        del host_reads
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------- roofline of the dominant kernel (count_reads_kernel) ----------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    kmers_per_launch = R * nk_per_read
+    # counts summed over nodes counts every hit once per entry of the k-mer (2 entries per distinct k-mer)
+    h = (total_counts / world / 2.0) / kmers_per_launch if world == 1 else None
+    h = (entry_hits / 2.0) / kmers_per_launch
+    occ = info["nonempty_buckets"] / modulo
+    sectors = (1 - h) * (1 - occ) * 1 + (1 - h) * occ * 3 + h * 5          # SURVEY.md section 8(d) K3 model
+    bytes_per_kmer = L / nk_per_read + 32.0 * sectors
+    achieved = kmers_per_launch * bytes_per_kmer / (kernel_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("count_reads_kernel_dram_bytes_per_launch_%s" % args.config)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "count_reads_kernel<bitmap=%s,both=true>" % str(info["has_bitmap"]).lower(),
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
+                "algorithmic_bytes_per_kmer": bytes_per_kmer, "sectors_per_kmer_model": sectors, "hit_fraction": h,
+                "bucket_occupancy": occ, "kmers_per_s_kernel_only": kmers_per_launch / (kernel_ms / 1e3),
+                "note": "random 32-B sector model of SURVEY 8(d): 1 sector empty bucket / 3 non-empty miss / 5 hit, + ASCII read bytes"}
+
+    # ---------------- CPU baseline (oracle port on the host cores, bounded sample) ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import c_oracle
+        idx = {"_hashes_to_index": h2i.cpu().numpy(), "_n_kmers": nkm.cpu().numpy().view(np.uint32),
+               "_kmers": s_kmers.cpu().numpy().view(np.uint64), "_nodes": s_nodes.cpu().numpy().view(np.uint32), "_modulo": modulo}
+        sample = reads[:min(R, 4_000_000)].cpu().numpy()
+        rate, kmers_done, secs, reads_done = cpu_count_rate(idx, sample, k, args.cpu_seconds)
+        cpu = {"value": rate, "unit": "kmers/s", "cores": c_oracle.num_threads(), "kind": "port",
+               "sample": "first %d reads (%d k-mers) of the step's batch in %.1f s; oracle/gki_oracle.c, OpenMP, host has %d threads"
+                         % (reads_done, kmers_done, secs, cpu_threads())}
+
+    line = {"metric": "read_kmers_per_s_through_get_node_counts", "value": value, "unit": "kmers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": bench_config(cfg, args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "index_build": {"entries_per_s": n / (build_ms / 1e3), "ms": build_ms, "entries": n,
+                            "compulsory_gbs": (50.0 * n + 8.0 * modulo) / (build_ms / 1e3) / 1e9,
+                            "note": "gki_index_build (skip_frequencies), device-resident, single untimed-warm-up-free run"},
+            "index": {"device_bytes": info["device_bytes"], "has_bitmap": info["has_bitmap"], "nonempty_buckets": info["nonempty_buckets"]}}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,7 +69,7 @@ _SIGNATURES = {
     "gki_index_create": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_i32, ctypes.POINTER(c_vp), c_vp],
     "gki_index_destroy": [c_vp],
     "gki_index_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_u64), ctypes.POINTER(c_i64),
-                       ctypes.POINTER(c_i64), ctypes.POINTER(c_i32)],
+                       ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)],
     "gki_reset_counts": [c_vp, c_vp],
     "gki_count_kmers": [c_vp, c_vp, c_i64, c_vp],
     "gki_count_reads": [c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp],

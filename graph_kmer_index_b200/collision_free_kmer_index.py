@@ -58,9 +58,11 @@ class DeviceIndex:
                    _c(index._nodes, np.uint32), int(index._modulo), ref, freq, af, flags)
 
     def info(self):
-        n, mod, mx, nbytes, bm = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32()
-        _lib.call("gki_index_info", self.handle, ctypes.byref(n), ctypes.byref(mod), ctypes.byref(mx), ctypes.byref(nbytes), ctypes.byref(bm))
-        return dict(n=n.value, modulo=mod.value, max_node=mx.value, device_bytes=nbytes.value, has_bitmap=bool(bm.value))
+        n, mod, mx, nbytes, bm, ne = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int64()
+        _lib.call("gki_index_info", self.handle, ctypes.byref(n), ctypes.byref(mod), ctypes.byref(mx), ctypes.byref(nbytes), ctypes.byref(bm),
+                  ctypes.byref(ne))
+        return dict(n=n.value, modulo=mod.value, max_node=mx.value, device_bytes=nbytes.value, has_bitmap=bool(bm.value),
+                    nonempty_buckets=ne.value)
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:

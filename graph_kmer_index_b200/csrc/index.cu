@@ -15,17 +15,49 @@
 //                a hit costs exactly one RED.ADD.  get_node_counts resolves every entry to its representative.
 // The probe is bound by random 32-byte sector accesses (L2 for the bitmap, HBM for cells / chain / counter),
 // not by streaming bandwidth; lanes keep NQ independent probes in flight to cover the latency.
+#include <stdlib.h>
 #include "reads_tile.cuh"
 
 namespace gki {
 
 struct IndexView {
     const uint2 *cells;
-    const uint32_t *bitmap;
+    const uint32_t *bitmap;   // bit g set <=> some bucket in [g << bitmap_shift, (g+1) << bitmap_shift) is non-empty
     const uint64_t *kmers;
     uint32_t *counts;
     FastMod fm;
+    uint32_t bitmap_shift;
 };
+
+// L2 eviction-priority hints: the bitmap is the only structure with reuse, everything else streams through.
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+template <bool HINT> __device__ __forceinline__ uint32_t ld_bitmap(const uint32_t *p, uint64_t pol) {
+    if (!HINT) return __ldg(p);
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool HINT> __device__ __forceinline__ uint2 ld_cell(const uint2 *p, uint64_t pol) {
+    if (!HINT) return __ldg(p);
+    uint2 v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+template <bool HINT> __device__ __forceinline__ uint64_t ld_kmer(const uint64_t *p, uint64_t pol) {
+    if (!HINT) return __ldg(p);
+    uint64_t v;
+    asm("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+    return v;
+}
 
 }  // namespace gki
 
@@ -36,6 +68,9 @@ struct gki_index {
     gki::FastMod fm{};
     uint2 *cells = nullptr;
     uint32_t *bitmap = nullptr;
+    uint32_t bitmap_shift = 0;
+    size_t bitmap_bytes = 0;
+    int l2_mode = 1;          // bit 0: per-load L2 eviction hints, bit 1: persisting access-policy window on the bitmap
     uint64_t *kmers = nullptr;
     uint32_t *nodes = nullptr;
     uint32_t *counts = nullptr;
@@ -51,7 +86,7 @@ struct gki_index {
     void *stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
 
-    gki::IndexView view() const { return gki::IndexView{cells, bitmap, kmers, counts, fm}; }
+    gki::IndexView view() const { return gki::IndexView{cells, bitmap, kmers, counts, fm, bitmap_shift}; }
 };
 
 namespace gki {
@@ -84,6 +119,23 @@ __global__ void make_cells_kernel(const int32_t *__restrict__ h2i, const uint32_
     if (lane == 0 && local) atomicAdd(nonempty, local);
 }
 
+// coarse[g] = OR of the 2^shift fine bits [g << shift, (g+1) << shift)
+__global__ void coarsen_bitmap_kernel(const uint32_t *__restrict__ fine, uint64_t fine_words, uint32_t shift,
+                                      uint32_t *__restrict__ coarse, uint64_t coarse_words) {
+    const uint32_t span = 1u << shift;
+    const uint32_t ones = span >= 32 ? 0xffffffffu : ((1u << span) - 1u);
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < coarse_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t out = 0;
+        for (uint32_t i = 0; i < 32; i++) {
+            uint64_t first_bit = (w * 32 + i) << shift;
+            uint64_t word = first_bit >> 5;
+            uint32_t v = word < fine_words ? __ldg(fine + word) : 0u;
+            out |= (uint32_t)(((v >> (first_bit & 31)) & ones) != 0u) << i;
+        }
+        coarse[w] = out;
+    }
+}
+
 __global__ void max_u32_kernel(const uint32_t *__restrict__ v, int64_t n, unsigned int *__restrict__ out) {
     unsigned int m = 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -96,28 +148,40 @@ __global__ void max_u32_kernel(const uint32_t *__restrict__ v, int64_t n, unsign
 // ------------------------------------------------------------------ probe
 // NQ independent probes per lane, staged so that the loads of one stage are all issued before the first
 // use: bitmap words (L2) -> cells (HBM) -> first chain k-mer (HBM) -> rest of the chain (rare).
-template <bool BITMAP>
-__device__ __forceinline__ void probe_count_batch(const IndexView &ix, const uint64_t (&q)[NQ], uint32_t live) {
+struct Policies {
+    uint64_t last, first;
+};
+template <bool HINT> __device__ __forceinline__ Policies make_policies() {
+    Policies p{0, 0};
+    if (HINT) {
+        p.last = policy_evict_last();
+        p.first = policy_evict_first();
+    }
+    return p;
+}
+
+template <bool BITMAP, bool HINT>
+__device__ __forceinline__ void probe_count_batch(const IndexView &ix, const Policies &pol, const uint64_t (&q)[NQ], uint32_t live) {
     uint32_t b[NQ];
 #pragma unroll
     for (int j = 0; j < NQ; j++) b[j] = fastmod(q[j], ix.fm);
     if (BITMAP) {
         uint32_t w[NQ];
 #pragma unroll
-        for (int j = 0; j < NQ; j++) w[j] = ((live >> j) & 1u) ? __ldg(ix.bitmap + (b[j] >> 5)) : 0u;
+        for (int j = 0; j < NQ; j++) w[j] = ((live >> j) & 1u) ? ld_bitmap<HINT>(ix.bitmap + (b[j] >> (5 + ix.bitmap_shift)), pol.last) : 0u;
 #pragma unroll
-        for (int j = 0; j < NQ; j++) live &= ~((((w[j] >> (b[j] & 31)) & 1u) ^ 1u) << j);
+        for (int j = 0; j < NQ; j++) live &= ~((((w[j] >> ((b[j] >> ix.bitmap_shift) & 31)) & 1u) ^ 1u) << j);
         if (!live) return;
     }
     uint2 cell[NQ];
 #pragma unroll
-    for (int j = 0; j < NQ; j++) cell[j] = ((live >> j) & 1u) ? __ldg(ix.cells + b[j]) : make_uint2(0u, 0u);
+    for (int j = 0; j < NQ; j++) cell[j] = ((live >> j) & 1u) ? ld_cell<HINT>(ix.cells + b[j], pol.first) : make_uint2(0u, 0u);
 #pragma unroll
     for (int j = 0; j < NQ; j++) live &= ~((uint32_t)(cell[j].y == 0u) << j);
     if (!live) return;
     uint64_t first[NQ];
 #pragma unroll
-    for (int j = 0; j < NQ; j++) first[j] = ((live >> j) & 1u) ? __ldg(ix.kmers + cell[j].x) : 0ull;
+    for (int j = 0; j < NQ; j++) first[j] = ((live >> j) & 1u) ? ld_kmer<HINT>(ix.kmers + cell[j].x, pol.first) : 0ull;
 #pragma unroll
     for (int j = 0; j < NQ; j++) {
         if (!((live >> j) & 1u)) continue;
@@ -126,7 +190,7 @@ __device__ __forceinline__ void probe_count_batch(const IndexView &ix, const uin
             continue;
         }
         for (uint32_t e = 1; e < cell[j].y; e++) {
-            if (__ldg(ix.kmers + cell[j].x + e) == q[j]) {
+            if (ld_kmer<HINT>(ix.kmers + cell[j].x + e, pol.first) == q[j]) {
                 atomicAdd(ix.counts + cell[j].x + e, 1u);
                 break;
             }
@@ -134,9 +198,10 @@ __device__ __forceinline__ void probe_count_batch(const IndexView &ix, const uin
     }
 }
 
-template <bool BITMAP>
+template <bool BITMAP, bool HINT>
 __global__ void __launch_bounds__(COUNT_THREADS) count_kmers_kernel(IndexView ix, const uint64_t *__restrict__ queries,
                                                                     int64_t nq) {
+    const Policies pol = make_policies<HINT>();
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
     const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     for (int64_t i0 = g; i0 < nq; i0 += T * NQ) {
@@ -149,15 +214,16 @@ __global__ void __launch_bounds__(COUNT_THREADS) count_kmers_kernel(IndexView ix
             q[j] = ok ? __ldg(queries + idx) : 0ull;
             live |= (uint32_t)ok << j;
         }
-        probe_count_batch<BITMAP>(ix, q, live);
+        probe_count_batch<BITMAP, HINT>(ix, pol, q, live);
     }
 }
 
 // Fused K1 -> K3: tiles of reads are staged + packed (reads_tile.cuh); a warp owns a read, each lane takes
 // NQ/2 windows and probes their forward and reverse-complement hashes.
-template <bool BITMAP, bool BOTH>
+template <bool BITMAP, bool BOTH, bool HINT>
 __global__ void __launch_bounds__(COUNT_THREADS) count_reads_kernel(IndexView ix, ReadBatch b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const Policies pol = make_policies<HINT>();
     const uint64_t mask = kmer_mask(b.k);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     constexpr int WPL = BOTH ? NQ / 2 : NQ;   // windows per lane per batch
@@ -185,7 +251,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) count_reads_kernel(IndexView ix
                         live |= (uint32_t)ok << u;
                     }
                 }
-                probe_count_batch<BITMAP>(ix, q, live);
+                probe_count_batch<BITMAP, HINT>(ix, pol, q, live);
             }
         }
     });
@@ -354,25 +420,49 @@ static int ensure_staging(gki_index *ix, size_t bytes) {
 static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cudaStream_t s) {
     if (nq <= 0) return GKI_OK;
     int grid = grid_for(nq, COUNT_THREADS * NQ, device_info().sms * 8);
-    if (ix->bitmap) count_kmers_kernel<true><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
-    else count_kmers_kernel<false><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
+    const bool hint = ix->l2_mode & 1;
+    if (ix->bitmap) {
+        if (hint) count_kmers_kernel<true, true><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
+        else count_kmers_kernel<true, false><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
+    } else {
+        if (hint) count_kmers_kernel<false, true><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
+        else count_kmers_kernel<false, false><<<grid, COUNT_THREADS, 0, s>>>(ix->view(), dq, nq);
+    }
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
 
-template <bool BITMAP, bool BOTH> static int launch_count_reads_t(gki_index *ix, const ReadBatch &b, size_t smem, cudaStream_t s) {
+template <bool BITMAP, bool BOTH, bool HINT> static int launch_count_reads_t(gki_index *ix, const ReadBatch &b, size_t smem, cudaStream_t s) {
     static bool attr_set = false;
     if (!attr_set) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BITMAP, BOTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BITMAP, BOTH, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         attr_set = true;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BITMAP, BOTH>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BITMAP, BOTH, HINT>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    int grid = grid_for(b.n_tiles, 1, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BITMAP, BOTH><<<grid, COUNT_THREADS, smem, s>>>(ix->view(), b);
-    GKI_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid_for(b.n_tiles, 1, device_info().sms * blocks_per_sm));
+    cfg.blockDim = dim3(COUNT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (BITMAP && (ix->l2_mode & 2)) {   // keep the bitmap in the persisting L2 set-aside
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = (void *)ix->bitmap;
+        attr[0].val.accessPolicyWindow.num_bytes = ix->bitmap_bytes;
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    GKI_CUDA(cudaLaunchKernelEx(&cfg, count_reads_kernel<BITMAP, BOTH, HINT>, ix->view(), b));
+    count_launch();
     return GKI_OK;
+}
+template <bool BITMAP, bool BOTH> static int launch_count_reads_h(gki_index *ix, const ReadBatch &b, size_t smem, cudaStream_t s) {
+    return (ix->l2_mode & 1) ? launch_count_reads_t<BITMAP, BOTH, true>(ix, b, smem, s) : launch_count_reads_t<BITMAP, BOTH, false>(ix, b, smem, s);
 }
 
 // reads: dense device rows
@@ -382,8 +472,8 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     size_t smem;
     make_read_batch(dreads, n_reads, read_len, stride, k, b, smem);
     GKI_REQUIRE(smem <= 64 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
-    if (ix->bitmap) return both ? launch_count_reads_t<true, true>(ix, b, smem, s) : launch_count_reads_t<true, false>(ix, b, smem, s);
-    return both ? launch_count_reads_t<false, true>(ix, b, smem, s) : launch_count_reads_t<false, false>(ix, b, smem, s);
+    if (ix->bitmap) return both ? launch_count_reads_h<true, true>(ix, b, smem, s) : launch_count_reads_h<true, false>(ix, b, smem, s);
+    return both ? launch_count_reads_h<false, true>(ix, b, smem, s) : launch_count_reads_h<false, false>(ix, b, smem, s);
 }
 
 }  // namespace gki
@@ -445,7 +535,36 @@ int gki_index_create(const int32_t *hashes_to_index, const uint32_t *n_kmers, co
         GKI_CUDA(cudaFree(ix->bitmap));
         ix->bitmap = nullptr;
     }
-    if (ix->bitmap) total += bitmap_words * 4;
+    if (const char *e = getenv("GKI_L2_MODE")) ix->l2_mode = atoi(e);
+    ix->bitmap_bytes = bitmap_words * 4;
+    if (ix->bitmap) {
+        // Coarsen the bitmap (one bit per 2^shift buckets) until it fits the L2 budget: a filter that misses L2
+        // costs a 64-byte HBM fetch per query, a coarser one only lets a few more queries through to the cells.
+        size_t budget = (size_t)24 << 20;
+        if (const char *e = getenv("GKI_BITMAP_MAX_MB")) budget = (size_t)atoi(e) << 20;
+        uint32_t shift = 0;
+        while (shift < 5 && (bitmap_words * 4 >> shift) > budget) shift++;
+        if (const char *e = getenv("GKI_BITMAP_SHIFT")) shift = (uint32_t)atoi(e);
+        if (shift > 5) shift = 5;
+        if (shift) {
+            uint64_t coarse_words = ((((modulo + ((1ull << shift) - 1)) >> shift) + 31) / 32);
+            uint32_t *coarse = nullptr;
+            GKI_CUDA(cudaMalloc((void **)&coarse, coarse_words * 4));
+            coarsen_bitmap_kernel<<<grid_for((int64_t)coarse_words, 256, device_info().sms * 16), 256, 0, s>>>(ix->bitmap, bitmap_words, shift, coarse, coarse_words);
+            GKI_CHECK_LAUNCH();
+            GKI_CUDA(cudaStreamSynchronize(s));
+            GKI_CUDA(cudaFree(ix->bitmap));
+            ix->bitmap = coarse;
+            ix->bitmap_shift = shift;
+            ix->bitmap_bytes = coarse_words * 4;
+        }
+        total += ix->bitmap_bytes;
+        if (ix->l2_mode & 2) {
+            cudaDeviceProp prop;
+            GKI_CUDA(cudaGetDeviceProperties(&prop, ix->device));
+            GKI_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)prop.persistingL2CacheMaxSize));
+        }
+    }
     ix->device_bytes = total;
     guard.p = nullptr;
     *out = ix;
@@ -473,13 +592,14 @@ int gki_index_destroy(gki_index_t *ix) {
 }
 
 int gki_index_info(const gki_index_t *ix, int64_t *n, uint64_t *modulo, int64_t *max_node, int64_t *device_bytes,
-                   int32_t *has_bitmap) {
+                   int32_t *has_bitmap, int64_t *nonempty_buckets) {
     GKI_REQUIRE(ix, GKI_ERR_INVALID, "gki_index_info: index is NULL");
     if (n) *n = ix->n;
     if (modulo) *modulo = ix->modulo;
     if (max_node) *max_node = ix->max_node;
     if (device_bytes) *device_bytes = (int64_t)ix->device_bytes;
     if (has_bitmap) *has_bitmap = ix->bitmap != nullptr;
+    if (nonempty_buckets) *nonempty_buckets = ix->nonempty;
     return GKI_OK;
 }
 

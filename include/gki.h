@@ -114,9 +114,10 @@ int gki_index_create(const int32_t *hashes_to_index, const uint32_t *n_kmers, co
                      const float *af, int64_t n, uint64_t modulo, int32_t flags, gki_index_t **out,
                      gki_stream_t stream);
 int gki_index_destroy(gki_index_t *index);
-/* introspection: n entries, modulo, max node id (cfki:237-238), device bytes, bitmap in use. */
+/* introspection: n entries, modulo, max node id (cfki:237-238), device bytes, bitmap in use, number of
+ * non-empty buckets.  Any output pointer may be NULL. */
 int gki_index_info(const gki_index_t *index, int64_t *n, uint64_t *modulo, int64_t *max_node,
-                   int64_t *device_bytes, int32_t *has_bitmap);
+                   int64_t *device_bytes, int32_t *has_bitmap, int64_t *nonempty_buckets);
 
 /* cfki:30-31 CounterKmerIndex.reset (intended meaning: zero every counter). */
 int gki_reset_counts(gki_index_t *index, gki_stream_t stream);

@@ -1,0 +1,63 @@
+"""Sweep the K3 layout knobs on the c2 workload: bitmap coarsening (GKI_BITMAP_SHIFT) x L2 mode (GKI_L2_MODE:
+bit0 per-load eviction hints, bit1 persisting access-policy window).  Prints kernel ms per launch; checks that the
+node counts are identical for every setting.  Usage: python profiles/tune_count.py [entries] [reads]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from graph_kmer_index_b200 import DeviceIndex, _lib, synthetic  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 60_000_000
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
+modulo, k, L, n_nodes, p_hit = 452_930_477, 31, 150, max(n // 10, 1), 100
+dev = torch.device("cuda")
+glen = synthetic.genome_length(n, k)
+genome = torch.empty(glen, dtype=torch.uint8, device=dev)
+_lib.call("gki_synth_genome", _lib.ptr(genome), glen, None)
+hashes = torch.empty(n, dtype=torch.int64, device=dev)
+nodes = torch.empty(n, dtype=torch.int32, device=dev)
+_lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(hashes), _lib.ptr(nodes), None, None, None)
+h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+nkm = torch.empty(modulo, dtype=torch.int32, device=dev)
+s_k, s_n = torch.empty_like(hashes), torch.empty_like(nodes)
+_lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, 1, _lib.ptr(h2i), _lib.ptr(nkm),
+          _lib.ptr(s_k), _lib.ptr(s_n), None, None, None, None, None)
+reads = torch.empty((R, L), dtype=torch.uint8, device=dev)
+_lib.call("gki_synth_reads", _lib.ptr(genome), glen, 0, R, L, p_hit, 0, _lib.ptr(reads), None)
+torch.cuda.synchronize()
+counts = torch.zeros(n_nodes, dtype=torch.float64, device=dev)
+ref_sum = None
+results = []
+combos = [(s, m) for s in (0, 1, 2, 3) for m in (0, 1, 2, 3)] + [(-1, 0)]
+for shift, mode in combos:
+    if shift < 0:
+        flags = _lib.GKI_INDEX_NO_BITMAP
+    else:
+        flags = 0
+        os.environ["GKI_BITMAP_SHIFT"] = str(shift)
+    os.environ["GKI_L2_MODE"] = str(mode)
+    index = DeviceIndex(h2i, nkm, s_k, s_n, modulo, flags=flags)
+    for _ in range(2):
+        index.reset_counts()
+        index.count_reads(reads, k, True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(5)]
+    for a, b in ev:
+        index.reset_counts()
+        a.record()
+        index.count_reads(reads, k, True)
+        b.record()
+    index.node_counts(n_nodes, out=counts)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    total = float(counts.sum().item())
+    ref_sum = total if ref_sum is None else ref_sum
+    assert total == ref_sum, (shift, mode, total, ref_sum)
+    info = index.info()
+    r = dict(bitmap_shift=shift, l2_mode=mode, kernel_ms=ms, gkmers_per_s=R * 240 / ms / 1e6, bitmap=info["has_bitmap"])
+    results.append(r)
+    print(json.dumps(r), flush=True)
+    index.close()
