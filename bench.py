@@ -224,6 +224,7 @@ def main():
     torch.cuda.synchronize()
     build_ms = build_ev[0].elapsed_time(build_ev[1])
     index = DeviceIndex(h2i, nkm, s_kmers, s_nodes, modulo)
+    index.prepare_counting(k)          # Bloom filter + count table (otherwise built inside the first counting call)
     info = index.info()
     del hashes, nodes
     reads = torch.empty((R, L), dtype=torch.uint8, device=dev)
@@ -335,7 +336,6 @@ def main():
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     kmers_per_launch = R * nk_per_read
     # counts summed over nodes counts every hit once per entry of the k-mer (2 entries per distinct k-mer)
-    h = (total_counts / world / 2.0) / kmers_per_launch if world == 1 else None
     h = (entry_hits / 2.0) / kmers_per_launch
     occ = info["nonempty_buckets"] / modulo
     sectors = (1 - h) * (1 - occ) * 1 + (1 - h) * occ * 3 + h * 5          # SURVEY.md section 8(d) K3 model
@@ -348,7 +348,7 @@ def main():
             traffic = json.load(open(tpath)).get("count_reads_kernel_dram_bytes_per_launch_%s" % args.config)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "count_reads_kernel<bitmap=%s,both=true>" % str(info["has_bitmap"]).lower(),
+    roofline = {"bound": "hbm", "kernel": "count_reads_kernel<both=true,paired=true> (L2 Bloom filter: %s)" % str(info["has_filter"]).lower(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
                 "algorithmic_bytes_per_kmer": bytes_per_kmer, "sectors_per_kmer_model": sectors, "hit_fraction": h,
@@ -375,7 +375,7 @@ def main():
             "index_build": {"entries_per_s": n / (build_ms / 1e3), "ms": build_ms, "entries": n,
                             "compulsory_gbs": (50.0 * n + 8.0 * modulo) / (build_ms / 1e3) / 1e9,
                             "note": "gki_index_build (skip_frequencies), device-resident, single untimed-warm-up-free run"},
-            "index": {"device_bytes": info["device_bytes"], "has_bitmap": info["has_bitmap"], "nonempty_buckets": info["nonempty_buckets"]}}
+            "index": {"device_bytes": info["device_bytes"], "has_filter": info["has_filter"], "nonempty_buckets": info["nonempty_buckets"]}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

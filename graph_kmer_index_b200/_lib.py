@@ -13,7 +13,7 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libgki.so")
-SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "build.cu", "synth.cu", "finder.cu"]
+SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "count.cu", "build.cu", "synth.cu", "finder.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
@@ -70,6 +70,7 @@ _SIGNATURES = {
     "gki_index_destroy": [c_vp],
     "gki_index_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_u64), ctypes.POINTER(c_i64),
                        ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)],
+    "gki_prepare_counting": [c_vp, c_i32, c_vp],
     "gki_reset_counts": [c_vp, c_vp],
     "gki_count_kmers": [c_vp, c_vp, c_i64, c_vp],
     "gki_count_reads": [c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp],
@@ -90,7 +91,6 @@ _SIGNATURES = {
 EXPORTED = [n for n in _SIGNATURES] + ["gki_last_error", "gki_version", "gki_launch_count"]
 
 GKI_BUILD_SKIP_FREQUENCIES = 1
-GKI_INDEX_NO_BITMAP, GKI_INDEX_FORCE_BITMAP = 1, 2
 GKI_COUNTS_WRAP_UINT16 = 1
 GKI_PROBE_SKIP_BUCKET0 = 1
 

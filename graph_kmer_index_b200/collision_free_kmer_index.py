@@ -61,8 +61,13 @@ class DeviceIndex:
         n, mod, mx, nbytes, bm, ne = ctypes.c_int64(), ctypes.c_uint64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int64()
         _lib.call("gki_index_info", self.handle, ctypes.byref(n), ctypes.byref(mod), ctypes.byref(mx), ctypes.byref(nbytes), ctypes.byref(bm),
                   ctypes.byref(ne))
-        return dict(n=n.value, modulo=mod.value, max_node=mx.value, device_bytes=nbytes.value, has_bitmap=bool(bm.value),
+        return dict(n=n.value, modulo=mod.value, max_node=mx.value, device_bytes=nbytes.value, has_filter=bool(bm.value),
                     nonempty_buckets=ne.value)
+
+    def prepare_counting(self, k=0):
+        """Build the counting structure (L2 Bloom filter + table over the distinct k-mers) now instead of inside the
+        first counting call.  k = k-mer length of the reads to be counted (0 if unknown); results never depend on it."""
+        _lib.call("gki_prepare_counting", self.handle, int(k), _lib.current_stream())
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
@@ -232,11 +237,15 @@ class CounterKmerIndex:
         self.counter = counter
 
     @classmethod
-    def from_kmer_index(cls, kmer_index):
-        """cfki:20-28.  The counter lives on the device, keyed by the index's own bucket layout (mod = index modulo)."""
+    def from_kmer_index(cls, kmer_index, k=None):
+        """cfki:20-28.  The counters live on the device in a table over the distinct index k-mers (csrc/count.cu).
+        `k` (extension, optional): the k-mer length, which lets both strands of a read position share one probe."""
         kmers = kmer_index._kmers.astype(np.int64)
         nodes = kmer_index._nodes
-        return cls(kmers, nodes, DeviceCounter(kmer_index.device_index()))
+        device = kmer_index.device_index()
+        if k is not None:
+            device.prepare_counting(k)
+        return cls(kmers, nodes, DeviceCounter(device))
 
     def reset(self):
         """cfki:30-31 (the reference rebinds the Counter to np.zeros_like(counter); the intent -- zero every count -- is kept)."""

@@ -1,0 +1,71 @@
+// index.cuh -- the device-resident index object shared by index.cu (reference layout + lookups) and
+// count.cu (probe table + counting).
+#pragma once
+#include "common.cuh"
+
+namespace gki {
+
+// Reference layout on the device: cells[b] = {hashes_to_index[b], n_kmers[b]} (one 8-byte load per probe instead
+// of two loads from two tables), kmers / nodes (+ optional payload columns) in bucket order.
+struct IndexView {
+    const uint2 *cells;
+    const uint64_t *kmers;
+    FastMod fm;
+};
+
+// Counting structure (count.cu): a bucketised open-addressing table over the DISTINCT index k-mers.
+//   slot   = {key, cnt[2]} (16 B); bucket = 4 slots = one 64-byte line = one HBM access per probe;
+//   key    = canonical form min(x, revcomp_k(x)) when the k-mer length k is known (k > 0), else x itself;
+//   cnt[o] = number of counted queries q with canonical(q) == key and orientation o = (q != key).
+// Both strands of a read position share one canonical key, so a position costs ONE filter access and at most
+// ONE table access, and a hit is ONE 64-bit RED on the line that was just fetched.
+//   filter = register-blocked Bloom filter (64-bit words, filter_k bits per key) sized to stay resident in L2.
+struct Slot {
+    unsigned long long key;
+    uint32_t cnt[2];
+};
+constexpr unsigned long long SLOT_EMPTY = ~0ull;
+constexpr int SLOTS_PER_BUCKET = 4;
+
+struct TableView {
+    Slot *slots;              // n_buckets * 4, + 1 special slot for the key that equals SLOT_EMPTY (raw mode only)
+    const uint64_t *filter;   // filter_words u64 (NULL: no filter)
+    uint32_t n_buckets;
+    uint32_t filter_words;
+    int32_t filter_k;         // bits set per key (1..3)
+    int32_t k;                // canonical k-mer length, 0 = raw keys
+};
+
+}  // namespace gki
+
+struct gki_index {
+    int device = 0;
+    int64_t n = 0;
+    uint64_t modulo = 0;
+    gki::FastMod fm{};
+    uint2 *cells = nullptr;
+    uint64_t *kmers = nullptr;
+    uint32_t *nodes = nullptr;
+    uint64_t *ref_offsets = nullptr;
+    uint16_t *freq = nullptr;
+    float *af = nullptr;
+    int64_t max_node = -1;
+    int64_t nonempty = 0;
+    uint64_t max_kmer = 0;
+    size_t device_bytes = 0;
+    // counting structure, built by the first counting call (count.cu)
+    gki::TableView table{};
+    int64_t n_distinct = 0;
+    size_t table_bytes = 0, filter_bytes = 0;
+    // host-buffer streaming (gki_count_reads / gki_count_kmers with host pointers)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    void *stage[2] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+
+    gki::IndexView view() const { return gki::IndexView{cells, kmers, fm}; }
+};
+
+namespace gki {
+void destroy_count_table(gki_index *ix);   // count.cu
+}

@@ -102,22 +102,25 @@ int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *k
 
 /* ------------------------------------------------------------------ K3: resident index, lookup, counting */
 
-#define GKI_INDEX_NO_BITMAP 1     /* never build the L2-resident bucket-occupancy bitmap   */
-#define GKI_INDEX_FORCE_BITMAP 2  /* always build it                                       */
-
 /* Upload a CollisionFreeKmerIndex (cfki:176-189 attribute arrays; npz layout cfki:393-402) and lay it
- * out for probing: {hashes_to_index, n_kmers} interleaved into one 8-byte cell per bucket, optional
- * bucket-occupancy bitmap, zeroed per-entry counters.  ref_offsets/frequencies/af may be NULL (only
- * gki_lookup_hits and the frequency gates need them). */
+ * out for probing: {hashes_to_index, n_kmers} interleaved into one 8-byte cell per bucket.
+ * ref_offsets/frequencies/af may be NULL (only gki_lookup_hits and the frequency gates need them).
+ * flags: reserved, pass 0. */
 int gki_index_create(const int32_t *hashes_to_index, const uint32_t *n_kmers, const uint64_t *kmers,
                      const uint32_t *nodes, const uint64_t *ref_offsets, const uint16_t *frequencies,
                      const float *af, int64_t n, uint64_t modulo, int32_t flags, gki_index_t **out,
                      gki_stream_t stream);
 int gki_index_destroy(gki_index_t *index);
-/* introspection: n entries, modulo, max node id (cfki:237-238), device bytes, bitmap in use, number of
+/* introspection: n entries, modulo, max node id (cfki:237-238), device bytes, L2 Bloom filter in use, number of
  * non-empty buckets.  Any output pointer may be NULL. */
 int gki_index_info(const gki_index_t *index, int64_t *n, uint64_t *modulo, int64_t *max_node,
-                   int64_t *device_bytes, int32_t *has_bitmap, int64_t *nonempty_buckets);
+                   int64_t *device_bytes, int32_t *has_filter, int64_t *nonempty_buckets);
+
+/* Build the counting structure now (otherwise the first counting call builds it): a Bloom filter sized to stay in
+ * L2 + a bucketised table over the distinct k-mers.  k = k-mer length of the reads that will be counted (lets both
+ * strands of a read position share one canonical key); k = 0 if unknown.  The first call fixes the mode; results
+ * never depend on it.  Synchronises `stream`. */
+int gki_prepare_counting(gki_index_t *index, int32_t k, gki_stream_t stream);
 
 /* cfki:30-31 CounterKmerIndex.reset (intended meaning: zero every counter). */
 int gki_reset_counts(gki_index_t *index, gki_stream_t stream);

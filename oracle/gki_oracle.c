@@ -114,20 +114,26 @@ int orc_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_
     free(cursor);
     memset(freq_o, 0, sizeof(uint16_t) * n);
     if (!skip_frequencies) {
+        /* first[a] = 1 iff no earlier entry of the bucket has the same (k-mer, ref_offset) pair */
+        uint8_t *first = (uint8_t *)malloc(n);
+        if (!first) return -1;
+#pragma omp parallel for schedule(dynamic, 4096)
+        for (int64_t a = 0; a < n; a++) {
+            int64_t s = hashes_to_index[kmers_o[a] % modulo];
+            uint8_t f = 1;
+            for (int64_t c = a - 1; c >= s; c--)
+                if (kmers_o[c] == kmers_o[a] && ref_o[c] == ref_o[a]) { f = 0; break; }
+            first[a] = f;
+        }
 #pragma omp parallel for schedule(dynamic, 4096)
         for (int64_t e = 0; e < n; e++) {
             uint64_t b = kmers_o[e] % modulo;
             int64_t s = hashes_to_index[b], t = s + n_kmers[b];
             uint32_t cnt = 0;
-            for (int64_t a = s; a < t; a++) {
-                if (kmers_o[a] != kmers_o[e]) continue;
-                int first = 1;
-                for (int64_t c = s; c < a; c++)
-                    if (kmers_o[c] == kmers_o[e] && ref_o[c] == ref_o[a]) { first = 0; break; }
-                cnt += first;
-            }
+            for (int64_t a = s; a < t; a++) cnt += (kmers_o[a] == kmers_o[e]) & first[a];
             freq_o[e] = (uint16_t)cnt;
         }
+        free(first);
     }
     return 0;
 }

@@ -1,6 +1,6 @@
-"""Sweep the K3 layout knobs on the c2 workload: bitmap coarsening (GKI_BITMAP_SHIFT) x L2 mode (GKI_L2_MODE:
-bit0 per-load eviction hints, bit1 persisting access-policy window).  Prints kernel ms per launch; checks that the
-node counts are identical for every setting.  Usage: python profiles/tune_count.py [entries] [reads]"""
+"""Sweep the K3 layout knobs on the c2 workload: Bloom filter budget (GKI_FILTER_MAX_MB), bits per key
+(GKI_FILTER_K), raw vs canonical keys (GKI_TABLE_RAW).  Prints kernel ms per launch; checks that the node counts are
+identical for every setting.  Usage: python profiles/tune_count.py [entries] [reads]"""
 import json
 import os
 import sys
@@ -32,15 +32,15 @@ torch.cuda.synchronize()
 counts = torch.zeros(n_nodes, dtype=torch.float64, device=dev)
 ref_sum = None
 results = []
-combos = [(s, m) for s in (0, 1, 2, 3) for m in (0, 1, 2, 3)] + [(-1, 0)]
-for shift, mode in combos:
-    if shift < 0:
-        flags = _lib.GKI_INDEX_NO_BITMAP
-    else:
-        flags = 0
-        os.environ["GKI_BITMAP_SHIFT"] = str(shift)
-    os.environ["GKI_L2_MODE"] = str(mode)
-    index = DeviceIndex(h2i, nkm, s_k, s_n, modulo, flags=flags)
+combos = [(mb, fk, raw) for mb in (0, 8, 16, 24, 32, 48, 64) for fk in (0,) for raw in (0,)] + [(32, 2, 0), (32, 1, 0), (32, 0, 1), (16, 2, 0)]
+for mb, fk, raw in combos:
+    os.environ["GKI_FILTER_MAX_MB"] = str(mb)
+    os.environ.pop("GKI_FILTER_K", None)
+    if fk:
+        os.environ["GKI_FILTER_K"] = str(fk)
+    os.environ["GKI_TABLE_RAW"] = str(raw)
+    index = DeviceIndex(h2i, nkm, s_k, s_n, modulo)
+    index.prepare_counting(k)
     for _ in range(2):
         index.reset_counts()
         index.count_reads(reads, k, True)
@@ -55,9 +55,10 @@ for shift, mode in combos:
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     total = float(counts.sum().item())
     ref_sum = total if ref_sum is None else ref_sum
-    assert total == ref_sum, (shift, mode, total, ref_sum)
+    assert total == ref_sum, (mb, fk, raw, total, ref_sum)
     info = index.info()
-    r = dict(bitmap_shift=shift, l2_mode=mode, kernel_ms=ms, gkmers_per_s=R * 240 / ms / 1e6, bitmap=info["has_bitmap"])
+    r = dict(filter_max_mb=mb, filter_k=fk or "auto", raw_keys=raw, kernel_ms=ms, gkmers_per_s=R * 240 / ms / 1e6,
+             has_filter=info["has_filter"], device_bytes=info["device_bytes"])
     results.append(r)
     print(json.dumps(r), flush=True)
     index.close()

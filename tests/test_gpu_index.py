@@ -173,18 +173,33 @@ def test_lookup_and_counts_golden(gki, name):
     assert np.array_equal(counter.get_node_counts(n_nodes), g["read_node_counts"])
 
 
-@pytest.mark.parametrize("flags", ["auto", "bitmap", "nobitmap"])
+@pytest.mark.parametrize("mode", ["canonical", "raw", "nofilter", "tinyfilter", "k_mismatch"])
 @pytest.mark.parametrize("n,modulo,n_reads,L,k", [(40000, 200003, 3000, 150, 31), (40000, 4099, 1500, 150, 31), (5000, 7, 300, 100, 15),
-                                                   (40000, 200003, 777, 64, 31)])
-def test_count_reads_vs_oracle(gki, flags, n, modulo, n_reads, L, k):
+                                                   (40000, 200003, 777, 64, 31), (3000, 1009, 400, 90, 16)])
+def test_count_reads_vs_oracle(gki, monkeypatch, mode, n, modulo, n_reads, L, k):
+    """every layout of the counting structure gives the oracle's node counts: canonical keys (both strands share a
+    probe), raw keys, no Bloom filter, a saturated filter, and a table prepared for another k"""
     import torch
     from graph_kmer_index_b200 import _lib, synthetic
     hashes, nodes, ref, af = synthetic.flat_kmers(n, 997, k)
+    if k % 2 == 0:                                     # even k: palindromic k-mers exist; make sure some are indexed and read
+        pal = np.array([no.sequence_to_kmer_hash("ACGT" * (k // 4))], dtype=np.uint64)
+        assert no.revcomp_hashes(pal, k)[0] == pal[0]
+        hashes = hashes.copy()
+        hashes[:3] = pal[0]
     idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
     reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=400, n_permille=10)
-    f = {"auto": 0, "bitmap": _lib.GKI_INDEX_FORCE_BITMAP, "nobitmap": _lib.GKI_INDEX_NO_BITMAP}[flags]
-    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo, flags=f)
-    assert dev.info()["has_bitmap"] == {"auto": dev.info()["has_bitmap"], "bitmap": True, "nobitmap": False}[flags]
+    if k % 2 == 0:
+        reads[:5, :k] = np.frombuffer(("ACGT" * (k // 4)).encode(), dtype=np.uint8)
+    if mode == "raw":
+        monkeypatch.setenv("GKI_TABLE_RAW", "1")
+    elif mode == "nofilter":
+        monkeypatch.setenv("GKI_FILTER_MAX_MB", "0")
+    elif mode == "tinyfilter":
+        monkeypatch.setenv("GKI_FILTER_K", "1")
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo)
+    dev.prepare_counting((k + 1 if k < 31 else k - 1) if mode == "k_mismatch" else (0 if mode == "raw" else k))
+    assert dev.info()["has_filter"] == (mode != "nofilter")
     want = c_oracle.read_node_counts(idx, reads, k, 1000)
     assert want.sum() > 0
     dev.count_reads(reads, k)                                   # host buffer: chunked H2D inside the call
