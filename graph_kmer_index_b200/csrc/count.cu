@@ -9,14 +9,18 @@
 // modulo-bucket tables behind a 56 MB bucket bitmap, was bound by exactly those two rates (132 GB of DRAM reads
 // per 2.4 G queries).  Hence this layout:
 //
-//   * Bloom filter, register-blocked (one 64-bit word per key, filter_k bits), sized <= ~32 MB so it stays in
+//   * Bloom filter, register-blocked (one 32-bit word per key, filter_k bits), sized <= 48 MB so it stays in
 //     L2: one L2 access decides most absent k-mers.
 //   * bucketised open-addressing table over the distinct k-mers: bucket = 4 slots x {key, cnt[2]} = one 64-byte
 //     line = ONE HBM access per surviving probe; the hit's RED lands on the line that was just fetched.
 //   * canonical keys: key = min(x, revcomp_k(x)), cnt[o] with o = (x != key).  The forward and reverse-complement
 //     hashes of a read position share the key, so a position (2 queries) costs one filter access, at most one
 //     table access and one 64-bit RED (+1 on both orientations).
-//   * multiply-xorshift hash + multiply-high range reduction: no 64-bit modulo in the hot loop.
+//   * multiply-fold hash + multiply-high range reduction: no 64-bit modulo in the hot loop.
+//
+// The fused kernel is warp-autonomous: every warp streams its own tiles of reads into shared memory with TMA
+// bulk copies (double-buffered on per-warp mbarriers), packs them to 2 bits per base and walks them with a
+// rolling window -- no CTA-wide barrier anywhere, so a warp that waits on HBM never stalls its neighbours.
 #include <stdlib.h>
 #include "index.cuh"
 #include "reads_tile.cuh"
@@ -24,13 +28,32 @@
 namespace gki {
 
 constexpr int COUNT_THREADS = 256;
+constexpr int COUNT_WARPS = COUNT_THREADS / 32;
 
 // ------------------------------------------------------------------ hashing / keys
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x *= 0x9E3779B97F4A7C15ull;
-    x ^= x >> 32;
-    x *= 0xD6E8FEB86659FD93ull;
-    return x ^ (x >> 32);
+struct Hash {
+    uint32_t hi;   // well-mixed: home bucket
+    uint32_t f;    // folded: Bloom word + bit positions
+};
+__device__ __forceinline__ Hash hash_key(unsigned long long key) {
+    unsigned long long a = key * 0x9E3779B97F4A7C15ull;
+    Hash h;
+    h.hi = (uint32_t)(a >> 32);
+    h.f = h.hi ^ (uint32_t)a;
+    return h;
+}
+__device__ __forceinline__ uint32_t home_bucket(const TableView &t, const Hash &h) { return __umulhi(h.hi, t.n_buckets); }
+__device__ __forceinline__ uint32_t filter_word(const TableView &t, const Hash &h) {
+    uint32_t g = h.f * 0x85EBCA6Bu;
+    g ^= g >> 15;
+    return __umulhi(g, t.filter_words);
+}
+__device__ __forceinline__ uint32_t filter_mask(const TableView &t, const Hash &h) {
+    uint32_t b = h.f * 0xC2B2AE35u;
+    uint32_t mask = 1u << (b >> 27);
+    if (t.filter_k > 1) mask |= 1u << ((b >> 22) & 31);
+    if (t.filter_k > 2) mask |= 1u << ((b >> 17) & 31);
+    return mask;
 }
 
 struct Key {
@@ -55,28 +78,8 @@ __device__ __forceinline__ Key make_key(uint64_t q, int k) {
     return key;
 }
 
-__device__ __forceinline__ bool filter_pass(const TableView &t, uint64_t h) {
-    if (!t.filter) return true;
-    uint32_t word = __umulhi((uint32_t)h, t.filter_words);
-    uint32_t hi = (uint32_t)(h >> 32);
-    unsigned long long mask = 1ull << (hi & 63);
-    if (t.filter_k > 1) mask |= 1ull << ((hi >> 6) & 63);
-    if (t.filter_k > 2) mask |= 1ull << ((hi >> 12) & 63);
-    return (__ldg(t.filter + word) & mask) == mask;
-}
-__device__ __forceinline__ unsigned long long filter_mask(const TableView &t, uint64_t h) {
-    uint32_t hi = (uint32_t)(h >> 32);
-    unsigned long long mask = 1ull << (hi & 63);
-    if (t.filter_k > 1) mask |= 1ull << ((hi >> 6) & 63);
-    if (t.filter_k > 2) mask |= 1ull << ((hi >> 12) & 63);
-    return mask;
-}
-__device__ __forceinline__ uint32_t home_bucket(const TableView &t, uint64_t h) {
-    return __umulhi((uint32_t)(h >> 32), t.n_buckets);
-}
-
 // slot holding key c, or nullptr.  Probing visits buckets linearly and stops at the first non-full bucket.
-__device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long long c, uint64_t h) {
+__device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long long c, const Hash &h) {
     if (c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker has its own slot,
         Slot *sp = t.slots + (size_t)t.n_buckets * SLOTS_PER_BUCKET;   // whose key field is 1 iff that value is indexed
         return __ldg(&sp->key) == 1ull ? sp : nullptr;
@@ -101,8 +104,11 @@ __device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long lon
 __device__ __forceinline__ void count_one(const TableView &t, uint64_t q) {
     Key key = make_key(q, t.k);
     if (!key.ok) return;
-    uint64_t h = mix64(key.c);
-    if (!filter_pass(t, h)) return;
+    Hash h = hash_key(key.c);
+    if (t.filter) {
+        uint32_t m = filter_mask(t, h);
+        if ((__ldg(t.filter + filter_word(t, h)) & m) != m) return;
+    }
     Slot *s = find_slot(t, key.c, h);
     if (s) atomicAdd(&s->cnt[key.o], 1u);
 }
@@ -137,7 +143,7 @@ __global__ void count_distinct_kernel(IndexView ix, int64_t n, unsigned long lon
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, (unsigned long long)local);
 }
 
-__global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ kmers, int64_t n, unsigned long long *__restrict__ filter,
+__global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ kmers, int64_t n, uint32_t *__restrict__ filter,
                                     unsigned int *__restrict__ failed) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         Key key = make_key(__ldg(kmers + e), t.k);
@@ -145,8 +151,8 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
             t.slots[(size_t)t.n_buckets * SLOTS_PER_BUCKET].key = 1ull;   // mark the special slot as present
             continue;
         }
-        uint64_t h = mix64(key.c);
-        if (filter) atomicOr(filter + __umulhi((uint32_t)h, t.filter_words), filter_mask(t, h));
+        Hash h = hash_key(key.c);
+        if (filter) atomicOr(filter + filter_word(t, h), filter_mask(t, h));
         uint32_t b = home_bucket(t, h);
         bool placed = false;
         for (uint32_t tries = 0; tries < t.n_buckets && !placed; tries++) {
@@ -173,78 +179,162 @@ __global__ void __launch_bounds__(COUNT_THREADS) count_kmers_kernel(TableView t,
         count_one(t, __ldg(queries + i));
 }
 
-// Fused K1 -> K3.  A warp owns a read; each lane takes WPL windows.  PAIRED (both strands, read k == table k):
-// forward and reverse-complement hash of a fully valid window share one canonical key -> one probe, one RED.
-constexpr int WPL = 4;
+// ---- fused K1 -> K3, warp-autonomous ----
+struct WarpBatch {
+    const uint8_t *reads;
+    int64_t n_reads;
+    int64_t row_stride;
+    int64_t n_wtiles;       // ceil(n_reads / rpw)
+    int32_t read_len;
+    int32_t k;
+    int32_t nk;             // read_len - k + 1
+    int32_t words;          // ceil(read_len / 32) + 1
+    int32_t rpw;            // reads per warp tile
+    int32_t bulk_ok;        // dense + aligned: full tiles are one TMA bulk copy
+    uint32_t stage_bytes;   // bytes of one ASCII stage (16-byte multiple, incl. slack)
+    uint32_t warp_bytes;    // shared memory per warp
+};
 
-template <bool BOTH, bool PAIRED>
-__global__ void __launch_bounds__(COUNT_THREADS) count_reads_kernel(TableView t, ReadBatch b) {
+constexpr int WPL = 4;   // consecutive windows per lane
+
+template <bool BOTH, bool PAIRED, int MINB>
+__global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // per-warp shared memory: [mbarrier | ASCII stage | codes | valid | dirty flags].  One ASCII stage is enough: it is
+    // dead once packed, so the next tile's bulk copy is issued right after packing and lands while the warp walks.
+    unsigned char *wbase = smem_raw + (size_t)warp * b.warp_bytes;
+    uint64_t *bar = (uint64_t *)wbase;
+    uint8_t *ascii = wbase + 16;
+    uint64_t *codes = (uint64_t *)(wbase + 16 + (size_t)b.stage_bytes);
+    uint64_t *valid = codes + (size_t)b.rpw * b.words;
+    uint32_t *dirty = (uint32_t *)(valid + (size_t)b.rpw * b.words);
     const uint64_t mask = kmer_mask(b.k);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for_each_tile(b, smem_raw, [&](int64_t tile, const TileSmem &ts) {
-        int64_t r0 = tile * (int64_t)b.tile_reads;
-        for (int r = warp; r < b.tile_reads && r0 + r < b.n_reads; r += nwarps) {
-            const uint64_t *cw = ts.codes + (size_t)r * b.words;
-            const uint64_t *vw = ts.valid + (size_t)r * b.words;
-            for (int base = 0; base < b.nk; base += 32 * WPL) {
-                uint64_t fwd[WPL], rc[WPL], h[WPL];
-                unsigned long long c[WPL];
-                uint32_t live = 0, slow = 0;
+    const uint32_t tile_bytes = (uint32_t)b.rpw * (uint32_t)b.read_len;
+
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t total_warps = (int64_t)gridDim.x * COUNT_WARPS;
+    int64_t wt = (int64_t)blockIdx.x * COUNT_WARPS + warp;
+    auto uses_bulk = [&](int64_t tile) { return b.bulk_ok && (tile + 1) * (int64_t)b.rpw <= b.n_reads; };
+    auto issue = [&](int64_t tile) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar);
+    };
+    if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt);
+    uint32_t phase = 0;
+
+    for (; wt < b.n_wtiles; wt += total_warps) {
+        const int64_t next = wt + total_warps;
+        const int64_t r0 = wt * (int64_t)b.rpw;
+        const int n_here = (int)min((int64_t)b.rpw, b.n_reads - r0);
+        if (uses_bulk(wt)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {   // strided / unaligned / tail tile: the warp copies its rows itself
+            for (int r = 0; r < n_here; r++) {
+                const uint8_t *src = b.reads + (r0 + r) * b.row_stride;
+                for (int i = lane; i < b.read_len; i += 32) ascii[(size_t)r * b.read_len + i] = __ldg(src + i);
+            }
+            __syncwarp();
+        }
+        // ---- pack to 2 bits per base (+ validity), flag reads that contain a non-ACGT byte ----
+        if (lane < n_here) dirty[lane] = 0;
+        __syncwarp();
+        for (int task = lane; task < n_here * b.words; task += 32) {
+            int r = task / b.words, w = task - r * b.words;
+            int first = w * 32;
+            int nb = min(32, b.read_len - first);
+            uint64_t cw = 0, vw = 0;
+            if (nb > 0) {
+                uint32_t addr = (uint32_t)r * (uint32_t)b.read_len + (uint32_t)first;
+                const uint32_t *aligned = (const uint32_t *)(ascii + (addr & ~3u));
+                uint32_t sh = (addr & 3u) * 8u;
+                uint32_t lo = aligned[0];
+                int nq = (nb + 3) >> 2;
 #pragma unroll
-                for (int u = 0; u < WPL; u++) {
-                    int i = base + u * 32 + lane;
-                    bool ok = i < b.nk;
-                    int ii = ok ? i : 0;
-                    fwd[u] = extract_window(cw, ii, mask);
-                    if (BOTH) {
-                        uint64_t v = extract_window(vw, ii, mask);
-                        rc[u] = revcomp_hash_masked(fwd[u], v, b.k);
-                        if (PAIRED) {
-                            bool clean = v == mask;            // no N: rc is the true reverse complement of fwd
-                            c[u] = fwd[u] < rc[u] ? fwd[u] : rc[u];
-                            live |= (uint32_t)(ok && clean) << u;
-                            slow |= (uint32_t)(ok && !clean) << u;
-                        } else {
-                            slow |= (uint32_t)ok << u;
-                        }
-                    } else {
-                        slow |= (uint32_t)ok << u;
+                for (int q = 0; q < 8; q++) {
+                    if (q < nq) {
+                        uint32_t hi = aligned[q + 1];
+                        uint32_t c8, v8;
+                        encode4(__funnelshift_r(lo, hi, sh), c8, v8);
+                        lo = hi;
+                        cw |= (uint64_t)c8 << (8 * q);
+                        vw |= (uint64_t)v8 << (8 * q);
                     }
                 }
-                if (PAIRED) {
-                    // stage 1: filter words (L2) for all windows of the lane
-                    uint64_t fw[WPL];
-                    unsigned long long fm[WPL];
+                uint64_t m = nb < 32 ? ((1ull << (2 * nb)) - 1ull) : ~0ull;
+                cw &= m;
+                vw &= m;
+                if (vw != m) dirty[r] = 1;
+            }
+            codes[(size_t)r * b.words + w] = cw;
+            valid[(size_t)r * b.words + w] = vw;
+        }
+        __syncwarp();
+        if (next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next);   // prefetch: overlaps the walk below
+        // ---- walk the reads ----
+        for (int r = 0; r < n_here; r++) {
+            const uint64_t *cw = codes + (size_t)r * b.words;
+            const uint64_t *vw = valid + (size_t)r * b.words;
+            if (PAIRED && !dirty[r]) {
+                // clean read: lane owns WPL consecutive windows, rolled from one extraction; the reverse-complement
+                // hash is rolled alongside (kmer_hashing.py:24-28 == bit reversal of the complemented window)
+                for (int base = 0; base < b.nk; base += 32 * WPL) {
+                    const int i0 = base + lane * WPL;
+                    uint64_t x = 0, rc = 0;
+                    uint32_t nxt = 0;
+                    if (i0 < b.nk) {
+                        x = extract_window(cw, i0, mask);
+                        nxt = (uint32_t)extract_window(cw, i0 + b.k, 0x3Full);
+                        rc = revcomp_hash(x, b.k);
+                    }
+                    unsigned long long c[WPL];
+                    Hash h[WPL];
+                    uint32_t fw[WPL], fm[WPL];
+                    uint32_t live = 0, pal = 0;
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
-                        h[u] = mix64(c[u]);
+                        if (u) {
+                            uint64_t nb = (nxt >> (2 * (u - 1))) & 3u;
+                            x = (x >> 2) | (nb << (2 * (b.k - 1)));
+                            rc = ((rc << 2) | (3u - nb)) & mask;
+                        }
+                        bool ok = i0 + u < b.nk;
+                        c[u] = x < rc ? x : rc;
+                        pal |= (uint32_t)(x == rc) << u;
+                        h[u] = hash_key(c[u]);
                         fm[u] = filter_mask(t, h[u]);
-                        fw[u] = (t.filter && ((live >> u) & 1u)) ? __ldg(t.filter + __umulhi((uint32_t)h[u], t.filter_words)) : ~0ull;
+                        fw[u] = (t.filter && ok) ? __ldg(t.filter + filter_word(t, h[u])) : 0xffffffffu;
+                        live |= (uint32_t)ok << u;
                     }
 #pragma unroll
                     for (int u = 0; u < WPL; u++) live &= ~((uint32_t)((fw[u] & fm[u]) != fm[u]) << u);
-                    // stage 2: table (HBM) for the survivors
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
                         if (!((live >> u) & 1u)) continue;
-                        Slot *s = find_slot(t, c[u], h[u]);
-                        if (!s) continue;
-                        if (fwd[u] == rc[u]) atomicAdd(&s->cnt[0], 2u);                                   // palindrome (even k)
-                        else atomicAdd((unsigned long long *)&s->cnt[0], 0x0000000100000001ull);        // +1 on both orientations
+                        Slot *slot = find_slot(t, c[u], h[u]);
+                        if (!slot) continue;
+                        if ((pal >> u) & 1u) atomicAdd(&slot->cnt[0], 2u);                                // palindrome (even k)
+                        else atomicAdd((unsigned long long *)&slot->cnt[0], 0x0000000100000001ull);      // +1 on both orientations
                     }
                 }
-                if (slow) {   // windows with non-ACGT bases, forward-only mode, or read k != table k: independent queries
-#pragma unroll
-                    for (int u = 0; u < WPL; u++) {
-                        if (!((slow >> u) & 1u)) continue;
-                        count_one(t, fwd[u]);
-                        if (BOTH) count_one(t, rc[u]);
-                    }
+            } else {
+                // general path: reads with non-ACGT bytes, forward-only counting, or read k != table k --
+                // every window is extracted on its own and each strand is an independent query
+                for (int i = lane; i < b.nk; i += 32) {
+                    uint64_t x = extract_window(cw, i, mask);
+                    count_one(t, x);
+                    if (BOTH) count_one(t, revcomp_hash_masked(x, extract_window(vw, i, mask), b.k));
                 }
             }
         }
-    });
+        __syncwarp();
+    }
 }
 
 // ------------------------------------------------------------------ counters -> per-entry / per-node
@@ -252,7 +342,7 @@ __device__ __forceinline__ uint32_t kmer_count(const TableView &t, uint64_t km, 
     Key key = make_key(km, t.k);
     uint32_t w = 0;
     if (key.ok) {
-        Slot *s = find_slot(t, key.c, mix64(key.c));
+        Slot *s = find_slot(t, key.c, hash_key(key.c));
         if (s) w = *(volatile uint32_t *)&s->cnt[key.o];
     }
     return wrap16 ? (w & 0xFFFFu) : w;
@@ -313,15 +403,15 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     if (const char *e = getenv("GKI_FILTER_MAX_MB")) budget = (size_t)atoi(e) << 20;
     size_t want = (size_t)distinct * 2;                  // 16 bits per key
     size_t fbytes = want < budget ? want : budget;
-    fbytes = (fbytes + 7) & ~(size_t)7;
+    fbytes = (fbytes + 3) & ~(size_t)3;
     if (fbytes < 64) fbytes = 64;
     double bits_per_key = distinct ? (double)fbytes * 8.0 / (double)distinct : 16.0;
-    unsigned long long *filter = nullptr;
+    uint32_t *filter = nullptr;
     if (budget > 0 && bits_per_key >= 1.5) {
         GKI_CUDA(cudaMalloc((void **)&filter, fbytes));
         GKI_CUDA(cudaMemsetAsync(filter, 0, fbytes, s));
-        t.filter = (const uint64_t *)filter;
-        t.filter_words = (uint32_t)(fbytes / 8);
+        t.filter = filter;
+        t.filter_words = (uint32_t)(fbytes / 4);
         t.filter_k = bits_per_key >= 5.0 ? 3 : (bits_per_key >= 3.0 ? 2 : 1);
         if (const char *e = getenv("GKI_FILTER_K")) t.filter_k = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
         ix->filter_bytes = fbytes;
@@ -363,17 +453,18 @@ static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cud
     return GKI_OK;
 }
 
-template <bool BOTH, bool PAIRED> static int launch_count_reads_t(gki_index *ix, const ReadBatch &b, size_t smem, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        attr_set = true;
+template <bool BOTH, bool PAIRED, int MINB> static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
+    const size_t smem = (size_t)b.warp_bytes * COUNT_WARPS;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    int grid = grid_for(b.n_tiles, 1, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BOTH, PAIRED><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
+    int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
+    count_reads_kernel<BOTH, PAIRED, MINB><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
@@ -381,13 +472,36 @@ template <bool BOTH, bool PAIRED> static int launch_count_reads_t(gki_index *ix,
 // reads: device rows
 static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_reads, int32_t read_len, int64_t stride, int32_t k,
                               int32_t both, cudaStream_t s) {
-    ReadBatch b;
-    size_t smem;
-    make_read_batch(dreads, n_reads, read_len, stride, k, b, smem);
-    GKI_REQUIRE(smem <= 64 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
-    if (!both) return launch_count_reads_t<false, false>(ix, b, smem, s);
-    if (ix->table.k == k) return launch_count_reads_t<true, true>(ix, b, smem, s);
-    return launch_count_reads_t<true, false>(ix, b, smem, s);
+    WarpBatch b;
+    b.reads = dreads;
+    b.n_reads = n_reads;
+    b.row_stride = stride;
+    b.read_len = read_len;
+    b.k = k;
+    b.nk = read_len - k + 1;
+    b.words = (read_len + 31) / 32 + 1;
+    auto warp_bytes = [&](int rpw) {
+        size_t stage = (((size_t)rpw * read_len + 15) & ~(size_t)15) + 16;
+        size_t bytes = 16 + stage + 2 * (size_t)rpw * b.words * 8 + (size_t)rpw * 4;
+        return (bytes + 15) & ~(size_t)15;
+    };
+    int rpw = 8;
+    if (const char *e = getenv("GKI_RPW")) rpw = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
+    while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
+    GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
+    b.rpw = rpw;
+    b.stage_bytes = (uint32_t)((((size_t)rpw * read_len + 15) & ~(size_t)15) + 16);
+    b.warp_bytes = (uint32_t)warp_bytes(rpw);
+    b.n_wtiles = (n_reads + rpw - 1) / rpw;
+    b.bulk_ok = (stride == read_len) && (((uintptr_t)dreads & 15) == 0) && (((int64_t)rpw * read_len) % 16 == 0);
+    if (!both) return launch_count_reads_t<false, false, 4>(ix, b, s);
+    if (ix->table.k != k) return launch_count_reads_t<true, false, 4>(ix, b, s);
+    int minb = 4;
+    if (const char *e = getenv("GKI_MINB")) minb = atoi(e);
+    if (minb == 5) return launch_count_reads_t<true, true, 5>(ix, b, s);
+    if (minb == 6) return launch_count_reads_t<true, true, 6>(ix, b, s);
+    if (minb == 3) return launch_count_reads_t<true, true, 3>(ix, b, s);
+    return launch_count_reads_t<true, true, 4>(ix, b, s);
 }
 
 }  // namespace gki

@@ -19,7 +19,7 @@ struct IndexView {
 //   cnt[o] = number of counted queries q with canonical(q) == key and orientation o = (q != key).
 // Both strands of a read position share one canonical key, so a position costs ONE filter access and at most
 // ONE table access, and a hit is ONE 64-bit RED on the line that was just fetched.
-//   filter = register-blocked Bloom filter (64-bit words, filter_k bits per key) sized to stay resident in L2.
+//   filter = register-blocked Bloom filter (32-bit words, filter_k bits per key) sized to stay resident in L2.
 struct Slot {
     unsigned long long key;
     uint32_t cnt[2];
@@ -29,7 +29,7 @@ constexpr int SLOTS_PER_BUCKET = 4;
 
 struct TableView {
     Slot *slots;              // n_buckets * 4, + 1 special slot for the key that equals SLOT_EMPTY (raw mode only)
-    const uint64_t *filter;   // filter_words u64 (NULL: no filter)
+    const uint32_t *filter;   // filter_words u32 (NULL: no filter)
     uint32_t n_buckets;
     uint32_t filter_words;
     int32_t filter_k;         // bits set per key (1..3)

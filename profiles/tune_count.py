@@ -32,13 +32,13 @@ torch.cuda.synchronize()
 counts = torch.zeros(n_nodes, dtype=torch.float64, device=dev)
 ref_sum = None
 results = []
-combos = [(mb, fk, raw) for mb in (0, 8, 16, 24, 32, 48, 64) for fk in (0,) for raw in (0,)] + [(32, 2, 0), (32, 1, 0), (32, 0, 1), (16, 2, 0)]
-for mb, fk, raw in combos:
-    os.environ["GKI_FILTER_MAX_MB"] = str(mb)
-    os.environ.pop("GKI_FILTER_K", None)
-    if fk:
-        os.environ["GKI_FILTER_K"] = str(fk)
-    os.environ["GKI_TABLE_RAW"] = str(raw)
+KNOBS = ("GKI_FILTER_MAX_MB", "GKI_FILTER_K", "GKI_TABLE_RAW", "GKI_RPW", "GKI_MINB")
+combos = json.loads(sys.argv[3]) if len(sys.argv) > 3 else [{"GKI_FILTER_MAX_MB": mb} for mb in (0, 16, 32, 48, 64)]
+for env in combos:
+    for key in KNOBS:
+        os.environ.pop(key, None)
+    for key, v in env.items():
+        os.environ[key] = str(v)
     index = DeviceIndex(h2i, nkm, s_k, s_n, modulo)
     index.prepare_counting(k)
     for _ in range(2):
@@ -55,10 +55,9 @@ for mb, fk, raw in combos:
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     total = float(counts.sum().item())
     ref_sum = total if ref_sum is None else ref_sum
-    assert total == ref_sum, (mb, fk, raw, total, ref_sum)
+    assert total == ref_sum, (env, total, ref_sum)
     info = index.info()
-    r = dict(filter_max_mb=mb, filter_k=fk or "auto", raw_keys=raw, kernel_ms=ms, gkmers_per_s=R * 240 / ms / 1e6,
-             has_filter=info["has_filter"], device_bytes=info["device_bytes"])
+    r = dict(env=env, kernel_ms=ms, gkmers_per_s=R * 240 / ms / 1e6, has_filter=info["has_filter"], device_bytes=info["device_bytes"])
     results.append(r)
     print(json.dumps(r), flush=True)
     index.close()
