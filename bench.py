@@ -81,19 +81,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken in [t0, t1] (the timed region); if the region was too short to catch one,
+        fall back to the samples nearest to it (the sampler runs from before the warm-up)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        lines = self.lines
+        if t0 is not None:
+            inside = [l for l in lines if t0 - 0.15 <= l[0] <= t1 + 0.15]
+            lines = inside or sorted(lines, key=lambda l: abs(l[0] - 0.5 * (t0 + t1)))[:3]
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        for _, line in lines:
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -244,13 +251,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     launches0 = _lib.launch_count()
+    wall0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     ev0.record()
@@ -265,7 +273,7 @@ def main():
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, time.time()) if rank == 0 else None
     elapsed_ms = ev0.elapsed_time(ev1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)

@@ -70,9 +70,12 @@ class DeviceIndex:
         _lib.call("gki_prepare_counting", self.handle, int(k), _lib.current_stream())
 
     def close(self):
-        if getattr(self, "handle", None) is not None and self.handle.value:
-            _lib.load().gki_index_destroy(self.handle)
-            self.handle = ctypes.c_void_p()
+        try:
+            if getattr(self, "handle", None) is not None and self.handle.value:
+                _lib.load().gki_index_destroy(self.handle)
+                self.handle = ctypes.c_void_p()
+        except (TypeError, AttributeError):      # interpreter shutdown: modules already torn down
+            pass
 
     __del__ = close
 

@@ -78,13 +78,9 @@ __device__ __forceinline__ Key make_key(uint64_t q, int k) {
     return key;
 }
 
-// slot holding key c, or nullptr.  Probing visits buckets linearly and stops at the first non-full bucket.
-__device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long long c, const Hash &h) {
-    if (c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker has its own slot,
-        Slot *sp = t.slots + (size_t)t.n_buckets * SLOTS_PER_BUCKET;   // whose key field is 1 iff that value is indexed
-        return __ldg(&sp->key) == 1ull ? sp : nullptr;
-    }
-    uint32_t b = home_bucket(t, h);
+// slot holding key c (c != SLOT_EMPTY) starting at bucket b, or nullptr.  Probing visits buckets linearly and stops at
+// the first non-full bucket.
+__device__ __forceinline__ Slot *find_slot_from(const TableView &t, unsigned long long c, uint32_t b) {
     for (uint32_t tries = 0; tries < t.n_buckets; tries++) {
         Slot *base = t.slots + (size_t)b * SLOTS_PER_BUCKET;
         unsigned long long key[SLOTS_PER_BUCKET];   // keys never change while a counting kernel runs: all four loads in flight
@@ -98,6 +94,15 @@ __device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long lon
         b = (b + 1 == t.n_buckets) ? 0 : b + 1;
     }
     return nullptr;
+}
+
+// slot holding key c, or nullptr
+__device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long long c, const Hash &h) {
+    if (c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker has its own slot,
+        Slot *sp = t.slots + (size_t)t.n_buckets * SLOTS_PER_BUCKET;   // whose key field is 1 iff that value is indexed
+        return __ldg(&sp->key) == 1ull ? sp : nullptr;
+    }
+    return find_slot_from(t, c, home_bucket(t, h));
 }
 
 // one independent query
@@ -196,6 +201,7 @@ struct WarpBatch {
 };
 
 constexpr int WPL = 4;   // consecutive windows per lane
+constexpr int QCAP = 64;  // survivor queue capacity per warp (< 32 pending + <= 32 pushed per ballot)
 
 template <bool BOTH, bool PAIRED, int MINB>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
@@ -208,9 +214,26 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
     uint8_t *ascii = wbase + 16;
     uint64_t *codes = (uint64_t *)(wbase + 16 + (size_t)b.stage_bytes);
     uint64_t *valid = codes + (size_t)b.rpw * b.words;
-    uint32_t *dirty = (uint32_t *)(valid + (size_t)b.rpw * b.words);
+    unsigned long long *qkey = (unsigned long long *)(valid + (size_t)b.rpw * b.words);   // survivor queue: keys
+    uint32_t *qmeta = (uint32_t *)(qkey + QCAP);                                           //   home bucket | palindrome << 31
+    uint32_t *dirty = qmeta + QCAP;
     const uint64_t mask = kmer_mask(b.k);
     const uint32_t tile_bytes = (uint32_t)b.rpw * (uint32_t)b.read_len;
+    uint32_t qn = 0, qhead = 0;   // warp-uniform: entries pushed / consumed so far
+    auto probe_queue = [&](uint32_t n) {   // the first n queued survivors, one per lane: bucket line from HBM, compare, RED
+        if ((uint32_t)lane < n) {
+            const uint32_t idx = (qhead + lane) & (QCAP - 1);
+            const unsigned long long key = qkey[idx];
+            const uint32_t meta = qmeta[idx];
+            Slot *slot = find_slot_from(t, key, meta & 0x7fffffffu);
+            if (slot) {
+                if (meta >> 31) atomicAdd(&slot->cnt[0], 2u);                                    // palindrome (even k)
+                else atomicAdd((unsigned long long *)&slot->cnt[0], 0x0000000100000001ull);      // +1 on both orientations
+            }
+        }
+        qhead += n;
+        __syncwarp();
+    };
 
     if (lane == 0) {
         mbar_init(bar, 1);
@@ -314,13 +337,22 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                     }
 #pragma unroll
                     for (int u = 0; u < WPL; u++) live &= ~((uint32_t)((fw[u] & fm[u]) != fm[u]) << u);
+                    // survivors (few, scattered over lanes) are compacted into the warp's queue; the table is probed
+                    // 32 survivors at a time, so every HBM round trip is shared by a full warp
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
-                        if (!((live >> u) & 1u)) continue;
-                        Slot *slot = find_slot(t, c[u], h[u]);
-                        if (!slot) continue;
-                        if ((pal >> u) & 1u) atomicAdd(&slot->cnt[0], 2u);                                // palindrome (even k)
-                        else atomicAdd((unsigned long long *)&slot->cnt[0], 0x0000000100000001ull);      // +1 on both orientations
+                        const bool mine = (live >> u) & 1u;
+                        const uint32_t votes = __ballot_sync(0xffffffffu, mine);
+                        if (mine) {
+                            uint32_t slot_idx = (qn + __popc(votes & ((1u << lane) - 1u))) & (QCAP - 1);
+                            qkey[slot_idx] = c[u];
+                            qmeta[slot_idx] = home_bucket(t, h[u]) | (((pal >> u) & 1u) << 31);
+                        }
+                        qn += __popc(votes);
+                        if (qn - qhead >= 32) {
+                            __syncwarp();
+                            probe_queue(32);
+                        }
                     }
                 }
             } else {
@@ -334,6 +366,10 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             }
         }
         __syncwarp();
+    }
+    if (qn != qhead) {   // drain the queue
+        __syncwarp();
+        probe_queue(qn - qhead);
     }
 }
 
@@ -390,7 +426,7 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     TableView t{};
     t.k = k;
     uint64_t buckets = (distinct + 1) / 2 + 16;          // 4 slots per bucket -> load factor <= 0.5
-    GKI_REQUIRE(buckets < (1ull << 32), GKI_ERR_UNSUPPORTED, "count table: too many distinct k-mers");
+    GKI_REQUIRE(buckets < (1ull << 31), GKI_ERR_UNSUPPORTED, "count table: too many distinct k-mers");
     t.n_buckets = (uint32_t)buckets;
     size_t n_slots = (size_t)buckets * SLOTS_PER_BUCKET + 1;
     GKI_CUDA(cudaMalloc((void **)&t.slots, n_slots * sizeof(Slot)));
@@ -482,7 +518,7 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     b.words = (read_len + 31) / 32 + 1;
     auto warp_bytes = [&](int rpw) {
         size_t stage = (((size_t)rpw * read_len + 15) & ~(size_t)15) + 16;
-        size_t bytes = 16 + stage + 2 * (size_t)rpw * b.words * 8 + (size_t)rpw * 4;
+        size_t bytes = 16 + stage + 2 * (size_t)rpw * b.words * 8 + (size_t)QCAP * 12 + (size_t)rpw * 4;
         return (bytes + 15) & ~(size_t)15;
     };
     int rpw = 8;
