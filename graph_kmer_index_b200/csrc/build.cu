@@ -3,15 +3,15 @@
 // Reference: collision_free_kmer_index.py:422-467 (from_flat_kmers) and :267-293 (set_frequencies):
 //   hashes = kmers % modulo; sorting = argsort(hashes); gather 5 columns; run heads -> hashes_to_index,
 //   run lengths -> n_kmers; frequencies = #distinct ref_offsets per k-mer.
-// Here: bucket keys (u32) -> STABLE LSD radix sort of (key, index) pairs, 8 bits per pass, only as many
-// passes as modulo-1 has bits -> run heads / tails written straight into the zeroed dense tables ->
+// Here: (bucket key << 32 | index) elements -> STABLE LSD radix sort, up to 10 bits per pass, only as many
+// passes as modulo-1 has bits (3 at the default modulo) -> run heads / tails written straight into the zeroed dense tables ->
 // one fused gather of the payload columns through the permutation -> frequencies by bucket-local scans.
 // The sort is stable so the payload order inside a bucket is the input order (the canonical order of
 // SURVEY.md section 8c(ii)); numpy's default argsort is not stable, so the reference's own payload order is
 // only defined up to a permutation inside each bucket.
 //
 // Roofline: HBM streaming.  Compulsory traffic 50*N + 8*modulo bytes; this implementation moves
-// 12 (keys) + P*(4 hist + 16 scatter) + 8 (tables) + ~24 gather-in (sector-amplified) + 24 out per entry.
+// 16 (elements) + P*(8 hist + 16 scatter) + 8 (tables) + ~24 gather-in (sector-amplified) + 24 out per entry.
 #include "common.cuh"
 
 namespace gki {
@@ -20,51 +20,77 @@ constexpr int RS_THREADS = 256;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RADIX = 256;
+constexpr int RADIX_MAX = 1024;   // digits of up to 10 bits: a 29-bit bucket id (default modulo) sorts in 3 passes
 
-__global__ void bucket_keys_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, uint32_t *__restrict__ keys) {
+// sort element = (bucket key << 32) | input index: one 8-byte item per entry instead of two 4-byte arrays halves
+// the number of scattered stores of a pass
+__device__ __forceinline__ uint32_t elem_key(unsigned long long e) { return (uint32_t)(e >> 32); }
+__device__ __forceinline__ uint32_t elem_idx(unsigned long long e) { return (uint32_t)e; }
+
+__global__ void bucket_keys_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, unsigned long long *__restrict__ elems) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        keys[i] = fastmod(__ldg(kmers + i), fm);
+        elems[i] = ((unsigned long long)fastmod(__ldg(kmers + i), fm) << 32) | (unsigned long long)(uint32_t)i;
 }
 
 // per-tile digit histogram, stored digit-major: hist[d * n_tiles + tile]
-__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const uint32_t *__restrict__ keys, int64_t n, int shift,
-                                                                uint32_t *__restrict__ hist, int64_t n_tiles) {
-    __shared__ uint32_t h[RADIX];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(RS_THREADS) radix_hist_kernel(const unsigned long long *__restrict__ elems, int64_t n, int shift,
+                                                                int radix, uint32_t *__restrict__ hist, int64_t n_tiles) {
+    __shared__ uint32_t h[RADIX_MAX];
+    for (int d = threadIdx.x; d < radix; d += RS_THREADS) h[d] = 0;
     __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    const uint32_t dmask = (uint32_t)radix - 1u;
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         int64_t i = base + it * RS_THREADS + threadIdx.x;
-        if (i < n) atomicAdd(&h[(__ldg(keys + i) >> shift) & 0xFFu], 1u);
+        if (i < n) atomicAdd(&h[(elem_key(__ldg(elems + i)) >> shift) & dmask], 1u);
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+    for (int d = threadIdx.x; d < radix; d += RS_THREADS) hist[(int64_t)d * n_tiles + blockIdx.x] = h[d];
 }
 
-// stable scatter of one tile.  Key order inside a tile: warp-major, then item, then lane -- i.e. memory order.
-// first_pass: values are the identity (not read).
+// lanes of `okmask` holding the same BITS-bit digit.  MATCH.ANY issues about once per 124 cycles per SM on B200
+// (ncu: profiles/r1/radix_scatter_match_any.txt), BITS ballots + logic ops are several times faster.
+template <int BITS> __device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t okmask) {
+    uint32_t peers = okmask;
+#pragma unroll
+    for (int b = 0; b < BITS; b++) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t votes = __ballot_sync(okmask, bit);
+        peers &= bit ? votes : ~votes;
+    }
+    return peers;
+}
+
+// stable scatter of one tile.  Element order inside a tile: warp-major, then item, then lane -- i.e. memory order.
+template <int BITS>
 __global__ void __launch_bounds__(RS_THREADS)
-    radix_scatter_kernel(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in, int64_t n, int shift,
-                         const uint32_t *__restrict__ offsets, int64_t n_tiles, uint32_t *__restrict__ keys_out,
-                         uint32_t *__restrict__ vals_out, bool first_pass) {
-    __shared__ uint32_t warp_hist[RS_WARPS][RADIX];
+    radix_scatter_kernel(const unsigned long long *__restrict__ in, int64_t n, int shift, const uint32_t *__restrict__ offsets,
+                         int64_t n_tiles, unsigned long long *__restrict__ out) {
+    constexpr int radix = 1 << BITS;
+    __shared__ uint32_t warp_hist[RS_WARPS][radix];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < RS_WARPS * RADIX; i += RS_THREADS) (&warp_hist[0][0])[i] = 0;
+    for (int w = 0; w < RS_WARPS; w++)
+        for (int d = threadIdx.x; d < radix; d += RS_THREADS) warp_hist[w][d] = 0;
     __syncthreads();
     const int64_t warp_base = (int64_t)blockIdx.x * RS_TILE + (int64_t)warp * (RS_ITEMS * 32);
-    uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+    const uint32_t dmask = (uint32_t)radix - 1u;
+    unsigned long long e[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];
+#pragma unroll
+    for (int it = 0; it < RS_ITEMS; it++) {   // all loads first: RS_ITEMS independent requests in flight
+        int64_t i = warp_base + it * 32 + lane;
+        e[it] = i < n ? __ldg(in + i) : 0ull;
+    }
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         int64_t i = warp_base + it * 32 + lane;
         bool ok = i < n;
-        key[it] = ok ? __ldg(keys_in + i) : 0u;
         uint32_t okmask = __ballot_sync(0xffffffffu, ok);
         rank[it] = 0;
         if (ok) {
-            uint32_t d = (key[it] >> shift) & 0xFFu;
-            uint32_t peers = __match_any_sync(okmask, d);
+            uint32_t d = (elem_key(e[it]) >> shift) & dmask;
+            uint32_t peers = digit_peers<BITS>(d, okmask);
             uint32_t before = __popc(peers & ((1u << lane) - 1u));
             int leader = __ffs(peers) - 1;
             uint32_t base = 0;
@@ -78,12 +104,12 @@ __global__ void __launch_bounds__(RS_THREADS)
         __syncwarp();
     }
     __syncthreads();
-    {   // digit = threadIdx.x: turn the per-warp counts into start positions in the output
-        uint32_t run = offsets[(int64_t)threadIdx.x * n_tiles + blockIdx.x];
+    for (int d = threadIdx.x; d < radix; d += RS_THREADS) {   // per-warp counts -> start positions in the output
+        uint32_t run = offsets[(int64_t)d * n_tiles + blockIdx.x];
 #pragma unroll
         for (int w = 0; w < RS_WARPS; w++) {
-            uint32_t c = warp_hist[w][threadIdx.x];
-            warp_hist[w][threadIdx.x] = run;
+            uint32_t c = warp_hist[w][d];
+            warp_hist[w][d] = run;
             run += c;
         }
     }
@@ -91,79 +117,127 @@ __global__ void __launch_bounds__(RS_THREADS)
 #pragma unroll
     for (int it = 0; it < RS_ITEMS; it++) {
         int64_t i = warp_base + it * 32 + lane;
-        if (i < n) {
-            uint32_t d = (key[it] >> shift) & 0xFFu;
-            uint32_t pos = warp_hist[warp][d] + rank[it];
-            keys_out[pos] = key[it];
-            vals_out[pos] = first_pass ? (uint32_t)i : __ldg(vals_in + i);
+        if (i < n) out[warp_hist[warp][(elem_key(e[it]) >> shift) & dmask] + rank[it]] = e[it];
+    }
+}
+
+// Stable sort of the packed elements by the low `bits` bits of their key.  On return *sorted points into the
+// scratch buffers owned by `bufs`.
+struct SortBuffers {
+    Scratch elems[2], hist;
+};
+
+static int radix_sort_elems(SortBuffers &bufs, int64_t n, int bits, const unsigned long long **sorted, cudaStream_t s) {
+    // bufs.elems[0] holds the input
+    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
+    if (bits < 1) bits = 1;
+    const int passes = (bits + 9) / 10;
+    int digit_bits = (bits + passes - 1) / passes;   // <= 10
+    if (digit_bits < 8) digit_bits = 8;
+    const int radix = 1 << digit_bits;
+    GKI_TRY(bufs.elems[1].alloc((size_t)n * 8, s));
+    GKI_TRY(bufs.hist.alloc((size_t)radix * n_tiles * 4, s));
+    int cur = 0;
+    for (int p = 0; p < passes; p++) {
+        const int shift = digit_bits * p;
+        radix_hist_kernel<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(bufs.elems[cur].as<unsigned long long>(), n, shift, radix,
+                                                                  bufs.hist.as<uint32_t>(), n_tiles);
+        GKI_CHECK_LAUNCH();
+        GKI_TRY(exclusive_scan_u32(bufs.hist.as<uint32_t>(), bufs.hist.as<uint32_t>(), (int64_t)radix * n_tiles, nullptr, s));
+        const unsigned long long *src = bufs.elems[cur].as<unsigned long long>();
+        unsigned long long *dst = bufs.elems[cur ^ 1].as<unsigned long long>();
+        if (digit_bits == 8) radix_scatter_kernel<8><<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(src, n, shift, bufs.hist.as<uint32_t>(), n_tiles, dst);
+        else if (digit_bits == 9) radix_scatter_kernel<9><<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(src, n, shift, bufs.hist.as<uint32_t>(), n_tiles, dst);
+        else radix_scatter_kernel<10><<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(src, n, shift, bufs.hist.as<uint32_t>(), n_tiles, dst);
+        GKI_CHECK_LAUNCH();
+        cur ^= 1;
+    }
+    *sorted = bufs.elems[cur].as<unsigned long long>();
+    return GKI_OK;
+}
+
+// run heads: hashes_to_index[bucket] = first sorted position (cfki:444-454).  The head also walks its run (runs are a
+// handful of entries unless modulo is tiny) and writes n_kmers[bucket]; runs longer than RUN_WALK are left to
+// run_tails_kernel, which is only launched when *long_runs != 0.
+constexpr int RUN_WALK = 32;
+__global__ void run_heads_kernel(const unsigned long long *__restrict__ sorted, int64_t n, int32_t *__restrict__ h2i,
+                                 uint32_t *__restrict__ nk, unsigned int *__restrict__ long_runs) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t k = elem_key(__ldg(sorted + i));
+        if (i == 0 || elem_key(__ldg(sorted + i - 1)) != k) {
+            h2i[k] = (int32_t)i;
+            int len = 1;
+            while (len <= RUN_WALK && i + len < n && elem_key(__ldg(sorted + i + len)) == k) len++;
+            if (len <= RUN_WALK) nk[k] = (uint32_t)len;
+            else *long_runs = 1u;
+        }
+    }
+}
+// run tails: n_kmers[bucket] = run length (cfki:455-457)
+__global__ void run_tails_kernel(const unsigned long long *__restrict__ sorted, int64_t n, const int32_t *__restrict__ h2i,
+                                 uint32_t *__restrict__ nk, const unsigned int *__restrict__ long_runs) {
+    if (*long_runs == 0u) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t k = elem_key(__ldg(sorted + i));
+        if (i == n - 1 || elem_key(__ldg(sorted + i + 1)) != k) nk[k] = (uint32_t)(i + 1 - h2i[k]);
+    }
+}
+
+// cfki:436-440: the payload columns follow the sort.  Gathering four columns through a random permutation costs four
+// HBM fetches (64-128 B each) per entry; interleaving them first into one record per entry (streaming pass) makes it
+// ONE fetch per entry.  Record = {kmer, node, af} (16 B) or {kmer, ref, node, af, pad} (32 B) when ref_offsets move too.
+template <bool WITH_REF>
+__global__ void pack_records_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes,
+                                    const uint64_t *__restrict__ ref, const float *__restrict__ af, uint4 *__restrict__ rec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t km = __ldg(kmers + i);
+        uint32_t nd = nodes ? __ldg(nodes + i) : 0u;
+        uint32_t a = af ? __float_as_uint(__ldg(af + i)) : 0u;
+        if (WITH_REF) {
+            uint64_t r = __ldg(ref + i);
+            rec[2 * i] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), (uint32_t)r, (uint32_t)(r >> 32));
+            rec[2 * i + 1] = make_uint4(nd, a, 0u, 0u);
+        } else {
+            rec[i] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), nd, a);
         }
     }
 }
 
-__global__ void iota_kernel(uint32_t *__restrict__ v, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
-}
-
-// Stable sort of (keys, identity) by the low `bits` bits.  On return *keys_sorted / *perm point into the
-// scratch buffers owned by `bufs`.
-struct SortBuffers {
-    Scratch keys[2], vals[2], hist;
-};
-
-static int radix_sort_pairs(SortBuffers &bufs, int64_t n, int bits, const uint32_t **keys_sorted, const uint32_t **perm,
-                            cudaStream_t s) {
-    // bufs.keys[0] holds the input keys
-    const int64_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-    int passes = (bits + 7) / 8;
-    if (passes < 1) passes = 1;
-    GKI_TRY(bufs.keys[1].alloc((size_t)n * 4, s));
-    GKI_TRY(bufs.vals[0].alloc((size_t)n * 4, s));
-    GKI_TRY(bufs.vals[1].alloc((size_t)n * 4, s));
-    GKI_TRY(bufs.hist.alloc((size_t)RADIX * n_tiles * 4, s));
-    int cur = 0;
-    for (int p = 0; p < passes; p++) {
-        int shift = 8 * p;
-        radix_hist_kernel<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(bufs.keys[cur].as<uint32_t>(), n, shift, bufs.hist.as<uint32_t>(), n_tiles);
-        GKI_CHECK_LAUNCH();
-        GKI_TRY(exclusive_scan_u32(bufs.hist.as<uint32_t>(), bufs.hist.as<uint32_t>(), (int64_t)RADIX * n_tiles, nullptr, s));
-        radix_scatter_kernel<<<(unsigned)n_tiles, RS_THREADS, 0, s>>>(bufs.keys[cur].as<uint32_t>(), bufs.vals[cur].as<uint32_t>(), n, shift,
-                                                                      bufs.hist.as<uint32_t>(), n_tiles, bufs.keys[cur ^ 1].as<uint32_t>(),
-                                                                      bufs.vals[cur ^ 1].as<uint32_t>(), p == 0);
-        GKI_CHECK_LAUNCH();
-        cur ^= 1;
-    }
-    *keys_sorted = bufs.keys[cur].as<uint32_t>();
-    *perm = bufs.vals[cur].as<uint32_t>();
-    return GKI_OK;
-}
-
-// run heads: hashes_to_index[bucket] = first sorted position (cfki:444-454)
-__global__ void run_heads_kernel(const uint32_t *__restrict__ keys, int64_t n, int32_t *__restrict__ h2i) {
+template <bool WITH_REF>
+__global__ void gather_records_kernel(const unsigned long long *__restrict__ sorted, int64_t n, const uint4 *__restrict__ rec,
+                                      uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o, uint64_t *__restrict__ ref_o,
+                                      float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t k = __ldg(keys + i);
-        if (i == 0 || __ldg(keys + i - 1) != k) h2i[k] = (int32_t)i;
-    }
-}
-// run tails: n_kmers[bucket] = run length (cfki:455-457)
-__global__ void run_tails_kernel(const uint32_t *__restrict__ keys, int64_t n, const int32_t *__restrict__ h2i,
-                                 uint32_t *__restrict__ nk) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t k = __ldg(keys + i);
-        if (i == n - 1 || __ldg(keys + i + 1) != k) nk[k] = (uint32_t)(i + 1 - h2i[k]);
+        const uint32_t p = elem_idx(__ldg(sorted + i));
+        uint4 a = __ldg(rec + (WITH_REF ? 2 * (int64_t)p : (int64_t)p));
+        uint32_t nd, afb;
+        if (WITH_REF) {
+            uint4 b = __ldg(rec + 2 * (int64_t)p + 1);
+            if (ref_o) ref_o[i] = ((uint64_t)a.w << 32) | a.z;
+            nd = b.x;
+            afb = b.y;
+        } else {
+            nd = a.z;
+            afb = a.w;
+        }
+        if (kmers_o) kmers_o[i] = ((uint64_t)a.y << 32) | a.x;
+        if (nodes_o) nodes_o[i] = nd;
+        if (af_o) af_o[i] = __uint_as_float(afb);
+        if (perm_o) perm_o[i] = p;
     }
 }
 
-// cfki:436-440: the payload columns follow the sort
-__global__ void gather_payload_kernel(const uint32_t *__restrict__ perm, int64_t n, const uint64_t *__restrict__ kmers,
+__global__ void gather_payload_kernel(const unsigned long long *__restrict__ sorted, int64_t n, const uint64_t *__restrict__ kmers,
                                       const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
                                       const float *__restrict__ af, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o,
-                                      uint64_t *__restrict__ ref_o, float *__restrict__ af_o) {
+                                      uint64_t *__restrict__ ref_o, float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t p = __ldg(perm + i);
+        uint32_t p = elem_idx(__ldg(sorted + i));
         if (kmers_o) kmers_o[i] = __ldg(kmers + p);
         if (nodes_o) nodes_o[i] = __ldg(nodes + p);
         if (ref_o) ref_o[i] = __ldg(ref + p);
         if (af_o) af_o[i] = __ldg(af + p);
+        if (perm_o) perm_o[i] = p;
     }
 }
 
@@ -174,11 +248,11 @@ template <typename T> __global__ void gather_kernel(const T *__restrict__ src, c
 
 // set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
 // (k-mer, ref_offset) pair
-__global__ void freq_first_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kmers,
+__global__ void freq_first_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
                                   const uint64_t *__restrict__ ref, const int32_t *__restrict__ h2i, int64_t n,
                                   uint8_t *__restrict__ first) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = h2i[__ldg(keys + e)];
+        int64_t s = h2i[elem_key(__ldg(sorted + e))];
         uint64_t km = __ldg(kmers + e);
         uint64_t ro = ref ? __ldg(ref + e) : 0ull;
         uint8_t f = 1;
@@ -192,11 +266,11 @@ __global__ void freq_first_kernel(const uint32_t *__restrict__ keys, const uint6
     }
 }
 // pass 2: frequency[e] = number of first-flagged entries of the bucket with the same k-mer (uint16, wraps)
-__global__ void freq_count_kernel(const uint32_t *__restrict__ keys, const uint64_t *__restrict__ kmers,
+__global__ void freq_count_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
                                   const int32_t *__restrict__ h2i, const uint32_t *__restrict__ nk, const uint8_t *__restrict__ first,
                                   int64_t n, uint16_t *__restrict__ freq) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t b = __ldg(keys + e);
+        uint32_t b = elem_key(__ldg(sorted + e));
         int64_t s = h2i[b], t = s + nk[b];
         uint64_t km = __ldg(kmers + e);
         uint32_t c = 0;
@@ -207,15 +281,16 @@ __global__ void freq_count_kernel(const uint32_t *__restrict__ keys, const uint6
 
 // flat_kmers.py:98-125: keep[i] = 0 for the first occurrence of a hash.  After the stable sort by
 // (hash % M) an earlier occurrence of the same hash sits earlier in the same key run.
-__global__ void non_first_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ perm,
-                                 const uint64_t *__restrict__ hashes, int64_t n, uint8_t *__restrict__ keep) {
+__global__ void non_first_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ hashes, int64_t n,
+                                 uint8_t *__restrict__ keep) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t key = __ldg(keys + p);
-        uint32_t me = __ldg(perm + p);
+        unsigned long long mine = __ldg(sorted + p);
+        uint32_t key = elem_key(mine);
+        uint32_t me = elem_idx(mine);
         uint64_t h = __ldg(hashes + me);
         uint8_t seen = 0;
-        for (int64_t c = p - 1; c >= 0 && __ldg(keys + c) == key; c--) {
-            if (__ldg(hashes + __ldg(perm + c)) == h) {
+        for (int64_t c = p - 1; c >= 0 && elem_key(__ldg(sorted + c)) == key; c--) {
+            if (__ldg(hashes + elem_idx(__ldg(sorted + c))) == h) {
                 seen = 1;
                 break;
             }
@@ -233,13 +308,13 @@ static int bit_length(uint64_t v) {
     return b;
 }
 
-static int sort_by_bucket(const uint64_t *d_kmers, int64_t n, uint64_t modulo, SortBuffers &bufs, const uint32_t **keys_sorted,
-                          const uint32_t **perm, cudaStream_t s) {
-    GKI_TRY(bufs.keys[0].alloc((size_t)n * 4, s));
+static int sort_by_bucket(const uint64_t *d_kmers, int64_t n, uint64_t modulo, SortBuffers &bufs, const unsigned long long **sorted,
+                          cudaStream_t s) {
+    GKI_TRY(bufs.elems[0].alloc((size_t)n * 8, s));
     int grid = grid_for(n, 256 * 4, device_info().sms * 16);
-    bucket_keys_kernel<<<grid, 256, 0, s>>>(d_kmers, n, make_fastmod(modulo), bufs.keys[0].as<uint32_t>());
+    bucket_keys_kernel<<<grid, 256, 0, s>>>(d_kmers, n, make_fastmod(modulo), bufs.elems[0].as<unsigned long long>());
     GKI_CHECK_LAUNCH();
-    return radix_sort_pairs(bufs, n, bit_length(modulo - 1), keys_sorted, perm, s);
+    return radix_sort_elems(bufs, n, bit_length(modulo - 1), sorted, s);
 }
 
 }  // namespace gki
@@ -278,15 +353,20 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
     GKI_TRY(o_perm.prepare(perm_out, (size_t)n * 4, s));
 
     SortBuffers bufs;
-    const uint32_t *keys_sorted, *perm;
-    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, bufs, &keys_sorted, &perm, s));
+    const unsigned long long *sorted;
+    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, bufs, &sorted, s));
 
     const int grid_n = grid_for(n, 256 * 4, device_info().sms * 16);
     GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)modulo * 4, s));
     GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)modulo * 4, s));
-    run_heads_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, n, o_h2i.as<int32_t>());
+    Scratch long_runs;
+    GKI_TRY(long_runs.alloc(4, s));
+    GKI_CUDA(cudaMemsetAsync(long_runs.ptr, 0, 4, s));
+    run_heads_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
     GKI_CHECK_LAUNCH();
-    run_tails_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>());
+    // buckets holding more than RUN_WALK entries (tiny modulo, or one heavily repeated k-mer): the tails pass exits
+    // immediately unless the heads pass flagged one
+    run_tails_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
     GKI_CHECK_LAUNCH();
 
     // the frequency pass needs sorted k-mers (and ref offsets) even if the caller did not ask for them
@@ -301,10 +381,28 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
         GKI_TRY(tmp_ref.alloc((size_t)n * 8, s));
         ref_sorted = tmp_ref.as<uint64_t>();
     }
-    gather_payload_kernel<<<grid_n, 256, 0, s>>>(perm, n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(),
-                                                 d_af.as<float>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>());
-    GKI_CHECK_LAUNCH();
-    if (o_perm.dptr) GKI_CUDA(cudaMemcpyAsync(o_perm.dptr, perm, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+    const int payload_columns = (kmers_sorted != nullptr) + (o_nodes.dptr != nullptr) + (ref_sorted != nullptr) + (o_af.dptr != nullptr);
+    if (payload_columns >= 2) {   // one interleaved record per entry: one random HBM fetch instead of one per column
+        const bool with_ref = ref_sorted != nullptr;
+        Scratch records;
+        GKI_TRY(records.alloc((size_t)n * (with_ref ? 32 : 16), s));
+        if (with_ref) {
+            pack_records_kernel<true><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), records.as<uint4>());
+            GKI_CHECK_LAUNCH();
+            gather_records_kernel<true><<<grid_n, 256, 0, s>>>(sorted, n, records.as<uint4>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+        } else {
+            pack_records_kernel<false><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), nullptr, d_af.as<float>(), records.as<uint4>());
+            GKI_CHECK_LAUNCH();
+            gather_records_kernel<false><<<grid_n, 256, 0, s>>>(sorted, n, records.as<uint4>(), kmers_sorted, o_nodes.as<uint32_t>(), nullptr, o_af.as<float>(), o_perm.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+        }
+    } else {
+        gather_payload_kernel<<<grid_n, 256, 0, s>>>(sorted, n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(),
+                                                     d_af.as<float>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(),
+                                                     o_perm.as<uint32_t>());
+        GKI_CHECK_LAUNCH();
+    }
 
     if (freq_out) {
         if (!want_freq) {
@@ -312,9 +410,9 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
         } else {
             Scratch first;
             GKI_TRY(first.alloc((size_t)n, s));
-            freq_first_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>());
+            freq_first_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>());
             GKI_CHECK_LAUNCH();
-            freq_count_kernel<<<grid_n, 256, 0, s>>>(keys_sorted, kmers_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), first.as<uint8_t>(), n,
+            freq_count_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), first.as<uint8_t>(), n,
                                                      o_freq.as<uint16_t>());
             GKI_CHECK_LAUNCH();
         }
@@ -365,9 +463,9 @@ int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *k
     uint64_t m = (uint64_t)(2 * n + 1025) | 1ull;   // sparse odd table size: runs of distinct hashes stay short
     if (m >= (1ull << 32)) m = (1ull << 32) - 1;
     SortBuffers bufs;
-    const uint32_t *keys_sorted, *perm;
-    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, bufs, &keys_sorted, &perm, s));
-    non_first_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(keys_sorted, perm, d_h.as<uint64_t>(), n, o.as<uint8_t>());
+    const unsigned long long *sorted;
+    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, bufs, &sorted, s));
+    non_first_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(sorted, d_h.as<uint64_t>(), n, o.as<uint8_t>());
     GKI_CHECK_LAUNCH();
     GKI_TRY(o.finish(s));
     return call.finish();
