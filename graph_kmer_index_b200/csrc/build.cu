@@ -27,9 +27,40 @@ constexpr int RADIX_MAX = 1024;   // digits of up to 10 bits: a 29-bit bucket id
 __device__ __forceinline__ uint32_t elem_key(unsigned long long e) { return (uint32_t)(e >> 32); }
 __device__ __forceinline__ uint32_t elem_idx(unsigned long long e) { return (uint32_t)e; }
 
-__global__ void bucket_keys_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, unsigned long long *__restrict__ elems) {
+// key = bucket - bucket_lo (whole-index build: bucket_lo = 0; hash-range partitioned build: the rank's first bucket),
+// or, with part_size != 0, key = bucket / part_size (the owner of the bucket range, for the all-to-all)
+__global__ void bucket_keys_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, uint32_t bucket_lo, uint32_t part_size,
+                                   unsigned long long *__restrict__ elems) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t b = fastmod(__ldg(kmers + i), fm);
+        uint32_t key = part_size ? b / part_size : b - bucket_lo;
+        elems[i] = ((unsigned long long)key << 32) | (unsigned long long)(uint32_t)i;
+    }
+}
+
+// first sorted position whose key is >= p, for p = 0..n_parts (bounds[p]); counts follow by difference
+__global__ void part_bounds_kernel(const unsigned long long *__restrict__ sorted, int64_t n, int n_parts, long long *__restrict__ bounds) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > n_parts) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (elem_key(__ldg(sorted + mid)) < (uint32_t)p) lo = mid + 1; else hi = mid;
+    }
+    bounds[p] = lo;
+}
+__global__ void part_counts_kernel(const long long *__restrict__ bounds, int n_parts, long long *__restrict__ counts) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_parts) counts[p] = bounds[p + 1] - bounds[p];
+}
+__global__ void extract_perm_kernel(const unsigned long long *__restrict__ sorted, int64_t n, uint32_t *__restrict__ perm) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        elems[i] = ((unsigned long long)fastmod(__ldg(kmers + i), fm) << 32) | (unsigned long long)(uint32_t)i;
+        perm[i] = elem_idx(__ldg(sorted + i));
+}
+// hashes_to_index holds local positions after a range build; the global position adds the entries of the lower ranks
+__global__ void add_offset_nonempty_kernel(int32_t *__restrict__ h2i, const uint32_t *__restrict__ nk, int64_t len, int32_t offset) {
+    for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < len; b += (int64_t)gridDim.x * blockDim.x)
+        if (nk[b]) h2i[b] += offset;
 }
 
 // per-tile digit histogram, stored digit-major: hist[d * n_tiles + tile]
@@ -308,13 +339,13 @@ static int bit_length(uint64_t v) {
     return b;
 }
 
-static int sort_by_bucket(const uint64_t *d_kmers, int64_t n, uint64_t modulo, SortBuffers &bufs, const unsigned long long **sorted,
-                          cudaStream_t s) {
+static int sort_by_bucket(const uint64_t *d_kmers, int64_t n, uint64_t modulo, uint32_t bucket_lo, uint32_t part_size, uint64_t max_key,
+                          SortBuffers &bufs, const unsigned long long **sorted, cudaStream_t s) {
     GKI_TRY(bufs.elems[0].alloc((size_t)n * 8, s));
     int grid = grid_for(n, 256 * 4, device_info().sms * 16);
-    bucket_keys_kernel<<<grid, 256, 0, s>>>(d_kmers, n, make_fastmod(modulo), bufs.elems[0].as<unsigned long long>());
+    bucket_keys_kernel<<<grid, 256, 0, s>>>(d_kmers, n, make_fastmod(modulo), bucket_lo, part_size, bufs.elems[0].as<unsigned long long>());
     GKI_CHECK_LAUNCH();
-    return radix_sort_elems(bufs, n, bit_length(modulo - 1), sorted, s);
+    return radix_sort_elems(bufs, n, bit_length(max_key), sorted, s);
 }
 
 }  // namespace gki
@@ -323,12 +354,15 @@ using namespace gki;
 
 extern "C" {
 
-int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
-                    uint64_t modulo, int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,
-                    uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out, uint32_t *perm_out,
-                    gki_stream_t stream) {
+static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
+                       uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset, int32_t flags,
+                       int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out,
+                       float *af_out, uint16_t *freq_out, uint32_t *perm_out, gki_stream_t stream) {
     CallScope call(stream);
     cudaStream_t s = call.stream;
+    GKI_REQUIRE(bucket_lo < bucket_hi && bucket_hi <= modulo, GKI_ERR_INVALID, "gki_index_build: bad bucket range");
+    GKI_REQUIRE(position_offset >= 0 && position_offset + n < (1ll << 31), GKI_ERR_UNSUPPORTED, "gki_index_build: positions must stay < 2^31");
+    const uint64_t table_len = bucket_hi - bucket_lo;
     GKI_REQUIRE(n >= 1, GKI_ERR_INVALID, "gki_index_build: empty FlatKmers (the reference raises IndexError, cfki:455)");
     GKI_REQUIRE(n < (1ll << 31), GKI_ERR_UNSUPPORTED, "gki_index_build: n must be < 2^31 (int32 hashes_to_index, cfki:453)");
     GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build: need 1 <= modulo < 2^32");
@@ -343,8 +377,8 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
     GKI_TRY(d_ref.stage((ref_out || want_freq) ? ref_offsets : nullptr, (size_t)n * 8, s));
     GKI_TRY(d_af.stage(af_out ? af : nullptr, (size_t)n * 4, s));
     DevOut o_h2i, o_nk, o_kmers, o_nodes, o_ref, o_af, o_freq, o_perm;
-    GKI_TRY(o_h2i.prepare(hashes_to_index, (size_t)modulo * 4, s));
-    GKI_TRY(o_nk.prepare(n_kmers, (size_t)modulo * 4, s));
+    GKI_TRY(o_h2i.prepare(hashes_to_index, (size_t)table_len * 4, s));
+    GKI_TRY(o_nk.prepare(n_kmers, (size_t)table_len * 4, s));
     GKI_TRY(o_kmers.prepare(kmers_out, (size_t)n * 8, s));
     GKI_TRY(o_nodes.prepare(nodes_out, (size_t)n * 4, s));
     GKI_TRY(o_ref.prepare(ref_out, (size_t)n * 8, s));
@@ -354,11 +388,12 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
 
     SortBuffers bufs;
     const unsigned long long *sorted;
-    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, bufs, &sorted, s));
+    // (a k-mer outside [bucket_lo, bucket_hi) would wrap to a huge key; the caller routes entries by range first)
+    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, (uint32_t)bucket_lo, 0u, table_len - 1, bufs, &sorted, s));
 
     const int grid_n = grid_for(n, 256 * 4, device_info().sms * 16);
-    GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)modulo * 4, s));
-    GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)modulo * 4, s));
+    GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)table_len * 4, s));
+    GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)table_len * 4, s));
     Scratch long_runs;
     GKI_TRY(long_runs.alloc(4, s));
     GKI_CUDA(cudaMemsetAsync(long_runs.ptr, 0, 4, s));
@@ -417,6 +452,11 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
             GKI_CHECK_LAUNCH();
         }
     }
+    if (position_offset) {
+        add_offset_nonempty_kernel<<<grid_for((int64_t)table_len, 256 * 4, device_info().sms * 16), 256, 0, s>>>(
+            o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), (int64_t)table_len, (int32_t)position_offset);
+        GKI_CHECK_LAUNCH();
+    }
     GKI_TRY(o_h2i.finish(s));
     GKI_TRY(o_nk.finish(s));
     GKI_TRY(o_kmers.finish(s));
@@ -425,6 +465,57 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
     GKI_TRY(o_af.finish(s));
     GKI_TRY(o_freq.finish(s));
     GKI_TRY(o_perm.finish(s));
+    return call.finish();
+}
+
+int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
+                    uint64_t modulo, int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,
+                    uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out, uint32_t *perm_out,
+                    gki_stream_t stream) {
+    GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build: need 1 <= modulo < 2^32");
+    return build_range(kmers, nodes, ref_offsets, af, n, modulo, 0, modulo, 0, flags, hashes_to_index, n_kmers, kmers_out, nodes_out,
+                       ref_out, af_out, freq_out, perm_out, stream);
+}
+
+int gki_index_build_range(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
+                          uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset, int32_t flags,
+                          int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out,
+                          float *af_out, uint16_t *freq_out, gki_stream_t stream) {
+    GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build_range: need 1 <= modulo < 2^32");
+    return build_range(kmers, nodes, ref_offsets, af, n, modulo, bucket_lo, bucket_hi, position_offset, flags, hashes_to_index, n_kmers,
+                       kmers_out, nodes_out, ref_out, af_out, freq_out, nullptr, stream);
+}
+
+int gki_partition_by_bucket_range(const uint64_t *kmers, int64_t n, uint64_t modulo, int32_t n_parts, uint32_t *perm_out,
+                                  int64_t *counts_out, gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    GKI_REQUIRE(n >= 0 && n < (1ll << 31) && n_parts >= 1 && n_parts <= 1024 && modulo >= 1 && modulo < (1ull << 32) && counts_out &&
+                    (n == 0 || (kmers && perm_out)),
+                GKI_ERR_INVALID, "gki_partition_by_bucket_range: bad arguments");
+    DevOut o_counts;
+    GKI_TRY(o_counts.prepare(counts_out, (size_t)n_parts * 8, s));
+    GKI_CUDA(cudaMemsetAsync(o_counts.dptr, 0, (size_t)n_parts * 8, s));
+    if (n > 0) {
+        DevIn d_kmers;
+        DevOut o_perm;
+        GKI_TRY(d_kmers.stage(kmers, (size_t)n * 8, s));
+        GKI_TRY(o_perm.prepare(perm_out, (size_t)n * 4, s));
+        const uint32_t part_size = (uint32_t)((modulo + n_parts - 1) / n_parts);
+        SortBuffers bufs;
+        const unsigned long long *sorted;
+        GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, 0u, part_size, (uint64_t)n_parts - 1, bufs, &sorted, s));
+        Scratch bounds;
+        GKI_TRY(bounds.alloc((size_t)(n_parts + 1) * 8, s));
+        part_bounds_kernel<<<(n_parts + 1 + 255) / 256, 256, 0, s>>>(sorted, n, n_parts, bounds.as<long long>());
+        GKI_CHECK_LAUNCH();
+        part_counts_kernel<<<(n_parts + 255) / 256, 256, 0, s>>>(bounds.as<long long>(), n_parts, (long long *)o_counts.dptr);
+        GKI_CHECK_LAUNCH();
+        extract_perm_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(sorted, n, o_perm.as<uint32_t>());
+        GKI_CHECK_LAUNCH();
+        GKI_TRY(o_perm.finish(s));
+    }
+    GKI_TRY(o_counts.finish(s));
     return call.finish();
 }
 
@@ -464,7 +555,7 @@ int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *k
     if (m >= (1ull << 32)) m = (1ull << 32) - 1;
     SortBuffers bufs;
     const unsigned long long *sorted;
-    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, bufs, &sorted, s));
+    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, 0u, 0u, m - 1, bufs, &sorted, s));
     non_first_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(sorted, d_h.as<uint64_t>(), n, o.as<uint8_t>());
     GKI_CHECK_LAUNCH();
     GKI_TRY(o.finish(s));

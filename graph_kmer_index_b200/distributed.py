@@ -59,3 +59,100 @@ def count_reads_sharded(device_index, reads, k, min_nodes=0, both_strands=True, 
         counts.copy_(torch.from_numpy(device_index.node_counts(min_nodes)))
     allreduce_node_counts(counts)
     return counts.cpu().numpy()
+
+
+def bucket_range(modulo, rank, world_size):
+    """Buckets owned by `rank` in the hash-range partitioned build: [lo, hi)."""
+    part = (int(modulo) + world_size - 1) // world_size
+    return min(rank * part, int(modulo)), min((rank + 1) * part, int(modulo))
+
+
+def build_index_partitioned(hashes, nodes, ref_offsets, allele_frequencies, modulo, skip_frequencies=True, replicate=False):
+    """Hash-range partitioned index build over the ranks of the default process group (NCCL, one process per GPU).
+
+    Every rank passes its own shard of the FlatKmers as device tensors (int64 / int32 / int64 / float32 views of the
+    reference's uint64 / uint32 / uint64 / float32 columns); the global input order is rank-major.  Entries travel to
+    the rank that owns their bucket range (one all-to-all per column), each rank builds its slice with
+    gki_index_build_range, and the slices concatenated in rank order are exactly the single-GPU index of the
+    concatenated FlatKmers.  Returns a dict of device tensors: the local slice, or -- with replicate=True -- the whole
+    index on every rank."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    dev = hashes.device
+    n = int(hashes.shape[0])
+    stream = _lib.current_stream()
+    cols = {"kmers": hashes, "nodes": nodes, "ref_offsets": ref_offsets, "allele_frequencies": allele_frequencies}
+    cols = {k: v for k, v in cols.items() if v is not None}
+    # 1. order the local entries by owner
+    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    _lib.call("gki_partition_by_bucket_range", _lib.ptr(hashes), n, int(modulo), world, _lib.ptr(perm), _lib.ptr(counts), stream)
+    send = {}
+    for name, col in cols.items():
+        out = torch.empty_like(col)
+        _lib.call("gki_gather", _lib.ptr(col), col.element_size(), _lib.ptr(perm), n, _lib.ptr(out), stream)
+        send[name] = out
+    # 2. all-to-all by bucket range
+    recv_counts = torch.empty_like(counts)
+    if world > 1:
+        dist.all_to_all_single(recv_counts, counts)
+    else:
+        recv_counts.copy_(counts)
+    in_splits, out_splits = counts.tolist(), recv_counts.tolist()
+    n_local = int(sum(out_splits))
+    recv = {}
+    for name, col in send.items():
+        buf = torch.empty(n_local, dtype=col.dtype, device=dev)
+        if world > 1:
+            dist.all_to_all_single(buf, col, output_split_sizes=out_splits, input_split_sizes=in_splits)
+        else:
+            buf.copy_(col)
+        recv[name] = buf
+    # 3. global position of the first local entry = entries owned by lower ranks
+    totals = torch.zeros(world, dtype=torch.int64, device=dev)
+    totals[rank] = n_local
+    if world > 1:
+        dist.all_reduce(totals)
+    totals = totals.tolist()
+    offset = int(sum(totals[:rank]))
+    # 4. local slice
+    lo, hi = bucket_range(modulo, rank, world)
+    h2i = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+    nk = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+    outs = {name: torch.empty_like(col) for name, col in recv.items()}
+    freq = torch.empty(n_local, dtype=torch.int16, device=dev)
+    if n_local:
+        _lib.call("gki_index_build_range", _lib.ptr(recv["kmers"]), _lib.ptr(recv.get("nodes")), _lib.ptr(recv.get("ref_offsets")),
+                  _lib.ptr(recv.get("allele_frequencies")), n_local, int(modulo), lo, hi, offset,
+                  _lib.GKI_BUILD_SKIP_FREQUENCIES if skip_frequencies else 0, _lib.ptr(h2i), _lib.ptr(nk), _lib.ptr(outs["kmers"]),
+                  _lib.ptr(outs.get("nodes")), _lib.ptr(outs.get("ref_offsets")), _lib.ptr(outs.get("allele_frequencies")), _lib.ptr(freq), stream)
+    else:
+        h2i.zero_()
+        nk.zero_()
+    local = dict(hashes_to_index=h2i, n_kmers=nk, frequencies=freq, bucket_range=(lo, hi), position_offset=offset, n_total=int(sum(totals)), **outs)
+    if not replicate or world == 1:
+        return local
+    # 5. replicate: every rank broadcasts its slice into the full arrays
+    n_total = int(sum(totals))
+    full = dict(hashes_to_index=torch.empty(int(modulo), dtype=torch.int32, device=dev),
+                n_kmers=torch.empty(int(modulo), dtype=torch.int32, device=dev),
+                frequencies=torch.empty(n_total, dtype=torch.int16, device=dev))
+    for name, col in outs.items():
+        full[name] = torch.empty(n_total, dtype=col.dtype, device=dev)
+    pos = 0
+    for r in range(world):
+        rlo, rhi = bucket_range(modulo, r, world)
+        slices = [(name, full[name][rlo:rhi]) for name in ("hashes_to_index", "n_kmers")]
+        slices += [(name, full[name][pos:pos + totals[r]]) for name in ["frequencies"] + list(outs)]
+        for name, sl in slices:
+            if sl.numel() == 0:
+                continue
+            if r == rank:
+                sl.copy_(local[name])
+            dist.broadcast(sl.view(torch.uint8), src=r)      # byte view: NCCL has no int16
+        pos += totals[r]
+    full.update(bucket_range=(0, int(modulo)), position_offset=0, n_total=n_total)
+    return full

@@ -93,6 +93,21 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
                     uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out,
                     uint32_t *perm_out, gki_stream_t stream);
 
+/* Hash-range partitioned build (the reference's closest analogue is the per-chunk index + merge of
+ * command_line_interface.py:588-620).  Rank p of n_parts owns buckets [p*S, min((p+1)*S, modulo)), S = ceil(modulo/n_parts).
+ * Step 1, on every rank: order the local FlatKmers by owner (stable; input order kept inside a part).
+ *   perm_out[n] u32, counts_out[n_parts] i64.  The caller gathers its columns through perm_out (gki_gather) and
+ *   exchanges them (all-to-all by counts).
+ * Step 2, on every rank: build the slice of the index for its bucket range from the received entries (every k-mer must
+ *   fall in the range).  Tables have bucket_hi-bucket_lo entries; hashes_to_index of non-empty buckets gets
+ *   position_offset (= entries owned by lower ranks) added, so the concatenation over ranks IS the global index. */
+int gki_partition_by_bucket_range(const uint64_t *kmers, int64_t n, uint64_t modulo, int32_t n_parts, uint32_t *perm_out,
+                                  int64_t *counts_out, gki_stream_t stream);
+int gki_index_build_range(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af,
+                          int64_t n, uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset,
+                          int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,
+                          uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out, gki_stream_t stream);
+
 /* out[i] = src[perm[i]] for items of item_size in {1,2,4,8} bytes (cfki:436-440 for any dtype). */
 int gki_gather(const void *src, int32_t item_size, const uint32_t *perm, int64_t n, void *out, gki_stream_t stream);
 

@@ -313,3 +313,59 @@ def test_large_modulo_device_build(gki):
     sel = torch.from_numpy(ub).to(dev)
     assert np.array_equal(h2i[sel].cpu().numpy(), first) and np.array_equal(nk[sel].cpu().numpy(), cnt)
     assert int((nk != 0).sum()) == len(ub) and int((h2i != 0).sum()) <= len(ub)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_partitioned_build_emulated_on_one_gpu(gki, world):
+    """hash-range partitioned build with the ranks emulated one after another on one device: partition by
+    owner -> exchange -> per-range build; the slices concatenated in rank order are the oracle's single index"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    from graph_kmer_index_b200.distributed import bucket_range, shard_bounds
+    n, modulo, k = 50_000, 100_003, 31
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 777, k)
+    hashes = hashes.copy()
+    hashes[::17] = hashes[3]                     # a heavy k-mer: one bucket far longer than the others
+    want = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=False)
+    dev = torch.device("cuda")
+    shards = [shard_bounds(n, r, world) for r in range(world)]
+    sent = []                                   # sent[src][dst] = dict of column chunks
+    for lo, hi in shards:
+        cols = dict(kmers=torch.from_numpy(hashes[lo:hi].view(np.int64)).to(dev), nodes=torch.from_numpy(nodes[lo:hi].view(np.int32)).to(dev),
+                    ref=torch.from_numpy(ref[lo:hi].view(np.int64)).to(dev), af=torch.from_numpy(af[lo:hi]).to(dev))
+        m = hi - lo
+        perm = torch.empty(m, dtype=torch.int32, device=dev)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        _lib.call("gki_partition_by_bucket_range", _lib.ptr(cols["kmers"]), m, modulo, world, _lib.ptr(perm), _lib.ptr(counts), None)
+        torch.cuda.synchronize()
+        assert int(counts.sum()) == m
+        bounds = np.concatenate([[0], np.cumsum(counts.cpu().numpy())])
+        g = {}
+        for name, col in cols.items():
+            out = torch.empty_like(col)
+            _lib.call("gki_gather", _lib.ptr(col), col.element_size(), _lib.ptr(perm), m, _lib.ptr(out), None)
+            g[name] = out
+        sent.append([{name: g[name][bounds[d]:bounds[d + 1]] for name in g} for d in range(world)])
+    got = {key: [] for key in ("h2i", "nk", "kmers", "nodes", "ref", "af", "freq")}
+    offset = 0
+    for r in range(world):
+        recv = {name: torch.cat([sent[src][r][name] for src in range(world)]).contiguous() for name in ("kmers", "nodes", "ref", "af")}
+        m = int(recv["kmers"].shape[0])
+        lo, hi = bucket_range(modulo, r, world)
+        h2i = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+        nk = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+        o = {name: torch.empty_like(col) for name, col in recv.items()}
+        fr = torch.empty(m, dtype=torch.int16, device=dev)
+        if m:
+            _lib.call("gki_index_build_range", _lib.ptr(recv["kmers"]), _lib.ptr(recv["nodes"]), _lib.ptr(recv["ref"]), _lib.ptr(recv["af"]), m, modulo,
+                      lo, hi, offset, 0, _lib.ptr(h2i), _lib.ptr(nk), _lib.ptr(o["kmers"]), _lib.ptr(o["nodes"]), _lib.ptr(o["ref"]), _lib.ptr(o["af"]),
+                      _lib.ptr(fr), None)
+        torch.cuda.synchronize()
+        offset += m
+        for key, t in (("h2i", h2i), ("nk", nk), ("kmers", o["kmers"]), ("nodes", o["nodes"]), ("ref", o["ref"]), ("af", o["af"]), ("freq", fr)):
+            got[key].append(t.cpu().numpy())
+    cat = {key: np.concatenate(v) for key, v in got.items()}
+    assert np.array_equal(cat["h2i"], want["_hashes_to_index"]) and np.array_equal(cat["nk"].view(np.uint32), want["_n_kmers"])
+    assert np.array_equal(cat["kmers"].view(np.uint64), want["_kmers"]) and np.array_equal(cat["nodes"].view(np.uint32), want["_nodes"])
+    assert np.array_equal(cat["ref"].view(np.uint64), want["_ref_offsets"]) and np.array_equal(cat["af"], want["_allele_frequencies"])
+    assert np.array_equal(cat["freq"].view(np.uint16), want["_frequencies"])

@@ -28,6 +28,19 @@ WORKER = textwrap.dedent("""
     got = distributed.count_reads_sharded(dev, reads, k, min_nodes=n_nodes)
     want = c_oracle.read_node_counts(idx, reads, k, n_nodes)
     assert np.array_equal(got, want), (rank, float(got.sum()), float(want.sum()))
+    # hash-range partitioned build: every rank contributes a shard of the FlatKmers, the replicated result is the oracle's index
+    lo, hi = distributed.shard_bounds(n, rank, world)
+    t = lambda a, dt: torch.from_numpy(a[lo:hi].view(dt)).cuda()
+    full = distributed.build_index_partitioned(t(hashes, np.int64), t(nodes, np.int32), t(ref, np.int64), torch.from_numpy(af[lo:hi]).cuda(),
+                                               modulo, skip_frequencies=False, replicate=True)
+    w2 = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=False)
+    assert np.array_equal(full["hashes_to_index"].cpu().numpy(), w2["_hashes_to_index"]), rank
+    assert np.array_equal(full["n_kmers"].cpu().numpy().view(np.uint32), w2["_n_kmers"]), rank
+    assert np.array_equal(full["kmers"].cpu().numpy().view(np.uint64), w2["_kmers"]), rank
+    assert np.array_equal(full["nodes"].cpu().numpy().view(np.uint32), w2["_nodes"]), rank
+    assert np.array_equal(full["ref_offsets"].cpu().numpy().view(np.uint64), w2["_ref_offsets"]), rank
+    assert np.array_equal(full["allele_frequencies"].cpu().numpy(), w2["_allele_frequencies"]), rank
+    assert np.array_equal(full["frequencies"].cpu().numpy().view(np.uint16), w2["_frequencies"]), rank
     dist.barrier()
     if rank == 0:
         print("OK", world, int(want.sum()))
