@@ -93,3 +93,64 @@ def reads(n_reads, read_len, n_entries, k=31, p_hit_permille=100, n_permille=0, 
         is_n = (rnd(SEED_NS, flat_idx) % np.uint64(1000)) < np.uint64(n_permille)
         ascii_ = np.where(is_n, np.uint8(ord("N")), ascii_)
     return np.ascontiguousarray(ascii_, dtype=np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Synthetic variant graph (BASELINE config 5): a linear backbone with a bubble every `spacing` bp on
+# average: SNPs (two 1-bp alleles), deletions (ref allele of 1-5 bp vs an empty dummy node) and, optionally, insertions
+# and bubbles nested inside an alternative allele.  Returned in the flat CSR form the finder takes
+# (same keys as oracle/obgraph_standin.Graph.to_arrays()).
+def variant_graph(n_variants, spacing=300, seed=0, p_deletion=0.2, p_insertion=0.0, p_nested=0.0, min_gap=1, tail=40):
+    rng = np.random.default_rng(seed)
+    seqs, edges, linear, af = {}, {}, [], {}
+    nid = 0
+
+    def new(seq, is_lin, freq=1.0):
+        nonlocal nid
+        n = nid
+        nid += 1
+        seqs[n] = seq
+        edges[n] = []
+        af[n] = freq
+        if is_lin:
+            linear.append(n)
+        return n
+
+    def rand_seq(length):
+        return "".join("ACGT"[c] for c in rng.integers(0, 4, length))
+
+    prev = [new(rand_seq(int(rng.integers(max(min_gap, 1), 2 * spacing))), True)]
+    for _ in range(n_variants):
+        f = float(np.round(rng.random() * 0.98 + 0.01, 3))
+        r = rng.random()
+        if r < p_deletion:                               # deletion: ref allele vs dummy
+            ref = new(rand_seq(int(rng.integers(1, 6))), True, 1 - f)
+            alts = [new("", False, f)]
+        elif r < p_deletion + p_insertion:               # insertion: dummy on the linear ref vs inserted sequence
+            ref = new("", False, 1 - f)
+            alts = [new(rand_seq(int(rng.integers(1, 6))), False, f)]
+        else:                                            # SNP (sometimes tri-allelic)
+            ref = new(rand_seq(1), True, 1 - f)
+            alts = [new(rand_seq(1), False, f)]
+            if rng.random() < 0.1:
+                alts.append(new(rand_seq(1), False, f / 2))
+        heads, tails = [ref] + alts, [ref] + alts
+        if rng.random() < p_nested:                      # a SNP nested inside a longer alternative allele
+            a0 = new(rand_seq(int(rng.integers(1, 8))), False, f)
+            s1, s2 = new(rand_seq(1), False, f), new(rand_seq(1), False, f / 3)
+            a1 = new(rand_seq(int(rng.integers(1, 8))), False, f)
+            edges[a0] += [s1, s2]
+            edges[s1].append(a1)
+            edges[s2].append(a1)
+            heads.append(a0)
+            tails.append(a1)
+        for p in prev:
+            edges[p] += heads
+        nxt = new(rand_seq(int(rng.integers(max(min_gap, 1), 2 * spacing))), True)
+        for t in tails:
+            edges[t].append(nxt)
+        prev = [nxt]
+    last = new(rand_seq(tail), True)
+    edges[prev[0]].append(last)
+    # an insertion's dummy bridges two linear-ref nodes: it is a "linear-ref dummy node"
+    return seqs, edges, linear, af

@@ -116,6 +116,9 @@ def install():
             except Exception:
                 _stub(name)
     # attributes the reference imports by name
+    from oracle import obgraph_standin
+    sys.modules["obgraph"].__dict__["Graph"] = obgraph_standin.Graph
+    sys.modules["obgraph.position_id"].__dict__["PositionId"] = obgraph_standin.PositionId
     sys.modules["obgraph"].__dict__.setdefault("Graph", object)
     sys.modules["obgraph"].__dict__.setdefault("VariantNotFoundException", Exception)
     sys.modules["obgraph.position_id"].__dict__.setdefault("PositionId", object)
