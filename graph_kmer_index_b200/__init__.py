@@ -13,3 +13,4 @@ from .cython_kmer_index import CythonKmerIndex  # noqa: F401
 from .read_kmers import ReadKmers  # noqa: F401
 
 __version__ = "0.1.0"
+from .kmer_finder import DenseKmerFinder, CriticalGraphPaths  # noqa: F401,E402

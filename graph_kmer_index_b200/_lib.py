@@ -88,7 +88,11 @@ _SIGNATURES = {
     "gki_synth_reads": [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp],
     "gki_calibrate_random_gather": [c_i64, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_copy": [c_i64, ctypes.POINTER(ctypes.c_float)],
-    "gki_finder_run": None,   # bound in kmer_finder.py when present
+    "gki_critical_paths": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp],
+    "gki_finder_prepare": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32,
+                           c_i32, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_vp],
+    "gki_finder_fill": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gki_finder_destroy": [c_vp],
 }
 EXPORTED = [n for n in _SIGNATURES] + ["gki_last_error", "gki_version", "gki_launch_count"]
 

@@ -183,6 +183,36 @@ int gki_lookup_entries(gki_index_t *index, const uint64_t *queries, int64_t nq, 
 /* `counter[keys]` for arbitrary keys (cfki:40): out[i] = current counter of queries[i], 0 when absent. */
 int gki_query_counts(gki_index_t *index, const uint64_t *queries, int64_t nq, uint32_t *out, gki_stream_t stream);
 
+/* ------------------------------------------------------------------ DenseKmerFinder (BASELINE config 5)
+ * The variant graph is passed as flat CSR arrays: seq_offsets[n_nodes+1] / seq (base codes 0..3; an empty node is a
+ * dummy node), edge_offsets[n_nodes+1] / edges, is_linear[n_nodes] (linear-ref node or linear-ref dummy node),
+ * allele_frequencies[n_nodes] f64, n_in_edges[n_nodes]. */
+typedef struct gki_finder gki_finder_t;
+
+/* critical_graph_paths.py:42-104 CriticalGraphPaths.from_graph.  nodes_out u32 / offsets_out u16 of `capacity`
+ * entries (n_nodes is always enough); *n_out = number of critical positions. */
+int gki_critical_paths(const int64_t *seq_offsets, const int64_t *edge_offsets, const int32_t *edges, const uint8_t *is_linear,
+                       const int32_t *n_in_edges, int64_t n_nodes, const int64_t *chromosome_start_nodes, int32_t n_chromosomes,
+                       int32_t k, uint32_t *nodes_out, uint16_t *offsets_out, int64_t capacity, int64_t *n_out,
+                       gki_stream_t stream);
+
+/* kmer_finder.py:179-434 DenseKmerFinder.find / find_only_kmers_starting_at_position, in two calls: prepare uploads
+ * the graph, walks every chain of starting points once to count the rows (*n_rows); fill walks again and writes the
+ * rows in the reference's order: kmers i64, nodes i32, start_nodes i32, start_offsets i16, allele_frequencies f64
+ * (kf:54-58).  crit_index[crit_len] is CriticalGraphPaths._index (critical_graph_paths.py:11-19); start_nodes /
+ * start_offsets list the starting points in processing order (kf:192-214), chain_first[n_chains+1] groups the ones a
+ * single walker must handle one after the other; store_flags (optional) is only_store_nodes as a per-node byte;
+ * treated_slots (power of two) sizes the set behind `_positions_treated` (kf:311-319). */
+int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int64_t *edge_offsets, const int32_t *edges,
+                       const uint8_t *is_linear, const double *allele_frequencies, int64_t n_nodes, const uint16_t *crit_index,
+                       int64_t crit_len, const uint8_t *store_flags, const int32_t *start_nodes, const int32_t *start_offsets,
+                       int64_t n_starts, const int64_t *chain_first, int64_t n_chains, int32_t k, int32_t max_variant_nodes,
+                       int32_t one_node_per_kmer, int32_t early_stop, int64_t treated_slots, gki_finder_t **out, int64_t *n_rows,
+                       gki_stream_t stream);
+int gki_finder_fill(gki_finder_t *finder, int64_t *kmers, int32_t *nodes, int32_t *start_nodes, int16_t *start_offsets,
+                    double *allele_frequencies, gki_stream_t stream);
+int gki_finder_destroy(gki_finder_t *finder);
+
 /* ------------------------------------------------------------------ synthetic workloads + calibration
  * (bench / test support; graph_kmer_index_b200/synthetic.py is the bit-identical host mirror) */
 int gki_synth_genome(uint8_t *codes, int64_t length, gki_stream_t stream);

@@ -1,0 +1,86 @@
+"""GPU parity of DenseKmerFinder / CriticalGraphPaths: ordered, element-wise equality with the
+unmodified reference on its own test graphs (tests/golden/finder_cases.npz, incl. the 38-row ordered golden of
+test_case1) and with the oracle port on larger random variant graphs."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import finder_oracle
+from oracle.obgraph_standin import Graph
+from test_oracle_finder import load_case
+
+pytestmark = pytest.mark.gpu
+
+KEYS = ("kmers", "nodes", "start_nodes", "start_offsets", "allele_frequencies")
+
+
+def run_product(arrays, opts):
+    import graph_kmer_index_b200 as gki
+    finder = gki.DenseKmerFinder(arrays, opts["k"], max_variant_nodes=opts["max_variant_nodes"],
+                                 only_save_one_node_per_kmer=opts["only_save_one_node_per_kmer"], only_store_nodes=opts["only_store_nodes"])
+    if opts["only_position"] is None:
+        finder.find()
+    else:
+        finder.find_only_kmers_starting_at_position(*opts["only_position"])
+    return finder
+
+
+def test_reference_fixtures():
+    import graph_kmer_index_b200 as gki
+    g = load_golden("finder_cases")
+    for i in range(int(g["n_cases"])):
+        arrays, opts, ref, crit = load_case(g, i)
+        c = gki.CriticalGraphPaths.from_graph(arrays, opts["k"])
+        assert np.array_equal(c.nodes, crit[0]) and np.array_equal(c.offsets, crit[1]), i
+        assert c.nodes.dtype == np.uint32 and c.offsets.dtype == np.uint16
+        finder = run_product(arrays, opts)
+        for key in KEYS:
+            got = finder._results[key]
+            assert got.dtype == ref[key].dtype or key in ("nodes", "kmers"), (i, key, got.dtype, ref[key].dtype)
+            assert np.array_equal(got, ref[key]), (i, key, got[:12], ref[key][:12])
+
+
+def test_reference_test_case1_order():
+    """tests/test_kmer_finder.py:412-475 of the reference: the exact ordered (k-mer, node) list"""
+    import graph_kmer_index_b200 as gki
+    graph = Graph.from_dicts({0: "AGTAGA", 1: "G", 2: "CT", 3: "ACTA", 5: "G", 6: "A", 7: "TCATA"},
+                             {0: [1, 2], 1: [3], 2: [3], 3: [5, 6], 5: [7], 6: [7], 7: []}, [0, 1, 3, 5, 7])
+    finder = gki.DenseKmerFinder(graph, k=3)
+    finder.find()
+    kmers, nodes = finder.get_found_kmers_and_nodes()
+    correct = [("AGT", 0), ("GTA", 0), ("TAG", 0), ("AGA", 0), ("GAG", 0), ("GAG", 1), ("AGA", 0), ("AGA", 1), ("AGA", 3), ("GAC", 1), ("GAC", 3),
+               ("GAC", 0), ("GAC", 2), ("ACT", 0), ("ACT", 2), ("CTA", 2), ("CTA", 3), ("TAC", 2), ("TAC", 3), ("ACT", 3), ("CTA", 3), ("TAG", 3),
+               ("TAG", 5), ("AGT", 3), ("AGT", 5), ("AGT", 7), ("GTC", 5), ("GTC", 7), ("TAA", 3), ("TAA", 6), ("AAT", 3), ("AAT", 6), ("AAT", 7),
+               ("ATC", 6), ("ATC", 7), ("TCA", 7), ("CAT", 7), ("ATA", 7)]
+    assert len(kmers) == len(correct)
+    for kmer, node, (seq, want_node) in zip(kmers, nodes, correct):
+        assert gki.kmer_hash_to_sequence(kmer, 3).upper() == seq and node == want_node
+    flat = finder.get_flat_kmers()
+    assert len(flat._hashes) == 38 and flat._start_nodes.dtype == np.int32
+    flat0 = finder.get_flat_kmers(v="0")
+    assert len(flat0._ref_offsets) == 38
+
+
+@pytest.mark.parametrize("seed,n_variants,spacing,k,kw", [
+    (1, 300, 40, 31, dict(max_variant_nodes=4)),
+    (2, 500, 12, 11, dict(max_variant_nodes=12, p_nested=0.2)),
+    (3, 200, 300, 31, dict(max_variant_nodes=5, only_save_one_node_per_kmer=True)),
+    (4, 400, 6, 5, dict(max_variant_nodes=12, p_nested=0.3)),
+    (6, 400, 8, 7, dict(max_variant_nodes=1)),
+    (5, 50, 2000, 31, dict(max_variant_nodes=5)),          # long nodes: the _process_whole_node rows
+])
+def test_random_graphs_vs_oracle(seed, n_variants, spacing, k, kw):
+    from graph_kmer_index_b200 import synthetic
+    p_nested = kw.pop("p_nested", 0.0)
+    seqs, edges, linear, af = synthetic.variant_graph(n_variants, spacing=spacing, seed=seed, p_deletion=0.25, p_nested=p_nested)
+    arrays = Graph.from_dicts(seqs, edges, linear, af).to_arrays()
+    opts = dict(k=k, max_variant_nodes=kw.get("max_variant_nodes", 4), only_save_one_node_per_kmer=kw.get("only_save_one_node_per_kmer", False),
+                only_store_nodes=None, only_position=None)
+    try:
+        want = finder_oracle.dense_kmer_finder(arrays, **opts)
+    except (AssertionError, OverflowError):
+        pytest.skip("the reference algorithm itself rejects this graph")
+    finder = run_product(arrays, opts)
+    assert len(want["kmers"]) > 1000
+    for key in KEYS:
+        assert np.array_equal(finder._results[key], want[key]), (key, len(finder._results[key]), len(want[key]))
