@@ -12,6 +12,7 @@
 // write rows -- reproduce the reference's row ORDER exactly (chains are concatenated in starting-point order, a chain
 // emits in depth-first order).  The interior of long nodes (the reference's _process_whole_node fast path, kf:349-381)
 // is not walked: the thread reserves the rows and a second, fully parallel kernel fills them.
+#include <vector>
 #include "common.cuh"
 
 namespace gki {
@@ -316,8 +317,7 @@ using namespace gki;
 struct gki_finder {
     FinderGraph g{};
     FinderParams p{};
-    void *dev[16] = {};
-    int n_dev = 0;
+    std::vector<void *> dev;   // every device allocation, freed by gki_finder_destroy
     long long total_rows = 0, total_jobs = 0;
     long long *row_base = nullptr;
     int grid = 0;
@@ -328,7 +328,7 @@ extern "C" {
 
 int gki_finder_destroy(gki_finder *f) {
     if (!f) return GKI_OK;
-    for (int i = 0; i < f->n_dev; i++) cudaFree(f->dev[i]);
+    for (void *d : f->dev) cudaFree(d);
     delete f;
     return GKI_OK;
 }
@@ -356,7 +356,7 @@ int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int
         *dst = nullptr;
         if (!src) return GKI_OK;
         GKI_CUDA(cudaMalloc(dst, bytes ? bytes : 16));
-        f->dev[f->n_dev++] = *dst;
+        f->dev.push_back(*dst);
         if (bytes) GKI_CUDA(cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyDefault, s));
         return GKI_OK;
     };
@@ -389,25 +389,25 @@ int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int
     f->grid = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     void *tmp;
     GKI_CUDA(cudaMalloc(&tmp, (size_t)treated_slots * 16));
-    f->dev[f->n_dev++] = tmp;
+    f->dev.push_back(tmp);
     f->p.treated = (unsigned long long *)tmp;
     GKI_CUDA(cudaMalloc(&tmp, (size_t)f->grid * threads * sizeof(Frame) * F_DEPTH));
-    f->dev[f->n_dev++] = tmp;
+    f->dev.push_back(tmp);
     f->p.stacks = (unsigned char *)tmp;
     GKI_CUDA(cudaMalloc(&tmp, 16));
-    f->dev[f->n_dev++] = tmp;
+    f->dev.push_back(tmp);
     f->p.error = (unsigned int *)tmp;
     GKI_CUDA(cudaMemsetAsync(f->p.error, 0, 16, s));
     GKI_CUDA(cudaMemsetAsync(f->p.treated, 0, (size_t)treated_slots * 16, s));
     long long *rows, *jobs, *totals;
     GKI_CUDA(cudaMalloc((void **)&rows, (size_t)n_chains * 8));
-    f->dev[f->n_dev++] = rows;
+    f->dev.push_back(rows);
     GKI_CUDA(cudaMalloc((void **)&jobs, (size_t)n_chains * 8));
-    f->dev[f->n_dev++] = jobs;
+    f->dev.push_back(jobs);
     GKI_CUDA(cudaMalloc((void **)&f->row_base, (size_t)n_chains * 8));
-    f->dev[f->n_dev++] = f->row_base;
+    f->dev.push_back(f->row_base);
     GKI_CUDA(cudaMalloc((void **)&totals, 16));
-    f->dev[f->n_dev++] = totals;
+    f->dev.push_back(totals);
     FinderOut none{};
     finder_kernel<false><<<f->grid, threads, 0, s>>>(f->g, f->p, nullptr, rows, jobs, none);
     GKI_CHECK_LAUNCH();
