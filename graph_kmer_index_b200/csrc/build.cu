@@ -330,6 +330,17 @@ __global__ void non_first_kernel(const unsigned long long *__restrict__ sorted, 
     }
 }
 
+// shared with count.cu: stable sort of n packed (key << 32 | payload) elements held in `a` by the low key_bits of the key
+int radix_sort_packed(Scratch &a, Scratch &b, Scratch &hist, int64_t n, int key_bits, const unsigned long long **sorted, cudaStream_t s) {
+    SortBuffers bufs;
+    bufs.elems[0].ptr = a.ptr;  bufs.elems[0].stream = a.stream;  a.ptr = nullptr;   // take ownership for the duration of the sort
+    int rc = radix_sort_elems(bufs, n, key_bits, sorted, s);
+    a.ptr = bufs.elems[0].ptr;  bufs.elems[0].ptr = nullptr;                          // hand both buffers back to the caller
+    b.ptr = bufs.elems[1].ptr;  b.stream = s;  bufs.elems[1].ptr = nullptr;
+    hist.ptr = bufs.hist.ptr;   hist.stream = s;  bufs.hist.ptr = nullptr;
+    return rc;
+}
+
 static int bit_length(uint64_t v) {
     int b = 0;
     while (v) {

@@ -197,4 +197,8 @@ inline int grid_for(int64_t work_items, int per_block, int max_blocks) {
 int exclusive_scan_u32(const uint32_t *in, uint32_t *out, int64_t n, uint32_t *total, cudaStream_t s);
 int exclusive_scan_u32_to_u64(const uint32_t *in, uint64_t *out, int64_t n, uint64_t *total, cudaStream_t s);
 
+// stable LSD radix sort (build.cu) of n packed (key << 32 | payload) u64 elements held in `a` by the low key_bits bits of
+// the key; `b` and `hist` receive the scratch the sort allocated (the result *sorted points into `a` or `b`).
+int radix_sort_packed(Scratch &a, Scratch &b, Scratch &hist, int64_t n, int key_bits, const unsigned long long **sorted, cudaStream_t s);
+
 }  // namespace gki

@@ -393,6 +393,36 @@ __global__ void node_counts_kernel(TableView t, const uint64_t *__restrict__ kme
     }
 }
 
+// ---- entries regrouped by slot: get_node_counts as a streaming pass ----
+__global__ void entry_slots_kernel(TableView t, const uint64_t *__restrict__ kmers, int64_t n, unsigned long long *__restrict__ elems) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        Key key = make_key(__ldg(kmers + e), t.k);
+        Slot *s = find_slot(t, key.c, hash_key(key.c));          // every index k-mer is in the table
+        unsigned long long slot = s ? (unsigned long long)(s - t.slots) : 0ull;
+        elems[e] = (slot << 32) | (unsigned long long)(uint32_t)e;
+    }
+}
+__global__ void csr_fill_kernel(TableView t, const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
+                                const uint32_t *__restrict__ nodes, int64_t n, uint32_t *__restrict__ cs_slot, uint32_t *__restrict__ cs_node) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long el = __ldg(sorted + i);
+        uint32_t e = (uint32_t)el;
+        Key key = make_key(__ldg(kmers + e), t.k);
+        cs_slot[i] = (uint32_t)(el >> 32);
+        cs_node[i] = __ldg(nodes + e) | (key.o << 31);
+    }
+}
+__global__ void node_counts_csr_kernel(TableView t, const uint32_t *__restrict__ cs_slot, const uint32_t *__restrict__ cs_node, int64_t n,
+                                       double *__restrict__ out, int64_t n_out, bool wrap16) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t nd = __ldg(cs_node + i);
+        uint32_t w = *(volatile uint32_t *)&t.slots[__ldg(cs_slot + i)].cnt[nd >> 31];
+        if (wrap16) w &= 0xFFFFu;
+        const uint32_t node = nd & 0x7fffffffu;
+        if (w && (int64_t)node < n_out) atomicAdd(out + node, (double)w);
+    }
+}
+
 __global__ void query_counts_kernel(TableView t, const uint64_t *__restrict__ queries, int64_t nq, uint32_t *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = kmer_count(t, __ldg(queries + i), false);
@@ -402,6 +432,9 @@ __global__ void query_counts_kernel(TableView t, const uint64_t *__restrict__ qu
 void destroy_count_table(gki_index *ix) {
     cudaFree(ix->table.slots);
     cudaFree((void *)ix->table.filter);
+    cudaFree(ix->cs_slot);
+    cudaFree(ix->cs_node);
+    ix->cs_slot = ix->cs_node = nullptr;
     ix->table = TableView{};
     ix->table_bytes = ix->filter_bytes = 0;
 }
@@ -463,6 +496,23 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     GKI_CUDA(cudaStreamSynchronize(s));
     ix->table = t;
     GKI_REQUIRE(failed == 0, GKI_ERR_CUDA, "count table: %u insertions failed", failed);
+    // regroup the entries by slot (one-time sort) so that get_node_counts reads the counters in table order
+    if (n_slots < (1ull << 32) && ix->max_node < (1ll << 31) && !getenv("GKI_NO_CSR")) {
+        Scratch a, b, hist;
+        GKI_TRY(a.alloc((size_t)ix->n * 8, s));
+        entry_slots_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, a.as<unsigned long long>());
+        GKI_CHECK_LAUNCH();
+        int bits = 1;
+        while ((1ull << bits) < n_slots) bits++;
+        const unsigned long long *sorted = nullptr;
+        GKI_TRY(radix_sort_packed(a, b, hist, ix->n, bits, &sorted, s));
+        GKI_CUDA(cudaMalloc((void **)&ix->cs_slot, (size_t)ix->n * 4));
+        GKI_CUDA(cudaMalloc((void **)&ix->cs_node, (size_t)ix->n * 4));
+        csr_fill_kernel<<<grid_n, 256, 0, s>>>(t, sorted, ix->kmers, ix->nodes, ix->n, ix->cs_slot, ix->cs_node);
+        GKI_CHECK_LAUNCH();
+        GKI_CUDA(cudaStreamSynchronize(s));
+        ix->table_bytes += (size_t)ix->n * 8;
+    }
     return GKI_OK;
 }
 
@@ -628,8 +678,10 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
     GKI_TRY(o.prepare(out, (size_t)n_out * 8, call.stream));
     GKI_CUDA(cudaMemsetAsync(o.dptr, 0, (size_t)n_out * 8, call.stream));
     if (ix->table.slots) {
-        node_counts_kernel<<<grid_for(ix->n, 256 * 4, device_info().sms * 16), 256, 0, call.stream>>>(
-            ix->table, ix->kmers, ix->nodes, ix->n, o.as<double>(), n_out, (flags & GKI_COUNTS_WRAP_UINT16) != 0);
+        const bool wrap = (flags & GKI_COUNTS_WRAP_UINT16) != 0;
+        const int grid = grid_for(ix->n, 256 * 4, device_info().sms * 16);
+        if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);
+        else node_counts_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->kmers, ix->nodes, ix->n, o.as<double>(), n_out, wrap);
         GKI_CHECK_LAUNCH();
     }
     GKI_TRY(o.finish(call.stream));

@@ -55,6 +55,9 @@ struct gki_index {
     size_t device_bytes = 0;
     // counting structure, built by the first counting call (count.cu)
     gki::TableView table{};
+    // entries regrouped by count-table slot (count.cu): slot index and node | orientation << 31, so that get_node_counts
+    // streams the table instead of looking every entry up
+    uint32_t *cs_slot = nullptr, *cs_node = nullptr;
     int64_t n_distinct = 0;
     size_t table_bytes = 0, filter_bytes = 0;
     // host-buffer streaming (gki_count_reads / gki_count_kmers with host pointers)

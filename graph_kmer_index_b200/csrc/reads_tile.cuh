@@ -57,6 +57,17 @@ __device__ __forceinline__ TileSmem carve_tile_smem(unsigned char *base, const R
 // SWAR encode of 4 ASCII bytes -> 8 bits of codes, 8 bits of validity
 __device__ __forceinline__ void encode4(uint32_t w, uint32_t &c8, uint32_t &v8) {
     uint32_t lc = w | 0x20202020u;
+    {   // fast path, all four bytes in ACGTacgt: code = (bit1 ^ bit2, bit2 ^ bit3) of the letter gives a0 c1 g2 t3; the letter
+        // rebuilt from the code ('a' + {0, 2, 6, 19}[code]) must equal the input; one multiply gathers the four 2-bit codes
+        uint32_t c = ((lc >> 1) ^ (lc >> 2)) & 0x03030303u;
+        uint32_t c1 = (c >> 1) & 0x01010101u;
+        uint32_t expect = 0x61616161u + (c + c1) * 2u + (c & c1) * 11u;
+        if (expect == lc) {
+            c8 = (c * 0x01041040u) >> 24;
+            v8 = 0xFFu;
+            return;
+        }
+    }
     uint32_t v = __vcmpeq4(lc, 0x61616161u) | __vcmpeq4(lc, 0x63636363u) | __vcmpeq4(lc, 0x67676767u) |
                  __vcmpeq4(lc, 0x74747474u);
     uint32_t x = (lc >> 1) & 0x03030303u;
