@@ -11,8 +11,8 @@
 //
 //   * Bloom filter, register-blocked (one 32-bit word per key, filter_k bits), sized <= 48 MB so it stays in
 //     L2: one L2 access decides most absent k-mers.
-//   * bucketised open-addressing table over the distinct k-mers: bucket = 4 slots x {key, cnt[2]} = one 64-byte
-//     line = ONE HBM access per surviving probe; the hit's RED lands on the line that was just fetched.
+//   * bucketised open-addressing table over the distinct k-mers: bucket = key[4] | cnt[4][2] = one 64-byte line; a
+//     probe reads the four keys with ONE 256-bit load (one 32-byte sector from HBM), a hit adds one RED on the other half.
 //   * canonical keys: key = min(x, revcomp_k(x)), cnt[o] with o = (x != key).  The forward and reverse-complement
 //     hashes of a read position share the key, so a position (2 queries) costs one filter access, at most one
 //     table access and one 64-bit RED (+1 on both orientations).
@@ -78,17 +78,51 @@ __device__ __forceinline__ Key make_key(uint64_t q, int k) {
     return key;
 }
 
-// slot holding key c (c != SLOT_EMPTY) starting at bucket b, or nullptr.  Probing visits buckets linearly and stops at
-// the first non-full bucket.
-__device__ __forceinline__ Slot *find_slot_from(const TableView &t, unsigned long long c, uint32_t b) {
+// L2 eviction-priority hints (createpolicy + ld.global.L2::cache_hint): the Bloom filter is the only structure with
+// reuse, table lines are touched once per probe.  HINTS bit 0: filter loads evict_last, bit 1: table loads evict_first.
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint32_t ld_u32_hint(const uint32_t *ptr, unsigned long long pol) {
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_u64_hint(const unsigned long long *ptr, unsigned long long pol) {
+    unsigned long long v;
+    asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(ptr), "l"(pol));
+    return v;
+}
+
+// The four keys of a bucket in ONE 256-bit load (LDG.E.256 on sm_100a).  ncu on the first table layout showed four
+// separate 8-byte loads of one line, issued back to back, each paying its own 32-byte HBM fetch (L2 does not merge
+// in-flight misses of different requests): 128 B of DRAM reads per probe instead of 32.
+__device__ __forceinline__ void load_bucket_keys(const Bucket *bk, unsigned long long (&key)[SLOTS_PER_BUCKET]) {
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(key[0]), "=l"(key[1]), "=l"(key[2]), "=l"(key[3]) : "l"(bk));
+}
+__device__ __forceinline__ void load_bucket_keys_hint(const Bucket *bk, unsigned long long (&key)[SLOTS_PER_BUCKET], unsigned long long pol) {
+    asm("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(key[0]), "=l"(key[1]), "=l"(key[2]), "=l"(key[3]) : "l"(bk), "l"(pol));
+}
+
+// counter pair {cnt[0], cnt[1]} of key c (c != SLOT_EMPTY) starting at bucket b, or nullptr.  Probing visits buckets
+// linearly and stops at the first non-full bucket.
+template <bool HINT = false>
+__device__ __forceinline__ uint32_t *find_slot_from(const TableView &t, unsigned long long c, uint32_t b, unsigned long long pol = 0) {
     for (uint32_t tries = 0; tries < t.n_buckets; tries++) {
-        Slot *base = t.slots + (size_t)b * SLOTS_PER_BUCKET;
-        unsigned long long key[SLOTS_PER_BUCKET];   // keys never change while a counting kernel runs: all four loads in flight
-#pragma unroll
-        for (int i = 0; i < SLOTS_PER_BUCKET; i++) key[i] = __ldg(&base[i].key);
+        Bucket *bk = t.buckets + b;
+        unsigned long long key[SLOTS_PER_BUCKET];   // keys never change while a counting kernel runs
+        if (HINT) load_bucket_keys_hint(bk, key, pol);
+        else load_bucket_keys(bk, key);
 #pragma unroll
         for (int i = 0; i < SLOTS_PER_BUCKET; i++) {
-            if (key[i] == c) return base + i;
+            if (key[i] == c) return bk->cnt[i];
             if (key[i] == SLOT_EMPTY) return nullptr;
         }
         b = (b + 1 == t.n_buckets) ? 0 : b + 1;
@@ -96,13 +130,21 @@ __device__ __forceinline__ Slot *find_slot_from(const TableView &t, unsigned lon
     return nullptr;
 }
 
-// slot holding key c, or nullptr
-__device__ __forceinline__ Slot *find_slot(const TableView &t, unsigned long long c, const Hash &h) {
-    if (c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker has its own slot,
-        Slot *sp = t.slots + (size_t)t.n_buckets * SLOTS_PER_BUCKET;   // whose key field is 1 iff that value is indexed
-        return __ldg(&sp->key) == 1ull ? sp : nullptr;
+// counter pair of key c, or nullptr
+__device__ __forceinline__ uint32_t *find_slot(const TableView &t, unsigned long long c, const Hash &h) {
+    if (c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker has its own bucket,
+        Bucket *sp = t.buckets + t.n_buckets;   // whose key[0] is 1 iff that value is indexed
+        return __ldg(&sp->key[0]) == 1ull ? sp->cnt[0] : nullptr;
     }
     return find_slot_from(t, c, home_bucket(t, h));
+}
+// slot id <-> counter pair (get_node_counts regroups the entries by slot id)
+__device__ __forceinline__ unsigned long long slot_id(const TableView &t, const uint32_t *cnt) {
+    const size_t off = (size_t)(cnt - (const uint32_t *)t.buckets);       // in u32 units: bucket * 16 + 8 + 2 * i
+    return (unsigned long long)(off >> 4) * SLOTS_PER_BUCKET + (((off & 15) - 8) >> 1);
+}
+__device__ __forceinline__ uint32_t *slot_counters(const TableView &t, unsigned long long slot) {
+    return t.buckets[slot >> 2].cnt[slot & 3];
 }
 
 // one independent query
@@ -114,19 +156,16 @@ __device__ __forceinline__ void count_one(const TableView &t, uint64_t q) {
         uint32_t m = filter_mask(t, h);
         if ((__ldg(t.filter + filter_word(t, h)) & m) != m) return;
     }
-    Slot *s = find_slot(t, key.c, h);
-    if (s) atomicAdd(&s->cnt[key.o], 1u);
+    uint32_t *cnt = find_slot(t, key.c, h);
+    if (cnt) atomicAdd(cnt + key.o, 1u);
 }
 
 // ------------------------------------------------------------------ table construction
-__global__ void table_init_kernel(Slot *__restrict__ slots, size_t n_slots) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x) {
-        Slot s;
-        s.key = SLOT_EMPTY;
-        s.cnt[0] = 0;
-        s.cnt[1] = 0;
-        slots[i] = s;
-    }
+__global__ void table_init_kernel(Bucket *__restrict__ buckets, size_t n_buckets) {
+    // one thread per 8-byte word: words 0-3 of a bucket are keys (empty), words 4-7 counters (zero)
+    unsigned long long *w = (unsigned long long *)buckets;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_buckets * 8; i += (size_t)gridDim.x * blockDim.x)
+        w[i] = (i & 4) ? 0ull : SLOT_EMPTY;
 }
 
 // number of distinct k-mers: entry e is a representative iff no earlier entry of its bucket holds the same k-mer
@@ -153,7 +192,7 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         Key key = make_key(__ldg(kmers + e), t.k);
         if (key.c == SLOT_EMPTY) {
-            t.slots[(size_t)t.n_buckets * SLOTS_PER_BUCKET].key = 1ull;   // mark the special slot as present
+            t.buckets[t.n_buckets].key[0] = 1ull;   // mark the special bucket as present
             continue;
         }
         Hash h = hash_key(key.c);
@@ -161,10 +200,10 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
         uint32_t b = home_bucket(t, h);
         bool placed = false;
         for (uint32_t tries = 0; tries < t.n_buckets && !placed; tries++) {
-            Slot *base = t.slots + (size_t)b * SLOTS_PER_BUCKET;
+            Bucket *bk = t.buckets + b;
             for (int i = 0; i < SLOTS_PER_BUCKET && !placed; i++) {
-                unsigned long long cur = *(volatile unsigned long long *)&base[i].key;
-                if (cur == SLOT_EMPTY) cur = atomicCAS(&base[i].key, SLOT_EMPTY, key.c);
+                unsigned long long cur = *(volatile unsigned long long *)&bk->key[i];
+                if (cur == SLOT_EMPTY) cur = atomicCAS(&bk->key[i], SLOT_EMPTY, key.c);
                 placed = (cur == SLOT_EMPTY) || (cur == key.c);
             }
             b = (b + 1 == t.n_buckets) ? 0 : b + 1;
@@ -173,9 +212,10 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
     }
 }
 
-__global__ void table_reset_kernel(Slot *__restrict__ slots, size_t n_slots) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_slots; i += (size_t)gridDim.x * blockDim.x)
-        *(unsigned long long *)&slots[i].cnt[0] = 0ull;
+__global__ void table_reset_kernel(Bucket *__restrict__ buckets, size_t n_buckets) {
+    // the counter half (32 B) of every bucket, 16 bytes per thread
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n_buckets * 2; i += (size_t)gridDim.x * blockDim.x)
+        *(uint4 *)((char *)&buckets[i >> 1].cnt[0][0] + 16 * (i & 1)) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // ------------------------------------------------------------------ counting kernels
@@ -203,8 +243,11 @@ struct WarpBatch {
 constexpr int WPL = 4;   // consecutive windows per lane
 constexpr int QCAP = 64;  // survivor queue capacity per warp (< 32 pending + <= 32 pushed per ballot)
 
-template <bool BOTH, bool PAIRED, int MINB>
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
+    const unsigned long long pol_last = (HINTS & 1) ? l2_policy_evict_last() : 0ull;
+    const unsigned long long pol_first = (HINTS & 2) ? l2_policy_evict_first() : 0ull;
+    const unsigned long long pol_stream = (HINTS & 4) ? l2_policy_evict_first() : 0ull;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // per-warp shared memory: [mbarrier | ASCII stage | codes | valid | dirty flags].  One ASCII stage is enough: it is
@@ -225,10 +268,10 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             const uint32_t idx = (qhead + lane) & (QCAP - 1);
             const unsigned long long key = qkey[idx];
             const uint32_t meta = qmeta[idx];
-            Slot *slot = find_slot_from(t, key, meta & 0x7fffffffu);
-            if (slot) {
-                if (meta >> 31) atomicAdd(&slot->cnt[0], 2u);                                    // palindrome (even k)
-                else atomicAdd((unsigned long long *)&slot->cnt[0], 0x0000000100000001ull);      // +1 on both orientations
+            uint32_t *cnt = find_slot_from<(HINTS & 2) != 0>(t, key, meta & 0x7fffffffu, pol_first);
+            if (cnt) {
+                if (meta >> 31) atomicAdd(cnt, 2u);                                              // palindrome (even k)
+                else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);                // +1 on both orientations
             }
         }
         qhead += n;
@@ -246,7 +289,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
     auto issue = [&](int64_t tile) {
         fence_proxy_async();
         mbar_expect_tx(bar, tile_bytes);
-        bulk_g2s(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar);
+        if (HINTS & 4) bulk_g2s_hint(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar, pol_stream);
+        else bulk_g2s(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar);
     };
     if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt);
     uint32_t phase = 0;
@@ -332,7 +376,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         pal |= (uint32_t)(x == rc) << u;
                         h[u] = hash_key(c[u]);
                         fm[u] = filter_mask(t, h[u]);
-                        fw[u] = (t.filter && ok) ? __ldg(t.filter + filter_word(t, h[u])) : 0xffffffffu;
+                        fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + filter_word(t, h[u]), pol_last) : __ldg(t.filter + filter_word(t, h[u])))
+                                                 : 0xffffffffu;
                         live |= (uint32_t)ok << u;
                     }
 #pragma unroll
@@ -378,8 +423,8 @@ __device__ __forceinline__ uint32_t kmer_count(const TableView &t, uint64_t km, 
     Key key = make_key(km, t.k);
     uint32_t w = 0;
     if (key.ok) {
-        Slot *s = find_slot(t, key.c, hash_key(key.c));
-        if (s) w = *(volatile uint32_t *)&s->cnt[key.o];
+        uint32_t *cnt = find_slot(t, key.c, hash_key(key.c));
+        if (cnt) w = *(volatile uint32_t *)(cnt + key.o);
     }
     return wrap16 ? (w & 0xFFFFu) : w;
 }
@@ -397,8 +442,8 @@ __global__ void node_counts_kernel(TableView t, const uint64_t *__restrict__ kme
 __global__ void entry_slots_kernel(TableView t, const uint64_t *__restrict__ kmers, int64_t n, unsigned long long *__restrict__ elems) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         Key key = make_key(__ldg(kmers + e), t.k);
-        Slot *s = find_slot(t, key.c, hash_key(key.c));          // every index k-mer is in the table
-        unsigned long long slot = s ? (unsigned long long)(s - t.slots) : 0ull;
+        uint32_t *cnt = find_slot(t, key.c, hash_key(key.c));    // every index k-mer is in the table
+        unsigned long long slot = cnt ? slot_id(t, cnt) : 0ull;
         elems[e] = (slot << 32) | (unsigned long long)(uint32_t)e;
     }
 }
@@ -416,7 +461,7 @@ __global__ void node_counts_csr_kernel(TableView t, const uint32_t *__restrict__
                                        double *__restrict__ out, int64_t n_out, bool wrap16) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t nd = __ldg(cs_node + i);
-        uint32_t w = *(volatile uint32_t *)&t.slots[__ldg(cs_slot + i)].cnt[nd >> 31];
+        uint32_t w = *(volatile uint32_t *)(slot_counters(t, __ldg(cs_slot + i)) + (nd >> 31));
         if (wrap16) w &= 0xFFFFu;
         const uint32_t node = nd & 0x7fffffffu;
         if (w && (int64_t)node < n_out) atomicAdd(out + node, (double)w);
@@ -430,7 +475,7 @@ __global__ void query_counts_kernel(TableView t, const uint64_t *__restrict__ qu
 
 // ------------------------------------------------------------------ host side
 void destroy_count_table(gki_index *ix) {
-    cudaFree(ix->table.slots);
+    cudaFree(ix->table.buckets);
     cudaFree((void *)ix->table.filter);
     cudaFree(ix->cs_slot);
     cudaFree(ix->cs_node);
@@ -441,7 +486,7 @@ void destroy_count_table(gki_index *ix) {
 
 // Build the table on first use.  k > 0 selects canonical keys (needs every index k-mer < 4^k), k == 0 raw keys.
 static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
-    if (ix->table.slots) return GKI_OK;
+    if (ix->table.buckets) return GKI_OK;
     if (k < 0 || k > 31) k = 0;
     if (k && (ix->max_kmer >> (2 * k)) != 0) k = 0;     // index values wider than k bases: canonical form undefined
     if (const char *e = getenv("GKI_TABLE_RAW")) if (atoi(e)) k = 0;
@@ -461,14 +506,15 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     uint64_t buckets = (distinct + 1) / 2 + 16;          // 4 slots per bucket -> load factor <= 0.5
     GKI_REQUIRE(buckets < (1ull << 31), GKI_ERR_UNSUPPORTED, "count table: too many distinct k-mers");
     t.n_buckets = (uint32_t)buckets;
-    size_t n_slots = (size_t)buckets * SLOTS_PER_BUCKET + 1;
-    GKI_CUDA(cudaMalloc((void **)&t.slots, n_slots * sizeof(Slot)));
-    ix->table_bytes = n_slots * sizeof(Slot);
-    table_init_kernel<<<grid_for((int64_t)n_slots, 256 * 4, device_info().sms * 16), 256, 0, s>>>(t.slots, n_slots);
+    const size_t n_slots = ((size_t)buckets + 1) * SLOTS_PER_BUCKET;
+    GKI_CUDA(cudaMalloc((void **)&t.buckets, ((size_t)buckets + 1) * sizeof(Bucket)));
+    ix->table_bytes = ((size_t)buckets + 1) * sizeof(Bucket);
+    table_init_kernel<<<grid_for((int64_t)(buckets + 1) * 8, 256 * 4, device_info().sms * 16), 256, 0, s>>>(t.buckets, (size_t)buckets + 1);
     GKI_CHECK_LAUNCH();
 
     // Bloom filter: as many bits per key as fit the L2 budget (<= 16); below 1.5 bits per key it filters nothing
-    size_t budget = (size_t)48 << 20;   // measured: random gathers stay at the L2 rate up to 48 MB (profiles/r1)
+    size_t budget = (size_t)32 << 20;   // measured optimum at c2 (profiles/r1/tune_filter_v4.jsonl): flat from 32 to 40 MB, worse
+                                        // below (false positives) and above (the filter starts missing L2)
     if (const char *e = getenv("GKI_FILTER_MAX_MB")) budget = (size_t)atoi(e) << 20;
     size_t want = (size_t)distinct * 2;                  // 16 bits per key
     // Indexes too large for an L2-resident filter still profit from an HBM-resident one at 8 bits per key (measured at
@@ -543,18 +589,18 @@ static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cud
     return GKI_OK;
 }
 
-template <bool BOTH, bool PAIRED, int MINB> static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0> static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
     const size_t smem = (size_t)b.warp_bytes * COUNT_WARPS;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BOTH, PAIRED, MINB><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
+    count_reads_kernel<BOTH, PAIRED, MINB, HINTS><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
@@ -588,6 +634,13 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     if (ix->table.k != k) return launch_count_reads_t<true, false, 4>(ix, b, s);
     int minb = 4;
     if (const char *e = getenv("GKI_MINB")) minb = atoi(e);
+    int hints = 0;
+    if (const char *e = getenv("GKI_HINTS")) hints = atoi(e);
+    if (hints == 1) return launch_count_reads_t<true, true, 4, 1>(ix, b, s);
+    if (hints == 2) return launch_count_reads_t<true, true, 4, 2>(ix, b, s);
+    if (hints == 3) return launch_count_reads_t<true, true, 4, 3>(ix, b, s);
+    if (hints == 4) return launch_count_reads_t<true, true, 4, 4>(ix, b, s);
+    if (hints == 5) return launch_count_reads_t<true, true, 4, 5>(ix, b, s);
     if (minb == 5) return launch_count_reads_t<true, true, 5>(ix, b, s);
     if (minb == 6) return launch_count_reads_t<true, true, 6>(ix, b, s);
     if (minb == 3) return launch_count_reads_t<true, true, 3>(ix, b, s);
@@ -607,9 +660,9 @@ int gki_prepare_counting(gki_index_t *ix, int32_t k, gki_stream_t stream) {
 
 int gki_reset_counts(gki_index_t *ix, gki_stream_t stream) {
     GKI_REQUIRE(ix, GKI_ERR_INVALID, "gki_reset_counts: index is NULL");
-    if (!ix->table.slots) return GKI_OK;   // nothing counted yet
-    size_t n_slots = (size_t)ix->table.n_buckets * SLOTS_PER_BUCKET + 1;
-    table_reset_kernel<<<grid_for((int64_t)n_slots, 256 * 4, device_info().sms * 16), 256, 0, (cudaStream_t)stream>>>(ix->table.slots, n_slots);
+    if (!ix->table.buckets) return GKI_OK;   // nothing counted yet
+    const size_t nb = (size_t)ix->table.n_buckets + 1;
+    table_reset_kernel<<<grid_for((int64_t)nb * 2, 256 * 4, device_info().sms * 16), 256, 0, (cudaStream_t)stream>>>(ix->table.buckets, nb);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
@@ -677,7 +730,7 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
     DevOut o;
     GKI_TRY(o.prepare(out, (size_t)n_out * 8, call.stream));
     GKI_CUDA(cudaMemsetAsync(o.dptr, 0, (size_t)n_out * 8, call.stream));
-    if (ix->table.slots) {
+    if (ix->table.buckets) {
         const bool wrap = (flags & GKI_COUNTS_WRAP_UINT16) != 0;
         const int grid = grid_for(ix->n, 256 * 4, device_info().sms * 16);
         if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);
@@ -693,7 +746,7 @@ int gki_entry_counts(gki_index_t *ix, uint32_t *out, gki_stream_t stream) {
     GKI_REQUIRE(ix && out, GKI_ERR_INVALID, "gki_entry_counts: bad arguments");
     DevOut o;
     GKI_TRY(o.prepare(out, (size_t)ix->n * 4, call.stream));
-    if (ix->table.slots) {
+    if (ix->table.buckets) {
         query_counts_kernel<<<grid_for(ix->n, 256 * 4, device_info().sms * 16), 256, 0, call.stream>>>(ix->table, ix->kmers, ix->n, o.as<uint32_t>());
         GKI_CHECK_LAUNCH();
     } else {
@@ -711,7 +764,7 @@ int gki_query_counts(gki_index_t *ix, const uint64_t *queries, int64_t nq, uint3
     GKI_TRY(q.stage(queries, (size_t)nq * 8, call.stream));
     DevOut o;
     GKI_TRY(o.prepare(out, (size_t)nq * 4, call.stream));
-    if (ix->table.slots) {
+    if (ix->table.buckets) {
         query_counts_kernel<<<grid_for(nq, 256 * 2, device_info().sms * 16), 256, 0, call.stream>>>(ix->table, q.as<uint64_t>(), nq, o.as<uint32_t>());
         GKI_CHECK_LAUNCH();
     } else {

@@ -14,21 +14,21 @@ struct IndexView {
 };
 
 // Counting structure (count.cu): a bucketised open-addressing table over the DISTINCT index k-mers.
-//   slot   = {key, cnt[2]} (16 B); bucket = 4 slots = one 64-byte line = one HBM access per probe;
+//   bucket = 64 bytes = key[4] (one 32-byte sector, read by a probe with ONE 256-bit load) | cnt[4][2] (the other sector);
 //   key    = canonical form min(x, revcomp_k(x)) when the k-mer length k is known (k > 0), else x itself;
 //   cnt[o] = number of counted queries q with canonical(q) == key and orientation o = (q != key).
 // Both strands of a read position share one canonical key, so a position costs ONE filter access and at most
 // ONE table access, and a hit is ONE 64-bit RED on the line that was just fetched.
 //   filter = register-blocked Bloom filter (32-bit words, filter_k bits per key) sized to stay resident in L2.
-struct Slot {
-    unsigned long long key;
-    uint32_t cnt[2];
+struct Bucket {
+    unsigned long long key[4];
+    uint32_t cnt[4][2];
 };
 constexpr unsigned long long SLOT_EMPTY = ~0ull;
 constexpr int SLOTS_PER_BUCKET = 4;
 
 struct TableView {
-    Slot *slots;              // n_buckets * 4, + 1 special slot for the key that equals SLOT_EMPTY (raw mode only)
+    Bucket *buckets;          // n_buckets, + 1 special bucket for the key that equals SLOT_EMPTY (raw mode only)
     const uint32_t *filter;   // filter_words u32 (NULL: no filter)
     uint32_t n_buckets;
     uint32_t filter_words;
