@@ -365,9 +365,18 @@ def main():
     # counts summed over nodes counts every hit once per entry of the k-mer (2 entries per distinct k-mer)
     h = (entry_hits / 2.0) / kmers_per_launch
     occ = info["nonempty_buckets"] / modulo
-    sectors = (1 - h) * (1 - occ) * 1 + (1 - h) * occ * 3 + h * 5          # SURVEY.md section 8(d) K3 model
-    bytes_per_kmer = L / nk_per_read + 32.0 * sectors
+    # Algorithmic bytes of one launch = 32-byte sectors the probe structure must touch.  The kernel
+    # probes the count table (csrc/count.cu), not the reference's modulo buckets, so SURVEY 8(d)'s sector figure is
+    # re-derived for that layout: per read position (= 2 k-mers, one canonical key): its share of the ASCII read, one
+    # Bloom-filter sector, and for a hit the bucket's key sector + its counter sector read and written back.
+    positions = kmers_per_launch / 2.0
+    h_pos = 2.0 * h                                         # hit positions / positions (a position hits on one strand)
+    bytes_per_position = 2.0 * L / nk_per_read + 32.0 * (1.0 + 3.0 * h_pos)
+    bytes_per_kmer = bytes_per_position / 2.0
     achieved = kmers_per_launch * bytes_per_kmer / (kernel_ms / 1e3) / 1e9
+    # the same for the reference's own bucket layout (SURVEY 8(d) as written: 1 sector empty bucket / 3 miss / 5 hit)
+    survey_sectors = (1 - h) * (1 - occ) * 1 + (1 - h) * occ * 3 + h * 5
+    survey_bytes_per_kmer = L / nk_per_read + 32.0 * survey_sectors
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -378,9 +387,14 @@ def main():
     roofline = {"bound": "hbm", "kernel": "count_reads_kernel<both=true,paired=true> (L2 Bloom filter: %s)" % str(info["has_filter"]).lower(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
-                "algorithmic_bytes_per_kmer": bytes_per_kmer, "sectors_per_kmer_model": sectors, "hit_fraction": h,
-                "bucket_occupancy": occ, "kmers_per_s_kernel_only": kmers_per_launch / (kernel_ms / 1e3),
-                "note": "random 32-B sector model of SURVEY 8(d): 1 sector empty bucket / 3 non-empty miss / 5 hit, + ASCII read bytes"}
+                "algorithmic_bytes_per_kmer": bytes_per_kmer, "hit_fraction_of_kmers": h, "positions_per_launch": positions,
+                "kmers_per_s_kernel_only": kmers_per_launch / (kernel_ms / 1e3),
+                "reference_layout_model": {"bytes_per_kmer": survey_bytes_per_kmer, "sectors_per_kmer": survey_sectors, "bucket_occupancy": occ,
+                                           "gbs": kmers_per_launch * survey_bytes_per_kmer / (kernel_ms / 1e3) / 1e9},
+                "random_access_ceilings": {"l2_resident_gathers_per_s": 217e9, "hbm_gathers_per_s": 37e9,
+                                           "source": "profiles/r1/calibrate_random_gather.jsonl (measured on this pool's B200)"},
+                "note": "sector model of the count-table layout: per read position 1 filter sector (served by L2 when the filter is resident) "
+                        "+ 3 sectors per hit (bucket keys, counter read, counter write-back) + ASCII; traffic = ncu dram bytes of one launch"}
 
     # ---------------- CPU baseline (oracle port on the host cores, bounded sample) ----------------
     cpu = None

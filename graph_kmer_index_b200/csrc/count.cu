@@ -487,6 +487,9 @@ void destroy_count_table(gki_index *ix) {
 // Build the table on first use.  k > 0 selects canonical keys (needs every index k-mer < 4^k), k == 0 raw keys.
 static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     if (ix->table.buckets) return GKI_OK;
+    if (const char *e = getenv("GKI_L2_FETCH")) {   // experiment knob: L2 fetch granularity for misses (32 / 64 / 128 bytes)
+        GKI_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
+    }
     if (k < 0 || k > 31) k = 0;
     if (k && (ix->max_kmer >> (2 * k)) != 0) k = 0;     // index values wider than k bases: canonical form undefined
     if (const char *e = getenv("GKI_TABLE_RAW")) if (atoi(e)) k = 0;
