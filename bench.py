@@ -365,13 +365,18 @@ def main():
     # counts summed over nodes counts every hit once per entry of the k-mer (2 entries per distinct k-mer)
     h = (entry_hits / 2.0) / kmers_per_launch
     occ = info["nonempty_buckets"] / modulo
-    # Algorithmic bytes of one launch = 32-byte sectors the probe structure must touch.  The kernel
-    # probes the count table (csrc/count.cu), not the reference's modulo buckets, so SURVEY 8(d)'s sector figure is
-    # re-derived for that layout: per read position (= 2 k-mers, one canonical key): its share of the ASCII read, one
-    # Bloom-filter sector, and for a hit the bucket's key sector + its counter sector read and written back.
+    # Algorithmic HBM bytes of one launch.  The kernel probes the count table (csrc/count.cu), not
+    # the reference's modulo buckets, so SURVEY 8(d)'s sector figure is re-derived for that layout, at the granularity
+    # this B200 fills L2 from HBM with: a whole 128-byte line per random access (measured: 127 B of DRAM reads per 8-byte
+    # gather, profiles/r1/calibrate_gather_v2_ncu.txt).  Per read position (= 2 k-mers, one canonical key): its share of
+    # the ASCII read; for a hit one table line (keys + counters) and the 32-byte counter sector written back; the Bloom
+    # filter word comes from L2 when the filter is resident there, else it is one more line.
+    LINE = 128.0
     positions = kmers_per_launch / 2.0
     h_pos = 2.0 * h                                         # hit positions / positions (a position hits on one strand)
-    bytes_per_position = 2.0 * L / nk_per_read + 32.0 * (1.0 + 3.0 * h_pos)
+    filter_resident = info["has_filter"] and (n // 2) <= (32 << 20)
+    filter_lines = 0.0 if filter_resident else (1.0 if info["has_filter"] else 0.0)
+    bytes_per_position = 2.0 * L / nk_per_read + LINE * filter_lines + (LINE + 32.0) * h_pos
     bytes_per_kmer = bytes_per_position / 2.0
     achieved = kmers_per_launch * bytes_per_kmer / (kernel_ms / 1e3) / 1e9
     # the same for the reference's own bucket layout (SURVEY 8(d) as written: 1 sector empty bucket / 3 miss / 5 hit)
@@ -384,17 +389,25 @@ def main():
             traffic = json.load(open(tpath)).get("count_reads_kernel_dram_bytes_per_launch_%s" % args.config)
         except Exception:
             traffic = None
+    # the other two resources the kernel leans on, against ceilings measured on this pool's B200 (profiles/r1/calibrate_gather_v2.jsonl):
+    # per-thread global requests through L1TEX (1 sector per cycle per SM) and random HBM line fetches
+    requests = positions * (1.0 + 2.0 * h_pos + 0.05)      # filter word + (keys load + RED) per hit + ~5 % false positives
+    hbm_lines = positions * (h_pos + filter_lines + 0.05)
     roofline = {"bound": "hbm", "kernel": "count_reads_kernel<both=true,paired=true> (L2 Bloom filter: %s)" % str(info["has_filter"]).lower(),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
                 "algorithmic_bytes_per_kmer": bytes_per_kmer, "hit_fraction_of_kmers": h, "positions_per_launch": positions,
                 "kmers_per_s_kernel_only": kmers_per_launch / (kernel_ms / 1e3),
+                "co_limits": {"l1tex_requests_per_s": requests / (kernel_ms / 1e3), "l1tex_ceiling_per_s": 291e9,
+                              "l1tex_frac": requests / (kernel_ms / 1e3) / 291e9,
+                              "hbm_random_lines_per_s": hbm_lines / (kernel_ms / 1e3), "hbm_random_ceiling_per_s": 37e9,
+                              "hbm_random_frac": hbm_lines / (kernel_ms / 1e3) / 37e9,
+                              "source": "profiles/r1/calibrate_gather_v2.jsonl: 291 G L2-resident gathers/s (L1TEX at 99 %), 37 G HBM gathers/s"},
                 "reference_layout_model": {"bytes_per_kmer": survey_bytes_per_kmer, "sectors_per_kmer": survey_sectors, "bucket_occupancy": occ,
                                            "gbs": kmers_per_launch * survey_bytes_per_kmer / (kernel_ms / 1e3) / 1e9},
-                "random_access_ceilings": {"l2_resident_gathers_per_s": 217e9, "hbm_gathers_per_s": 37e9,
-                                           "source": "profiles/r1/calibrate_random_gather.jsonl (measured on this pool's B200)"},
-                "note": "sector model of the count-table layout: per read position 1 filter sector (served by L2 when the filter is resident) "
-                        "+ 3 sectors per hit (bucket keys, counter read, counter write-back) + ASCII; traffic = ncu dram bytes of one launch"}
+                "note": "HBM bytes of the count-table layout at the measured 128-byte fill granularity: ASCII + per hit one table line "
+                        "and the counter sector written back (+ one line per position when the filter does not fit L2); "
+                        "traffic = ncu dram bytes of one launch (false-positive and chain probes are the excess)"}
 
     # ---------------- CPU baseline (oracle port on the host cores, bounded sample) ----------------
     cpu = None

@@ -11,6 +11,8 @@ from .collision_free_kmer_index import CollisionFreeKmerIndex, CounterKmerIndex,
 from .collision_free_kmer_index import CollisionFreeKmerIndex as KmerIndex  # noqa: F401
 from .cython_kmer_index import CythonKmerIndex  # noqa: F401
 from .read_kmers import ReadKmers  # noqa: F401
+from .reverse_kmer_index import ReverseKmerIndex  # noqa: F401
+from .reference_kmer_index import ReferenceKmerIndex  # noqa: F401
 
 __version__ = "0.1.0"
 from .kmer_finder import DenseKmerFinder, CriticalGraphPaths  # noqa: F401,E402

@@ -330,6 +330,57 @@ __global__ void non_first_kernel(const unsigned long long *__restrict__ sorted, 
     }
 }
 
+// ---- side indexes keyed by node / reference position (reverse_kmer_index.py:59-84, reference_kmer_index.py:81-121) ----
+template <typename K>
+__global__ void group_keys_kernel(const K *__restrict__ keys, int64_t n, unsigned long long n_keys, unsigned long long *__restrict__ elems,
+                                  unsigned int *__restrict__ bad) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long k = (unsigned long long)__ldg(keys + i);
+        if (k >= n_keys) {
+            *bad = 1u;
+            k = 0;
+        }
+        elems[i] = (k << 32) | (unsigned long long)(uint32_t)i;
+    }
+}
+// reference_kmer_index.py:92-118: ref_position_to_index[p] = first sorted position of p for every present position but
+// the smallest (ediff1d(..., to_begin=0) leaves the first run unmarked), then fill_zeros_from_end gives every other
+// slot the value of the next marked slot to its right.  Run head i >= 1 therefore owns the slots (key[i-1], key[i]],
+// and the head of the second run also owns [0, key[0]].  Short ranges are filled in place, long ones are queued.
+constexpr int FILL_INLINE = 32;
+__global__ void ref_heads_fill_kernel(const unsigned long long *__restrict__ sorted, int64_t n, uint32_t *__restrict__ first,
+                                      uint4 *__restrict__ work, unsigned int *__restrict__ n_work) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i == 0) continue;
+        const uint32_t k = elem_key(__ldg(sorted + i)), kp = elem_key(__ldg(sorted + i - 1));
+        if (k == kp) continue;
+        const uint32_t lo = (kp == elem_key(__ldg(sorted))) ? 0u : kp + 1u;
+        if (k - lo < (uint32_t)FILL_INLINE) {
+            for (uint32_t r = lo; r <= k; r++) first[r] = (uint32_t)i;
+        } else {
+            work[atomicAdd(n_work, 1u)] = make_uint4(lo, k, (uint32_t)i, 0u);
+        }
+    }
+}
+__global__ void ref_long_fill_kernel(const uint4 *__restrict__ work, const unsigned int *__restrict__ n_work, uint32_t *__restrict__ first) {
+    const unsigned int nw = *n_work;
+    for (unsigned int w = blockIdx.x; w < nw; w += gridDim.x) {
+        const uint4 item = work[w];
+        for (uint64_t r = (uint64_t)item.x + threadIdx.x; r <= item.y; r += blockDim.x) first[r] = item.z;
+    }
+}
+__global__ void count_long_gaps_kernel(const unsigned long long *__restrict__ sorted, int64_t n, unsigned int *__restrict__ n_long) {
+    unsigned int local = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (i == 0) continue;
+        const uint32_t k = elem_key(__ldg(sorted + i)), kp = elem_key(__ldg(sorted + i - 1));
+        if (k == kp) continue;
+        const uint32_t lo = (kp == elem_key(__ldg(sorted))) ? 0u : kp + 1u;
+        local += (k - lo >= (uint32_t)FILL_INLINE);
+    }
+    if (local) atomicAdd(n_long, local);
+}
+
 // shared with count.cu: stable sort of n packed (key << 32 | payload) elements held in `a` by the low key_bits of the key
 int radix_sort_packed(Scratch &a, Scratch &b, Scratch &hist, int64_t n, int key_bits, const unsigned long long **sorted, cudaStream_t s) {
     SortBuffers bufs;
@@ -527,6 +578,80 @@ int gki_partition_by_bucket_range(const uint64_t *kmers, int64_t n, uint64_t mod
         GKI_TRY(o_perm.finish(s));
     }
     GKI_TRY(o_counts.finish(s));
+    return call.finish();
+}
+
+int gki_group_by_key(const void *keys, int32_t key_size, int64_t n, uint64_t n_keys, int32_t flags, uint32_t *perm_out,
+                     uint32_t *first_out, uint32_t *count_out, gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    const bool ref_mode = (flags & GKI_GROUP_REFERENCE_INDEX) != 0;
+    GKI_REQUIRE((key_size == 4 || key_size == 8) && n >= 1 && n < (1ll << 32) - 1 && n_keys >= 1 && n_keys <= (1ull << 32) && keys,
+                GKI_ERR_INVALID, "gki_group_by_key: need 4- or 8-byte keys, 1 <= n < 2^32-1, 1 <= n_keys <= 2^32");
+    GKI_REQUIRE(!(ref_mode && count_out), GKI_ERR_INVALID, "gki_group_by_key: count_out is not defined with GKI_GROUP_REFERENCE_INDEX");
+    DevIn d_keys;
+    DevOut o_perm, o_first, o_count;
+    GKI_TRY(d_keys.stage(keys, (size_t)n * key_size, s));
+    GKI_TRY(o_perm.prepare(perm_out, (size_t)n * 4, s));
+    GKI_TRY(o_first.prepare(first_out, (size_t)n_keys * 4, s));
+    GKI_TRY(o_count.prepare(count_out, (size_t)n_keys * 4, s));
+    Scratch flagbuf;
+    GKI_TRY(flagbuf.alloc(16, s));
+    GKI_CUDA(cudaMemsetAsync(flagbuf.ptr, 0, 16, s));
+    unsigned int *d_flags = flagbuf.as<unsigned int>();   // [0] key out of range, [1] long runs / long gaps, [2] work items
+    SortBuffers bufs;
+    GKI_TRY(bufs.elems[0].alloc((size_t)n * 8, s));
+    const int grid = grid_for(n, 256 * 4, device_info().sms * 16);
+    if (key_size == 4) group_keys_kernel<uint32_t><<<grid, 256, 0, s>>>(d_keys.as<uint32_t>(), n, n_keys, bufs.elems[0].as<unsigned long long>(), d_flags);
+    else group_keys_kernel<unsigned long long><<<grid, 256, 0, s>>>(d_keys.as<unsigned long long>(), n, n_keys, bufs.elems[0].as<unsigned long long>(), d_flags);
+    GKI_CHECK_LAUNCH();
+    const unsigned long long *sorted;
+    GKI_TRY(radix_sort_elems(bufs, n, bit_length(n_keys - 1) ? bit_length(n_keys - 1) : 1, &sorted, s));
+    if (o_perm.dptr) {
+        extract_perm_kernel<<<grid, 256, 0, s>>>(sorted, n, o_perm.as<uint32_t>());
+        GKI_CHECK_LAUNCH();
+    }
+    if (o_first.dptr) GKI_CUDA(cudaMemsetAsync(o_first.dptr, 0, (size_t)n_keys * 4, s));
+    if (o_count.dptr) GKI_CUDA(cudaMemsetAsync(o_count.dptr, 0, (size_t)n_keys * 4, s));
+    Scratch work;
+    if (ref_mode && o_first.dptr) {
+        count_long_gaps_kernel<<<grid, 256, 0, s>>>(sorted, n, d_flags + 1);
+        GKI_CHECK_LAUNCH();
+        unsigned int host_flags[2];
+        GKI_CUDA(cudaMemcpyAsync(host_flags, d_flags, 8, cudaMemcpyDeviceToHost, s));
+        GKI_CUDA(cudaStreamSynchronize(s));
+        GKI_REQUIRE(host_flags[0] == 0, GKI_ERR_INVALID, "gki_group_by_key: a key is >= n_keys");
+        GKI_TRY(work.alloc(((size_t)host_flags[1] + 1) * 16, s));
+        ref_heads_fill_kernel<<<grid, 256, 0, s>>>(sorted, n, o_first.as<uint32_t>(), work.as<uint4>(), d_flags + 2);
+        GKI_CHECK_LAUNCH();
+        if (host_flags[1]) {
+            ref_long_fill_kernel<<<device_info().sms * 8, 256, 0, s>>>(work.as<uint4>(), d_flags + 2, o_first.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+        }
+    } else if (o_first.dptr || o_count.dptr) {
+        Scratch tmp_first, tmp_count;   // run_heads writes both tables
+        int32_t *h2i = (int32_t *)o_first.dptr;
+        uint32_t *nk = (uint32_t *)o_count.dptr;
+        if (!h2i) {
+            GKI_TRY(tmp_first.alloc((size_t)n_keys * 4, s));
+            h2i = tmp_first.as<int32_t>();
+        }
+        if (!nk) {
+            GKI_TRY(tmp_count.alloc((size_t)n_keys * 4, s));
+            nk = tmp_count.as<uint32_t>();
+        }
+        run_heads_kernel<<<grid, 256, 0, s>>>(sorted, n, h2i, nk, d_flags + 1);
+        GKI_CHECK_LAUNCH();
+        run_tails_kernel<<<grid, 256, 0, s>>>(sorted, n, h2i, nk, d_flags + 1);
+        GKI_CHECK_LAUNCH();
+        unsigned int bad = 0;
+        GKI_CUDA(cudaMemcpyAsync(&bad, d_flags, 4, cudaMemcpyDeviceToHost, s));
+        GKI_CUDA(cudaStreamSynchronize(s));
+        GKI_REQUIRE(bad == 0, GKI_ERR_INVALID, "gki_group_by_key: a key is >= n_keys");
+    }
+    GKI_TRY(o_perm.finish(s));
+    GKI_TRY(o_first.finish(s));
+    GKI_TRY(o_count.finish(s));
     return call.finish();
 }
 

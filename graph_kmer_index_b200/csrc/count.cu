@@ -49,7 +49,7 @@ __device__ __forceinline__ uint32_t filter_word(const TableView &t, const Hash &
     return __umulhi(g, t.filter_words);
 }
 __device__ __forceinline__ uint32_t filter_mask(const TableView &t, const Hash &h) {
-    uint32_t b = h.f * 0xC2B2AE35u;
+    uint32_t b = h.hi * 0xC2B2AE35u;     // bit positions from the high half, word from the fold: 64 bits of the product are used
     uint32_t mask = 1u << (b >> 27);
     if (t.filter_k > 1) mask |= 1u << ((b >> 22) & 31);
     if (t.filter_k > 2) mask |= 1u << ((b >> 17) & 31);
@@ -107,25 +107,39 @@ __device__ __forceinline__ unsigned long long ld_u64_hint(const unsigned long lo
 __device__ __forceinline__ void load_bucket_keys(const Bucket *bk, unsigned long long (&key)[SLOTS_PER_BUCKET]) {
     asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(key[0]), "=l"(key[1]), "=l"(key[2]), "=l"(key[3]) : "l"(bk));
 }
+__device__ __forceinline__ void load_bucket_keys_64B(const Bucket *bk, unsigned long long (&key)[SLOTS_PER_BUCKET]) {   // experiment: 64-byte L2 fill
+    asm("ld.global.nc.L2::64B.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(key[0]), "=l"(key[1]), "=l"(key[2]), "=l"(key[3]) : "l"(bk));
+}
 __device__ __forceinline__ void load_bucket_keys_hint(const Bucket *bk, unsigned long long (&key)[SLOTS_PER_BUCKET], unsigned long long pol) {
     asm("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(key[0]), "=l"(key[1]), "=l"(key[2]), "=l"(key[3]) : "l"(bk), "l"(pol));
 }
 
-// counter pair {cnt[0], cnt[1]} of key c (c != SLOT_EMPTY) starting at bucket b, or nullptr.  Probing visits buckets
-// linearly and stops at the first non-full bucket.
-template <bool HINT = false>
-__device__ __forceinline__ uint32_t *find_slot_from(const TableView &t, unsigned long long c, uint32_t b, unsigned long long pol = 0) {
-    for (uint32_t tries = 0; tries < t.n_buckets; tries++) {
+// Probe order: HBM fills L2 in whole 128-byte lines on this part (measured: 127 B of DRAM reads per random 8-byte gather,
+// profiles/r1/calibrate_gather_ncu.txt), so a line holds two 64-byte buckets and the second one is free once the first
+// was fetched: home bucket, then its line mate, then the next line starting with the same half.  n_buckets is even.
+__device__ __forceinline__ uint32_t next_bucket(const TableView &t, uint32_t b, uint32_t tries) {
+    if (!(tries & 1u)) return b ^ 1u;
+    b = (b ^ 1u) + 2u;
+    return b >= t.n_buckets ? b - t.n_buckets : b;
+}
+
+// counter pair {cnt[0], cnt[1]} of key c (c != SLOT_EMPTY) starting at bucket b, or nullptr.  Probing follows
+// next_bucket and stops at the first non-full bucket.
+template <int HINT = 0>
+__device__ __forceinline__ uint32_t *find_slot_from(const TableView &t, unsigned long long c, uint32_t b, unsigned long long pol = 0,
+                                                    uint32_t tries0 = 0) {
+    for (uint32_t tries = tries0; tries < t.n_buckets; tries++) {
         Bucket *bk = t.buckets + b;
         unsigned long long key[SLOTS_PER_BUCKET];   // keys never change while a counting kernel runs
-        if (HINT) load_bucket_keys_hint(bk, key, pol);
+        if (HINT == 1) load_bucket_keys_hint(bk, key, pol);
+        else if (HINT == 2) load_bucket_keys_64B(bk, key);
         else load_bucket_keys(bk, key);
 #pragma unroll
         for (int i = 0; i < SLOTS_PER_BUCKET; i++) {
             if (key[i] == c) return bk->cnt[i];
             if (key[i] == SLOT_EMPTY) return nullptr;
         }
-        b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+        b = next_bucket(t, b, tries);
     }
     return nullptr;
 }
@@ -206,7 +220,7 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
                 if (cur == SLOT_EMPTY) cur = atomicCAS(&bk->key[i], SLOT_EMPTY, key.c);
                 placed = (cur == SLOT_EMPTY) || (cur == key.c);
             }
-            b = (b + 1 == t.n_buckets) ? 0 : b + 1;
+            b = next_bucket(t, b, tries);
         }
         if (!placed) atomicAdd(failed, 1u);
     }
@@ -241,7 +255,7 @@ struct WarpBatch {
 };
 
 constexpr int WPL = 4;   // consecutive windows per lane
-constexpr int QCAP = 64;  // survivor queue capacity per warp (< 32 pending + <= 32 pushed per ballot)
+constexpr int QCAP = 128;  // survivor queue capacity per warp (32 in flight + < 32 waiting + <= 32 pushed per ballot)
 
 template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
@@ -263,12 +277,46 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
     const uint64_t mask = kmer_mask(b.k);
     const uint32_t tile_bytes = (uint32_t)b.rpw * (uint32_t)b.read_len;
     uint32_t qn = 0, qhead = 0;   // warp-uniform: entries pushed / consumed so far
+    // HINTS bit 5: the probe is split in two -- the bucket keys of 32 survivors are requested (probe_issue) and only
+    // compared when the next 32 are ready (probe_complete), so the HBM round trip is covered by the warp's own filter work
+    constexpr bool PIPE = (HINTS & 32) != 0;
+    unsigned long long pk[SLOTS_PER_BUCKET] = {0, 0, 0, 0};
+    uint32_t n_flight = 0;        // warp-uniform: entries [qhead, qhead + n_flight) have their bucket load in flight
+    auto probe_issue = [&](uint32_t n) {
+        if ((uint32_t)lane < n) load_bucket_keys(t.buckets + (qmeta[(qhead + lane) & (QCAP - 1)] & 0x7fffffffu), pk);
+        n_flight = n;
+    };
+    auto probe_complete = [&]() {
+        if ((uint32_t)lane < n_flight) {
+            const uint32_t idx = (qhead + lane) & (QCAP - 1);
+            const unsigned long long key = qkey[idx];
+            const uint32_t meta = qmeta[idx], home = meta & 0x7fffffffu;
+            uint32_t *cnt = nullptr;
+            bool full = true;
+#pragma unroll
+            for (int i = 0; i < SLOTS_PER_BUCKET; i++) {
+                if (full && pk[i] == key) {
+                    cnt = t.buckets[home].cnt[i];
+                    full = false;
+                }
+                if (pk[i] == SLOT_EMPTY) full = false;
+            }
+            if (full) cnt = find_slot_from(t, key, next_bucket(t, home, 0), 0ull, 1);   // rare: continue with the line mate
+            if (cnt) {
+                if (meta >> 31) atomicAdd(cnt, 2u);
+                else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);
+            }
+        }
+        qhead += n_flight;
+        n_flight = 0;
+        __syncwarp();
+    };
     auto probe_queue = [&](uint32_t n) {   // the first n queued survivors, one per lane: bucket line from HBM, compare, RED
-        if ((uint32_t)lane < n) {
+        if (!(HINTS & 16) && (uint32_t)lane < n) {   // HINTS bit 4: experiment only, survivors are dropped
             const uint32_t idx = (qhead + lane) & (QCAP - 1);
             const unsigned long long key = qkey[idx];
             const uint32_t meta = qmeta[idx];
-            uint32_t *cnt = find_slot_from<(HINTS & 2) != 0>(t, key, meta & 0x7fffffffu, pol_first);
+            uint32_t *cnt = find_slot_from<(HINTS & 2) ? 1 : ((HINTS & 64) ? 2 : 0)>(t, key, meta & 0x7fffffffu, pol_first);
             if (cnt) {
                 if (meta >> 31) atomicAdd(cnt, 2u);                                              // palindrome (even k)
                 else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);                // +1 on both orientations
@@ -390,11 +438,19 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         const uint32_t votes = __ballot_sync(0xffffffffu, mine);
                         if (mine) {
                             uint32_t slot_idx = (qn + __popc(votes & ((1u << lane) - 1u))) & (QCAP - 1);
+                            const uint32_t home = home_bucket(t, h[u]);
                             qkey[slot_idx] = c[u];
-                            qmeta[slot_idx] = home_bucket(t, h[u]) | (((pal >> u) & 1u) << 31);
+                            qmeta[slot_idx] = home | (((pal >> u) & 1u) << 31);
+                            if (HINTS & 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.buckets + home));   // line is in L2 by the time the queue is probed
                         }
                         qn += __popc(votes);
-                        if (qn - qhead >= 32) {
+                        if (PIPE) {
+                            if (qn - qhead - n_flight >= 32) {
+                                __syncwarp();
+                                probe_complete();
+                                probe_issue(32);
+                            }
+                        } else if (qn - qhead >= 32) {
                             __syncwarp();
                             probe_queue(32);
                         }
@@ -412,10 +468,9 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
         }
         __syncwarp();
     }
-    if (qn != qhead) {   // drain the queue
-        __syncwarp();
-        probe_queue(qn - qhead);
-    }
+    __syncwarp();
+    if (PIPE) probe_complete();
+    if (qn != qhead) probe_queue(qn - qhead);   // drain the queue
 }
 
 // ------------------------------------------------------------------ counters -> per-entry / per-node
@@ -506,7 +561,7 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
 
     TableView t{};
     t.k = k;
-    uint64_t buckets = (distinct + 1) / 2 + 16;          // 4 slots per bucket -> load factor <= 0.5
+    uint64_t buckets = ((distinct + 1) / 2 + 17) & ~1ull;   // 4 slots per bucket -> load factor <= 0.5; even (next_bucket)
     GKI_REQUIRE(buckets < (1ull << 31), GKI_ERR_UNSUPPORTED, "count table: too many distinct k-mers");
     t.n_buckets = (uint32_t)buckets;
     const size_t n_slots = ((size_t)buckets + 1) * SLOTS_PER_BUCKET;
@@ -644,6 +699,12 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     if (hints == 3) return launch_count_reads_t<true, true, 4, 3>(ix, b, s);
     if (hints == 4) return launch_count_reads_t<true, true, 4, 4>(ix, b, s);
     if (hints == 5) return launch_count_reads_t<true, true, 4, 5>(ix, b, s);
+    if (hints == 8) return launch_count_reads_t<true, true, 4, 8>(ix, b, s);
+    if (hints == 9) return launch_count_reads_t<true, true, 4, 9>(ix, b, s);
+    if (hints == 16) return launch_count_reads_t<true, true, 4, 16>(ix, b, s);
+    if (hints == 32 && minb == 3) return launch_count_reads_t<true, true, 3, 32>(ix, b, s);
+    if (hints == 32) return launch_count_reads_t<true, true, 4, 32>(ix, b, s);
+    if (hints == 64) return launch_count_reads_t<true, true, 4, 64>(ix, b, s);
     if (minb == 5) return launch_count_reads_t<true, true, 5>(ix, b, s);
     if (minb == 6) return launch_count_reads_t<true, true, 6>(ix, b, s);
     if (minb == 3) return launch_count_reads_t<true, true, 3>(ix, b, s);

@@ -56,9 +56,26 @@ __global__ void synth_reads_kernel(const uint8_t *__restrict__ g, int64_t glen, 
     }
 }
 
-// dependent == 0: each thread issues independent gathers; dependent == 1: each gather's address depends on the
-// previous value (2-deep chain like cell -> chain).
-__global__ void random_gather_kernel(const uint64_t *__restrict__ table, uint64_t n_words, int64_t n_gathers, int dependent,
+// mode bit 0: each gather is followed by a second one whose address depends on the loaded value (2-deep chain like
+// cell -> chain); bit 1: loads carry the L2::64B fill-size qualifier (default fill on B200 is the whole 128-byte line).
+// Addresses come from a 32-bit multiply-xorshift hash and a multiply-high range reduction, a handful of
+// instructions per gather, so the kernel measures the memory system and not the address arithmetic.
+template <bool FILL64>
+__device__ __forceinline__ uint64_t gather_load(const uint64_t *p) {
+    uint64_t v;
+    if (FILL64) asm volatile("ld.global.nc.L2::64B.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    else v = __ldg(p);
+    return v;
+}
+__device__ __forceinline__ uint32_t gather_slot(uint32_t x, uint32_t n_words) {
+    x *= 0x9E3779B1u;
+    x ^= x >> 15;
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 13;
+    return __umulhi(x, n_words);
+}
+template <bool FILL64>
+__global__ void random_gather_kernel(const uint64_t *__restrict__ table, uint32_t n_words, int64_t n_gathers, int dependent,
                                      uint64_t *__restrict__ sink) {
     uint64_t acc = 0;
     const int64_t T = (int64_t)gridDim.x * blockDim.x;
@@ -67,11 +84,11 @@ __global__ void random_gather_kernel(const uint64_t *__restrict__ table, uint64_
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             int64_t idx = i + j * T;
-            v[j] = idx < n_gathers ? __ldg(table + splitmix64((uint64_t)idx) % n_words) : 0;
+            v[j] = idx < n_gathers ? gather_load<FILL64>(table + gather_slot((uint32_t)idx, n_words)) : 0;
         }
         if (dependent) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) v[j] = __ldg(table + (v[j] ^ splitmix64(v[j] + j)) % n_words);
+            for (int j = 0; j < 4; j++) v[j] = gather_load<FILL64>(table + gather_slot((uint32_t)v[j] + j, n_words));
         }
 #pragma unroll
         for (int j = 0; j < 4; j++) acc += v[j];
@@ -145,8 +162,11 @@ int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t fir
 }
 
 int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms) {
-    GKI_REQUIRE(table_bytes >= 8 && n_gathers >= 1 && ms, GKI_ERR_INVALID, "gki_calibrate_random_gather: bad arguments");
+    GKI_REQUIRE(table_bytes >= 8 && table_bytes <= (32ll << 30) && n_gathers >= 1 && ms, GKI_ERR_INVALID,
+                "gki_calibrate_random_gather: bad arguments");
     uint64_t n_words = (uint64_t)table_bytes / 8;
+    const int dependent = dependent_loads & 1;
+    const bool fill64 = (dependent_loads & 2) != 0;
     uint64_t *table = nullptr, *sink = nullptr;
     GKI_CUDA(cudaMalloc((void **)&table, n_words * 8));
     GKI_CUDA(cudaMalloc((void **)&sink, 8));
@@ -156,10 +176,14 @@ int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t 
     cudaEvent_t a, b;
     GKI_CUDA(cudaEventCreate(&a));
     GKI_CUDA(cudaEventCreate(&b));
-    random_gather_kernel<<<grid, 256>>>(table, n_words, n_gathers / 8 + 1, dependent_loads, sink);   // warm-up
+    auto run = [&](int64_t n) {
+        if (fill64) random_gather_kernel<true><<<grid, 256>>>(table, (uint32_t)n_words, n, dependent, sink);
+        else random_gather_kernel<false><<<grid, 256>>>(table, (uint32_t)n_words, n, dependent, sink);
+    };
+    run(n_gathers / 8 + 1);   // warm-up
     GKI_CHECK_LAUNCH();
     GKI_CUDA(cudaEventRecord(a));
-    random_gather_kernel<<<grid, 256>>>(table, n_words, n_gathers, dependent_loads, sink);
+    run(n_gathers);
     GKI_CHECK_LAUNCH();
     GKI_CUDA(cudaEventRecord(b));
     GKI_CUDA(cudaEventSynchronize(b));

@@ -108,6 +108,19 @@ int gki_index_build_range(const uint64_t *kmers, const uint32_t *nodes, const ui
                           int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,
                           uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out, gki_stream_t stream);
 
+/* Side indexes keyed by node or reference position: ReverseKmerIndex.from_flat_kmers (reverse_kmer_index.py:59-84,
+ * key = node) and ReferenceKmerIndex.from_flat_kmers (reference_kmer_index.py:81-121, key = ref_offset).
+ * Stable grouping of n entries by an integer key < n_keys <= 2^32 (keys: 4- or 8-byte unsigned, key_size says which):
+ *   perm_out[n] u32      stable argsort of the keys; the caller moves its columns with gki_gather
+ *   first_out[n_keys] u32, count_out[n_keys] u32   first sorted position and run length of every key, 0 when absent
+ * flags GKI_GROUP_REFERENCE_INDEX: first_out is ReferenceKmerIndex.ref_position_to_index instead -- the smallest key
+ *   is left unmarked (np.ediff1d(..., to_begin=0), :92) and every unmarked slot takes the value of the next marked
+ *   slot to its right (fill_zeros_from_end, :16-21); count_out must be NULL.
+ * Any output may be NULL. */
+#define GKI_GROUP_REFERENCE_INDEX 1
+int gki_group_by_key(const void *keys, int32_t key_size, int64_t n, uint64_t n_keys, int32_t flags, uint32_t *perm_out,
+                     uint32_t *first_out, uint32_t *count_out, gki_stream_t stream);
+
 /* out[i] = src[perm[i]] for items of item_size in {1,2,4,8} bytes (cfki:436-440 for any dtype). */
 int gki_gather(const void *src, int32_t item_size, const uint32_t *perm, int64_t n, void *out, gki_stream_t stream);
 
@@ -220,8 +233,10 @@ int gki_synth_flat_kmers(const uint8_t *genome_codes, int64_t n_entries, int64_t
                          uint32_t *nodes, uint64_t *ref_offsets, float *af, gki_stream_t stream);
 int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t first_read, int64_t n_reads,
                     int32_t read_len, int32_t p_hit_permille, int32_t n_permille, uint8_t *reads, gki_stream_t stream);
-/* random 8-byte gathers over a table of table_bytes (power of two not required): the measured
- * random-access ceiling K3 is compared with.  *ms receives the kernel time. Synchronous. */
+/* random 8-byte gathers over a table of table_bytes (<= 32 GB, power of two not required): the measured
+ * random-access ceiling K3 is compared with.  dependent_loads bit 0: every gather is followed by a dependent second
+ * one; bit 1: loads ask for a 64-byte L2 fill (ld.global.nc.L2::64B) instead of the default whole line.
+ * *ms receives the kernel time. Synchronous. */
 int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms);
 int gki_calibrate_copy(int64_t bytes, float *ms);
 

@@ -274,3 +274,40 @@ def read_node_counts(index, reads_u8, k, min_nodes=0, both_strands=True):
     fwd, rc = hash_reads(reads_u8, k)
     q = np.concatenate([fwd.ravel(), rc.ravel()]) if both_strands else fwd.ravel()
     return node_counts(index, q, min_nodes)
+
+
+# ---- side indexes keyed by node / reference position ----------------------------------------------------
+def reverse_index(hashes, nodes, ref_offsets):
+    """reverse_kmer_index.py:59-84 with a stable argsort -> (nodes_to_index_positions u32, nodes_to_n_hashes u16 (wraps),
+    hashes, ref_positions)."""
+    nodes = np.asarray(nodes)
+    order = np.argsort(nodes, kind="stable")
+    s_nodes = nodes[order]
+    first = np.zeros(int(s_nodes[-1]) + 1, dtype=np.uint32)
+    n_kmers = np.zeros(int(s_nodes[-1]) + 1, dtype=np.uint16)
+    heads = np.flatnonzero(np.concatenate([[True], s_nodes[1:] != s_nodes[:-1]]))
+    first[s_nodes[heads]] = heads
+    n_kmers[s_nodes[heads]] = (np.diff(np.concatenate([heads, [len(nodes)]])) & 0xFFFF).astype(np.uint16)
+    return first, n_kmers, np.asarray(hashes)[order], np.asarray(ref_offsets)[order]
+
+
+def reference_index(hashes, nodes, ref_offsets):
+    """reference_kmer_index.py:81-121 with a stable argsort -> (ref_position_to_index u32, kmers (u32 if all < 2^32),
+    ref_positions, nodes).  The first run is left unmarked (:92, to_begin=0) and unmarked slots take the next marked value
+    to their right (:16-21)."""
+    ref = np.asarray(ref_offsets)
+    order = np.argsort(ref, kind="stable")
+    s_ref = ref[order]
+    kmers = np.asarray(hashes)[order]
+    if kmers.max() < 2 ** 32:
+        kmers = kmers.astype(np.uint32)
+    heads = np.flatnonzero(s_ref[1:] != s_ref[:-1]) + 1            # run heads except the first run
+    table = np.zeros(int(s_ref[-1]) + 1, dtype=np.uint32)
+    table[s_ref[heads].astype(np.int64)] = heads
+    out = np.zeros_like(table)
+    nxt = 0
+    for p in range(len(table) - 1, -1, -1):                        # small cases only
+        if table[p]:
+            nxt = table[p]
+        out[p] = nxt
+    return out, kmers, s_ref, np.asarray(nodes)[order]

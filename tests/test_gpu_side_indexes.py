@@ -1,0 +1,115 @@
+"""GPU parity of ReverseKmerIndex / ReferenceKmerIndex (gki_group_by_key) against the fixtures generated from the
+unmodified reference (tests/golden/make_golden_side_indexes.py), the numpy oracle on larger seeded inputs, and the
+reference's own test (tests/test_reverse_kmer_index.py)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gki():
+    import graph_kmer_index_b200 as g
+    return g
+
+
+def same(got, want, what):
+    assert got.dtype == want.dtype, (what, got.dtype, want.dtype)
+    assert np.array_equal(got, want), what
+
+
+def test_reference_reverse_index_test(gki, tmp_path):
+    """tests/test_reverse_kmer_index.py:5-19."""
+    flat = gki.FlatKmers(np.array([10, 3, 11, 4]), np.array([5, 3, 5, 8]))
+    reverse = gki.ReverseKmerIndex.from_flat_kmers(flat)
+    assert 11 in reverse.get_node_kmers(5)
+    assert 10 in reverse.get_node_kmers(5)
+    assert 3 in reverse.get_node_kmers(3)
+    assert 4 in reverse.get_node_kmers(8)
+    reverse.to_file(str(tmp_path / "tmp.reverse"))
+    new_reverse = gki.ReverseKmerIndex.from_file(str(tmp_path / "tmp.reverse.npz"))
+    assert 3 in new_reverse.get_node_kmers(3)
+    assert list(new_reverse.get_node_kmers(4)) == []
+
+
+def test_side_indexes_golden(gki, tmp_path):
+    g = load_golden("side_indexes")
+    for name in g["names"]:
+        flat = gki.FlatKmers(g[name + "/hashes"], g[name + "/nodes"], g[name + "/ref_offsets"])
+        rev = gki.ReverseKmerIndex.from_flat_kmers(flat)
+        same(rev.nodes_to_index_positions, g[name + "/rev_nodes_to_index_positions"], (name, "nodes_to_index_positions"))
+        same(rev.nodes_to_n_hashes, g[name + "/rev_nodes_to_n_hashes"], (name, "nodes_to_n_hashes"))
+        same(rev.hashes, g[name + "/rev_hashes"], (name, "hashes"))
+        same(rev.ref_positions, g[name + "/rev_ref_positions"], (name, "ref_positions"))
+        ref = gki.ReferenceKmerIndex.from_flat_kmers(flat)
+        same(ref.ref_position_to_index, g[name + "/ref_ref_position_to_index"], (name, "ref_position_to_index"))
+        same(ref.kmers, g[name + "/ref_kmers"], (name, "kmers"))
+        same(ref.ref_positions, g[name + "/ref_ref_positions"], (name, "ref_positions"))
+        same(ref.nodes, g[name + "/ref_nodes"], (name, "nodes"))
+    # npz round trip (reference_kmer_index.py:123-160)
+    ref.to_file(str(tmp_path / "refindex"))
+    back = gki.ReferenceKmerIndex.from_file(str(tmp_path / "refindex"))
+    same(back.ref_position_to_index, ref.ref_position_to_index, "round trip")
+    assert list(back.get_between(1, 4)) == list(ref.kmers[ref.ref_position_to_index[1]:ref.ref_position_to_index[4]])
+
+
+def test_reference_index_from_sequence(gki):
+    g = load_golden("side_indexes")
+    seq = g["seq"].tobytes().decode()
+    for k in (5, 16, 31):
+        idx = gki.ReferenceKmerIndex.from_sequence(seq, k)
+        same(idx.kmers, g["seq_k%d_kmers" % k], ("kmers", k))
+        same(idx.ref_position_to_index, g["seq_k%d_index" % k], ("index", k))
+    only = gki.ReferenceKmerIndex.from_sequence(seq, 31, only_store_kmers=True)
+    assert only.ref_position_to_index is None
+    same(only.kmers, g["seq_k31_kmers"], "only_store_kmers")
+
+
+@pytest.mark.parametrize("n,n_nodes,max_ref", [(200_000, 30_000, 150_000), (1_000_000, 5, 4_000_000_000), (300_000, 250_000, 40)])
+def test_side_indexes_vs_oracle(gki, n, n_nodes, max_ref):
+    rng = np.random.default_rng(n + n_nodes)
+    hashes = rng.integers(0, 2 ** 62, n, dtype=np.uint64)
+    nodes = rng.integers(0, n_nodes, n).astype(np.uint32)
+    if max_ref > 2 ** 31:        # sparse positions, long gaps, values above 2^31
+        ref = np.sort(rng.choice(np.arange(0, max_ref, 4001, dtype=np.uint64), size=n // 50))[rng.integers(0, n // 50, n)]
+        ref = ref // 1000       # keep the table small enough for the oracle's Python loop
+    else:
+        ref = rng.integers(0, max_ref, n).astype(np.uint64)
+    flat = gki.FlatKmers(hashes, nodes, ref)
+    rev = gki.ReverseKmerIndex.from_flat_kmers(flat)
+    for got, want in zip((rev.nodes_to_index_positions, rev.nodes_to_n_hashes, rev.hashes, rev.ref_positions), no.reverse_index(hashes, nodes, ref)):
+        same(got, want, "reverse")
+    refi = gki.ReferenceKmerIndex.from_flat_kmers(flat)
+    for got, want in zip((refi.ref_position_to_index, refi.kmers, refi.ref_positions, refi.nodes), no.reference_index(hashes, nodes, ref)):
+        same(got, want, "reference")
+
+
+def test_group_by_key_properties(gki):
+    """Full-size properties: the permutation is a stable sort, first/count describe the runs."""
+    from graph_kmer_index_b200.reverse_kmer_index import group_by_key
+    rng = np.random.default_rng(3)
+    n, n_keys = 20_000_000, 3_000_000
+    keys = rng.integers(0, n_keys, n).astype(np.uint32)
+    perm, first, counts = group_by_key(keys, n_keys)
+    s = keys[perm]
+    assert np.all(s[1:] >= s[:-1])
+    same_key = s[1:] == s[:-1]
+    assert np.all(perm[1:][same_key] > perm[:-1][same_key])          # stable
+    assert np.array_equal(counts, np.bincount(keys, minlength=n_keys).astype(np.uint32))
+    present = counts > 0
+    assert np.array_equal(first[present], (np.cumsum(counts) - counts)[present].astype(np.uint32))
+    assert not first[~present].any()
+
+
+def test_group_by_key_errors(gki):
+    from graph_kmer_index_b200 import _lib
+    from graph_kmer_index_b200.reverse_kmer_index import group_by_key
+    with pytest.raises(_lib.GkiError):
+        group_by_key(np.array([1, 2, 9], dtype=np.uint32), 5)            # key >= n_keys
+    with pytest.raises(_lib.GkiError):
+        group_by_key(np.zeros(0, dtype=np.uint32), 5)                    # empty (np.max of an empty array raises in the reference)
