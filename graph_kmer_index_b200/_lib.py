@@ -13,9 +13,9 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libgki.so")
-SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "count.cu", "build.cu", "synth.cu", "finder.cu"]
+SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "count.cu", "build.cu", "synth.cu", "finder.cu", "ingest.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-lpthread"]
 
 
 class GkiError(RuntimeError):
@@ -30,7 +30,7 @@ def needs_build():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = _sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + [os.path.join(_PKG, "..", "include", "gki.h")]
+    deps = _sources() + glob.glob(os.path.join(_CSRC, "*.cuh")) + glob.glob(os.path.join(_CSRC, "*.h")) + [os.path.join(_PKG, "..", "include", "gki.h")]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -74,6 +74,8 @@ _SIGNATURES = {
     "gki_index_info": [c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_u64), ctypes.POINTER(c_i64),
                        ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i64)],
     "gki_prepare_counting": [c_vp, c_i32, c_vp],
+    "gki_pack_reads": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32, c_i32],
+    "gki_count_packed_reads": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp],
     "gki_reset_counts": [c_vp, c_vp],
     "gki_count_kmers": [c_vp, c_vp, c_i64, c_vp],
     "gki_count_reads": [c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp],

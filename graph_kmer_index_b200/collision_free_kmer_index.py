@@ -100,6 +100,13 @@ class DeviceIndex:
             p = reads.data_ptr()
         _lib.call("gki_count_reads", self.handle, p, n, L, stride, k, int(both_strands), _lib.current_stream())
 
+    def count_packed_reads(self, packed, read_len, k, both_strands=True):
+        """packed: (n_reads, ceil(read_len/32)) uint64 rows from read_kmers.pack_reads (numpy, or a torch tensor on host / device;
+        torch has no uint64 arithmetic, an int64 tensor with the same bits is fine)."""
+        assert packed.shape[1] == (read_len + 31) // 32
+        _lib.call("gki_count_packed_reads", self.handle, _lib.ptr(packed), int(packed.shape[0]), int(read_len), k, int(both_strands),
+                  _lib.current_stream())
+
     def node_counts(self, min_nodes=0, out=None, wrap_uint16=False):
         n_out = max(int(min_nodes), self.max_node + 1)
         if out is None:

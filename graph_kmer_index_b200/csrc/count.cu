@@ -22,7 +22,16 @@
 // bulk copies (double-buffered on per-warp mbarriers), packs them to 2 bits per base and walks them with a
 // rolling window -- no CTA-wide barrier anywhere, so a warp that waits on HBM never stalls its neighbours.
 #include <stdlib.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
 #include "index.cuh"
+#include "ingest.h"
 #include "reads_tile.cuh"
 
 namespace gki {
@@ -257,7 +266,9 @@ struct WarpBatch {
 constexpr int WPL = 4;   // consecutive windows per lane
 constexpr int QCAP = 128;  // survivor queue capacity per warp (32 in flight + < 32 waiting + <= 32 pushed per ballot)
 
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0>
+// PACKED: the batch is already 2 bits per base (gki_pack_reads layout: read r owns b.words 64-bit words, every byte was
+// one of ACGTacgt) -- the tile lands straight in the code words, double-buffered, and the pack phase disappears.
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
     const unsigned long long pol_last = (HINTS & 1) ? l2_policy_evict_last() : 0ull;
     const unsigned long long pol_first = (HINTS & 2) ? l2_policy_evict_first() : 0ull;
@@ -271,11 +282,16 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
     uint8_t *ascii = wbase + 16;
     uint64_t *codes = (uint64_t *)(wbase + 16 + (size_t)b.stage_bytes);
     uint64_t *valid = codes + (size_t)b.rpw * b.words;
-    unsigned long long *qkey = (unsigned long long *)(valid + (size_t)b.rpw * b.words);   // survivor queue: keys
+    if (PACKED) {   // [2 mbarriers | code stage 0 | code stage 1 | queue | -]
+        codes = (uint64_t *)(wbase + 16);
+        valid = (uint64_t *)(wbase + 16 + (size_t)b.stage_bytes);
+    }
+    unsigned long long *qkey = PACKED ? (unsigned long long *)(wbase + 16 + 2 * (size_t)b.stage_bytes)
+                                      : (unsigned long long *)(valid + (size_t)b.rpw * b.words);   // survivor queue: keys
     uint32_t *qmeta = (uint32_t *)(qkey + QCAP);                                           //   home bucket | palindrome << 31
     uint32_t *dirty = qmeta + QCAP;
     const uint64_t mask = kmer_mask(b.k);
-    const uint32_t tile_bytes = (uint32_t)b.rpw * (uint32_t)b.read_len;
+    const uint32_t tile_bytes = PACKED ? (uint32_t)b.rpw * (uint32_t)b.words * 8u : (uint32_t)b.rpw * (uint32_t)b.read_len;
     uint32_t qn = 0, qhead = 0;   // warp-uniform: entries pushed / consumed so far
     // HINTS bit 5: the probe is split in two -- the bucket keys of 32 survivors are requested (probe_issue) and only
     // compared when the next 32 are ready (probe_complete), so the HBM round trip is covered by the warp's own filter work
@@ -328,26 +344,43 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
 
     if (lane == 0) {
         mbar_init(bar, 1);
+        if (PACKED) mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     __syncwarp();
     const int64_t total_warps = (int64_t)gridDim.x * COUNT_WARPS;
     int64_t wt = (int64_t)blockIdx.x * COUNT_WARPS + warp;
     auto uses_bulk = [&](int64_t tile) { return b.bulk_ok && (tile + 1) * (int64_t)b.rpw <= b.n_reads; };
-    auto issue = [&](int64_t tile) {
+    auto issue = [&](int64_t tile, int stage) {   // stage: PACKED only (code stage and its mbarrier)
+        void *dst = PACKED ? (void *)(stage ? valid : codes) : (void *)ascii;
+        uint64_t *mb = PACKED ? bar + stage : bar;
         fence_proxy_async();
-        mbar_expect_tx(bar, tile_bytes);
-        if (HINTS & 4) bulk_g2s_hint(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar, pol_stream);
-        else bulk_g2s(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar);
+        mbar_expect_tx(mb, tile_bytes);
+        if (HINTS & 4) bulk_g2s_hint(dst, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, mb, pol_stream);
+        else bulk_g2s(dst, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, mb);
     };
-    if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt);
-    uint32_t phase = 0;
+    if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt, 0);
+    uint32_t phase = 0;   // PACKED: bit s is the parity of stage s
 
-    for (; wt < b.n_wtiles; wt += total_warps) {
+    for (int it = 0; wt < b.n_wtiles; wt += total_warps, ++it) {
         const int64_t next = wt + total_warps;
         const int64_t r0 = wt * (int64_t)b.rpw;
         const int n_here = (int)min((int64_t)b.rpw, b.n_reads - r0);
-        if (uses_bulk(wt)) {
+        const uint64_t *tile_codes = codes;
+        if (PACKED) {
+            const int st = it & 1;
+            tile_codes = st ? valid : codes;
+            __syncwarp();
+            if (next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next, st ^ 1);   // the other stage was walked last round
+            if (uses_bulk(wt)) {
+                mbar_wait(bar + st, (phase >> st) & 1u);
+                phase ^= 1u << st;
+            } else {   // unaligned batch or tail tile: the warp copies its words itself
+                const unsigned long long *src = (const unsigned long long *)(b.reads + r0 * b.row_stride);
+                for (int i = lane; i < n_here * b.words; i += 32) ((uint64_t *)tile_codes)[i] = __ldg(src + i);
+                __syncwarp();
+            }
+        } else if (uses_bulk(wt)) {
             mbar_wait(bar, phase);
             phase ^= 1;
         } else {   // strided / unaligned / tail tile: the warp copies its rows itself
@@ -358,9 +391,9 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             __syncwarp();
         }
         // ---- pack to 2 bits per base (+ validity), flag reads that contain a non-ACGT byte ----
-        if (lane < n_here) dirty[lane] = 0;
+        if (!PACKED && lane < n_here) dirty[lane] = 0;
         __syncwarp();
-        for (int task = lane; task < n_here * b.words; task += 32) {
+        for (int task = lane; !PACKED && task < n_here * b.words; task += 32) {
             int r = task / b.words, w = task - r * b.words;
             int first = w * 32;
             int nb = min(32, b.read_len - first);
@@ -391,12 +424,12 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             valid[(size_t)r * b.words + w] = vw;
         }
         __syncwarp();
-        if (next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next);   // prefetch: overlaps the walk below
+        if (!PACKED && next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next, 0);   // prefetch: overlaps the walk below
         // ---- walk the reads ----
         for (int r = 0; r < n_here; r++) {
-            const uint64_t *cw = codes + (size_t)r * b.words;
+            const uint64_t *cw = tile_codes + (size_t)r * b.words;
             const uint64_t *vw = valid + (size_t)r * b.words;
-            if (PAIRED && !dirty[r]) {
+            if (PAIRED && (PACKED || !dirty[r])) {
                 // clean read: lane owns WPL consecutive windows, rolled from one extraction; the reverse-complement
                 // hash is rolled alongside (kmer_hashing.py:24-28 == bit reversal of the complemented window)
                 for (int base = 0; base < b.nk; base += 32 * WPL) {
@@ -462,7 +495,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                 for (int i = lane; i < b.nk; i += 32) {
                     uint64_t x = extract_window(cw, i, mask);
                     count_one(t, x);
-                    if (BOTH) count_one(t, revcomp_hash_masked(x, extract_window(vw, i, mask), b.k));
+                    if (BOTH) count_one(t, PACKED ? revcomp_hash(x, b.k) : revcomp_hash_masked(x, extract_window(vw, i, mask), b.k));
                 }
             }
         }
@@ -529,7 +562,10 @@ __global__ void query_counts_kernel(TableView t, const uint64_t *__restrict__ qu
 }
 
 // ------------------------------------------------------------------ host side
+static void destroy_pipeline(gki_index *ix);
+
 void destroy_count_table(gki_index *ix) {
+    destroy_pipeline(ix);
     cudaFree(ix->table.buckets);
     cudaFree((void *)ix->table.filter);
     cudaFree(ix->cs_slot);
@@ -647,18 +683,22 @@ static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cud
     return GKI_OK;
 }
 
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0> static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
+static std::mutex g_launch_mutex;   // the packing lanes launch from their own host threads
+
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false>
+static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
+    std::lock_guard<std::mutex> lock(g_launch_mutex);
     const size_t smem = (size_t)b.warp_bytes * COUNT_WARPS;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BOTH, PAIRED, MINB, HINTS><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
+    count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
@@ -709,6 +749,251 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     if (minb == 6) return launch_count_reads_t<true, true, 6>(ix, b, s);
     if (minb == 3) return launch_count_reads_t<true, true, 3>(ix, b, s);
     return launch_count_reads_t<true, true, 4>(ix, b, s);
+}
+
+// packed reads (gki_pack_reads layout): device rows of ceil(read_len / 32) 64-bit words
+static int launch_count_packed_reads(gki_index *ix, const uint64_t *dpacked, int64_t n_reads, int32_t read_len, int32_t k, int32_t both,
+                                     cudaStream_t s) {
+    WarpBatch b;
+    b.reads = (const uint8_t *)dpacked;
+    b.n_reads = n_reads;
+    b.read_len = read_len;
+    b.k = k;
+    b.nk = read_len - k + 1;
+    b.words = (read_len + 31) / 32;
+    b.row_stride = (int64_t)b.words * 8;
+    auto warp_bytes = [&](int rpw) {
+        size_t stage = (size_t)rpw * b.words * 8 + 16;
+        return (16 + 2 * stage + (size_t)QCAP * 12 + 15) & ~(size_t)15;
+    };
+    int rpw = 8;
+    while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
+    GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_packed_reads: read_len %d too long for the tile path", read_len);
+    b.rpw = rpw;
+    b.stage_bytes = (uint32_t)((size_t)rpw * b.words * 8 + 16);
+    b.warp_bytes = (uint32_t)warp_bytes(rpw);
+    b.n_wtiles = (n_reads + rpw - 1) / rpw;
+    b.bulk_ok = (((uintptr_t)dpacked & 15) == 0) && (((int64_t)rpw * b.words * 8) % 16 == 0);
+    if (!both) return launch_count_reads_t<false, false, 4, 0, true>(ix, b, s);
+    if (ix->table.k != k) return launch_count_reads_t<true, false, 4, 0, true>(ix, b, s);
+    return launch_count_reads_t<true, true, 4, 0, true>(ix, b, s);
+}
+
+// ---- host reads through CPU packing lanes + the copy engine ----
+// PCIe carries ASCII reads at ~52 GB/s, a quarter of what the count kernel consumes.  Host threads ("lanes") therefore
+// pack chunks to 2 bits per base (ingest.cpp) into pinned buffers -- 3.75x fewer bytes on the bus -- while the calling thread
+// keeps the copy engine busy with plain ASCII chunks; both take chunks from one atomic counter, so the split follows
+// whatever the host cores and the bus deliver.  Reads with a non-ACGT byte travel as ASCII next to their chunk; a chunk
+// with more than 1/16 such reads is left to the ASCII path.
+struct PackLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    uint64_t *h_packed[2] = {nullptr, nullptr}, *d_packed[2] = {nullptr, nullptr};
+    uint8_t *h_dirty[2] = {nullptr, nullptr}, *d_dirty[2] = {nullptr, nullptr};
+    bool used[2] = {false, false};
+    int tog = 0;
+};
+
+// one batch handed to the lanes
+struct PackJob {
+    const uint8_t *reads = nullptr;
+    int64_t n_reads = 0, row_stride = 0, n_units = 0;
+    int32_t read_len = 0, k = 0, both = 0;
+};
+
+constexpr int64_t UNIT_READS = 32768;      // a lane packs one unit at a time (about 1 ms of CPU work at 150 bp)
+constexpr int64_t ASCII_UNITS = 4;         // the copy engine moves four units per transfer
+
+struct Pipeline {
+    gki_index *ix = nullptr;
+    int n_lanes = 0;
+    int32_t read_len = 0;
+    int64_t dirty_cap = 0;
+    std::vector<PackLane> lanes;
+    std::vector<std::thread> threads;
+    cudaEvent_t start = nullptr;
+    // job hand-off: workers sleep on cv until generation changes; the caller sleeps on cv_done until all have finished
+    std::mutex mu;
+    std::condition_variable cv, cv_done;
+    uint64_t generation = 0;
+    int running = 0;
+    bool quit = false;
+    PackJob job;
+    std::atomic<int64_t> next{0};
+    std::atomic<int> failed{0};
+    std::vector<int64_t> deferred;   // units left to the ASCII path (too many dirty reads); guarded by mu
+    std::string error;               // guarded by mu
+
+    int lane_body(int li);
+    void worker(int li);
+};
+
+int Pipeline::lane_body(int li) {
+    PackLane &L = lanes[(size_t)li];
+    const PackJob j = job;
+    const size_t words = (size_t)(j.read_len + 31) / 32;
+    while (!failed.load(std::memory_order_relaxed)) {
+        const int64_t u = next.fetch_add(1);
+        if (u >= j.n_units) break;
+        const int64_t r0 = u * UNIT_READS, r1 = r0 + UNIT_READS < j.n_reads ? r0 + UNIT_READS : j.n_reads;
+        const int t = L.tog;
+        if (L.used[t]) GKI_CUDA(cudaEventSynchronize(L.done[t]));
+        int64_t n_dirty = 0;
+        const int64_t clean = pack_rows(j.reads, j.row_stride, j.read_len, r0, r1, L.h_packed[t], L.h_dirty[t], nullptr, dirty_cap, &n_dirty, 0);
+        if (n_dirty > dirty_cap) {
+            std::lock_guard<std::mutex> lock(mu);
+            deferred.push_back(u);
+            continue;
+        }
+        if (clean) {
+            GKI_CUDA(cudaMemcpyAsync(L.d_packed[t], L.h_packed[t], (size_t)clean * words * 8, cudaMemcpyHostToDevice, L.stream));
+            GKI_TRY(launch_count_packed_reads(ix, L.d_packed[t], clean, j.read_len, j.k, j.both, L.stream));
+        }
+        if (n_dirty) {
+            GKI_CUDA(cudaMemcpyAsync(L.d_dirty[t], L.h_dirty[t], (size_t)n_dirty * j.read_len, cudaMemcpyHostToDevice, L.stream));
+            GKI_TRY(launch_count_reads(ix, L.d_dirty[t], n_dirty, j.read_len, j.read_len, j.k, j.both, L.stream));
+        }
+        GKI_CUDA(cudaEventRecord(L.done[t], L.stream));
+        L.used[t] = true;
+        L.tog ^= 1;
+    }
+    return GKI_OK;
+}
+
+void Pipeline::worker(int li) {
+    cudaSetDevice(ix->device);
+    uint64_t seen = 0;
+    for (;;) {
+        {
+            std::unique_lock<std::mutex> lock(mu);
+            cv.wait(lock, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+        }
+        const int rc = lane_body(li);
+        std::lock_guard<std::mutex> lock(mu);
+        if (rc != GKI_OK) {
+            if (error.empty()) error = gki_last_error();
+            failed.store(1);
+        }
+        if (--running == 0) cv_done.notify_all();
+    }
+}
+
+static void destroy_pipeline(gki_index *ix) {
+    Pipeline *p = (Pipeline *)ix->pipeline;
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->quit = true;
+    }
+    p->cv.notify_all();
+    for (auto &t : p->threads) t.join();
+    for (PackLane &L : p->lanes) {
+        for (int j = 0; j < 2; j++) {
+            cudaFreeHost(L.h_packed[j]);
+            cudaFreeHost(L.h_dirty[j]);
+            cudaFree(L.d_packed[j]);
+            cudaFree(L.d_dirty[j]);
+            if (L.done[j]) cudaEventDestroy(L.done[j]);
+        }
+        if (L.stream) cudaStreamDestroy(L.stream);
+    }
+    if (p->start) cudaEventDestroy(p->start);
+    delete p;
+    ix->pipeline = nullptr;
+}
+
+static int ensure_pipeline(gki_index *ix, int n_lanes, int32_t read_len) {
+    Pipeline *p = (Pipeline *)ix->pipeline;
+    if (p && p->n_lanes == n_lanes && p->read_len == read_len) return GKI_OK;
+    destroy_pipeline(ix);
+    p = new Pipeline();
+    ix->pipeline = p;
+    p->ix = ix;
+    p->n_lanes = n_lanes;
+    p->read_len = read_len;
+    p->dirty_cap = UNIT_READS / 16 + 1;
+    p->lanes.resize((size_t)n_lanes);
+    const size_t words = (size_t)(read_len + 31) / 32;
+    GKI_CUDA(cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming));
+    for (PackLane &L : p->lanes) {
+        GKI_CUDA(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+        for (int j = 0; j < 2; j++) {
+            GKI_CUDA(cudaEventCreateWithFlags(&L.done[j], cudaEventDisableTiming));
+            GKI_CUDA(cudaHostAlloc((void **)&L.h_packed[j], (size_t)UNIT_READS * words * 8 + 16, cudaHostAllocDefault));
+            GKI_CUDA(cudaHostAlloc((void **)&L.h_dirty[j], (size_t)p->dirty_cap * read_len + 16, cudaHostAllocDefault));
+            GKI_CUDA(cudaMalloc((void **)&L.d_packed[j], (size_t)UNIT_READS * words * 8 + 16));
+            GKI_CUDA(cudaMalloc((void **)&L.d_dirty[j], (size_t)p->dirty_cap * read_len + 16));
+        }
+    }
+    for (int i = 0; i < n_lanes; i++) p->threads.emplace_back(&Pipeline::worker, p, i);
+    return GKI_OK;
+}
+
+static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, int32_t k,
+                                     int32_t both, cudaStream_t s, int n_lanes) {
+    GKI_TRY(ensure_pipeline(ix, n_lanes, read_len));
+    Pipeline *p = (Pipeline *)ix->pipeline;
+    GKI_TRY(ensure_staging(ix, (size_t)ASCII_UNITS * UNIT_READS * read_len + 16));
+    GKI_CUDA(cudaEventRecord(p->start, s));            // lane kernels follow whatever the caller queued on s
+    for (PackLane &L : p->lanes) GKI_CUDA(cudaStreamWaitEvent(L.stream, p->start, 0));
+    {
+        std::lock_guard<std::mutex> lock(p->mu);
+        p->job.reads = reads;
+        p->job.n_reads = n_reads;
+        p->job.row_stride = row_stride;
+        p->job.n_units = (n_reads + UNIT_READS - 1) / UNIT_READS;
+        p->job.read_len = read_len;
+        p->job.k = k;
+        p->job.both = both;
+        p->next.store(0);
+        p->failed.store(0);
+        p->deferred.clear();
+        p->error.clear();
+        p->running = n_lanes;
+        p->generation++;
+    }
+    p->cv.notify_all();
+    // the calling thread feeds the copy engine with ASCII transfers (double-buffered staging, kernels on s)
+    int slot = 0;
+    bool staged[2] = {false, false};
+    auto ascii_units = [&](int64_t u0, int64_t n_units) -> int {
+        const int64_t r0 = u0 * UNIT_READS;
+        const int64_t r1 = r0 + n_units * UNIT_READS < n_reads ? r0 + n_units * UNIT_READS : n_reads, cnt = r1 - r0;
+        if (cnt <= 0) return GKI_OK;
+        if (staged[slot]) GKI_CUDA(cudaEventSynchronize(ix->done[slot]));   // paces this lane at bus speed
+        if (row_stride == read_len)
+            GKI_CUDA(cudaMemcpyAsync(ix->stage[slot], reads + r0 * row_stride, (size_t)cnt * read_len, cudaMemcpyHostToDevice, ix->copy_stream));
+        else
+            GKI_CUDA(cudaMemcpy2DAsync(ix->stage[slot], read_len, reads + r0 * row_stride, row_stride, read_len, cnt, cudaMemcpyHostToDevice, ix->copy_stream));
+        GKI_CUDA(cudaEventRecord(ix->ready[slot], ix->copy_stream));
+        GKI_CUDA(cudaStreamWaitEvent(s, ix->ready[slot], 0));
+        GKI_TRY(launch_count_reads(ix, (const uint8_t *)ix->stage[slot], cnt, read_len, read_len, k, both, s));
+        GKI_CUDA(cudaEventRecord(ix->done[slot], s));
+        staged[slot] = true;
+        slot ^= 1;
+        return GKI_OK;
+    };
+    int rc = GKI_OK;
+    while (rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
+        const int64_t u = p->next.fetch_add(ASCII_UNITS);
+        if (u >= p->job.n_units) break;
+        rc = ascii_units(u, u + ASCII_UNITS <= p->job.n_units ? ASCII_UNITS : p->job.n_units - u);
+    }
+    if (rc != GKI_OK) p->failed.store(1);
+    {
+        std::unique_lock<std::mutex> lock(p->mu);
+        p->cv_done.wait(lock, [&] { return p->running == 0; });
+    }
+    for (size_t i = 0; rc == GKI_OK && !p->failed.load() && i < p->deferred.size(); i++) rc = ascii_units(p->deferred[i], 1);
+    for (PackLane &L : p->lanes) cudaStreamSynchronize(L.stream);
+    cudaStreamSynchronize(s);
+    if (rc == GKI_OK && p->failed.load()) {
+        set_error("%s", p->error.empty() ? "gki_count_reads: a packing lane failed" : p->error.c_str());
+        rc = GKI_ERR_CUDA;
+    }
+    return rc;
 }
 
 }  // namespace gki
@@ -764,8 +1049,13 @@ int gki_count_reads(gki_index_t *ix, const uint8_t *reads, int64_t n_reads, int3
     GKI_REQUIRE(reads, GKI_ERR_INVALID, "gki_count_reads: reads is NULL");
     GKI_TRY(ensure_table(ix, k, s));
     if (is_device_ptr(reads)) return launch_count_reads(ix, reads, n_reads, read_len, row_stride, k, both_strands, s);
-    // host reads: rows are compacted to dense device rows (so every full tile is one TMA bulk copy) in chunks;
-    // the copy of chunk c+1 overlaps the count kernel of chunk c
+    // host reads, large batch: CPU packing lanes + the copy engine share the chunks (count_reads_host_pipeline)
+    {
+        const int n_lanes = default_pack_threads();
+        if (n_lanes > 0 && n_reads >= 16 * UNIT_READS) return count_reads_host_pipeline(ix, reads, n_reads, read_len, row_stride, k, both_strands, s, n_lanes);
+    }
+    // host reads, small batch: rows are compacted to dense device rows (so every full tile is one TMA bulk copy) in
+    // chunks; the copy of chunk c+1 overlaps the count kernel of chunk c
     int64_t chunk_reads = ((32ll << 20) / (read_len > 0 ? read_len : 1)) & ~31ll;
     if (chunk_reads < 32) chunk_reads = 32;
     GKI_TRY(ensure_staging(ix, (size_t)chunk_reads * read_len + 16));
@@ -785,6 +1075,58 @@ int gki_count_reads(gki_index_t *ix, const uint8_t *reads, int64_t n_reads, int3
     }
     GKI_CUDA(cudaStreamSynchronize(s));
     return GKI_OK;
+}
+
+int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, uint64_t *packed, int64_t *dirty_index,
+                   int64_t dirty_cap, int64_t *n_clean, int64_t *n_dirty, int32_t n_threads, int32_t flags) {
+    GKI_REQUIRE(n_reads >= 0 && read_len >= 1 && row_stride >= read_len && n_clean && n_dirty && dirty_cap >= 0 && (n_reads == 0 || (reads && packed)),
+                GKI_ERR_INVALID, "gki_pack_reads: bad arguments");
+    GKI_REQUIRE(n_reads == 0 || (!is_device_ptr(reads) && !is_device_ptr(packed)), GKI_ERR_INVALID, "gki_pack_reads: host buffers only");
+    const int64_t words = (read_len + 31) / 32;
+    int T = n_threads > 0 ? n_threads : default_pack_threads() + 1;
+    if (T > 64) T = 64;
+    if ((int64_t)T > n_reads / 4096 + 1) T = (int)(n_reads / 4096 + 1);
+    std::vector<int64_t> clean((size_t)T, 0);
+    std::vector<std::vector<int64_t>> dirty((size_t)T);
+    auto body = [&](int t) {
+        const int64_t r0 = n_reads * t / T, r1 = n_reads * (t + 1) / T;
+        dirty[(size_t)t].resize((size_t)(r1 - r0 < dirty_cap ? r1 - r0 : dirty_cap));
+        int64_t nd = 0;
+        clean[(size_t)t] = pack_rows(reads, row_stride, read_len, r0, r1, packed + r0 * words, nullptr, dirty[(size_t)t].data(),
+                                     (int64_t)dirty[(size_t)t].size(), &nd, flags & GKI_PACK_FORCE_SCALAR);
+        if ((size_t)nd < dirty[(size_t)t].size()) dirty[(size_t)t].resize((size_t)nd);
+        dirty[(size_t)t].push_back(nd);   // last element: the slice's dirty count
+    };
+    std::vector<std::thread> threads;
+    for (int t = 1; t < T; t++) threads.emplace_back(body, t);
+    body(0);
+    for (auto &th : threads) th.join();
+    int64_t acc = 0, nd_total = 0, listed = 0;
+    for (int t = 0; t < T; t++) {   // close the gaps the dirty rows left between the slices
+        const int64_t r0 = n_reads * t / T;
+        if (acc != r0 && clean[(size_t)t]) memmove(packed + acc * words, packed + r0 * words, (size_t)clean[(size_t)t] * words * 8);
+        acc += clean[(size_t)t];
+        nd_total += dirty[(size_t)t].back();
+        for (size_t i = 0; i + 1 < dirty[(size_t)t].size() && listed < dirty_cap; i++)
+            if (dirty_index) dirty_index[listed++] = dirty[(size_t)t][i];
+    }
+    *n_clean = acc;
+    *n_dirty = nd_total;
+    return GKI_OK;
+}
+
+int gki_count_packed_reads(gki_index_t *ix, const uint64_t *packed, int64_t n_reads, int32_t read_len, int32_t k, int32_t both_strands,
+                           gki_stream_t stream) {
+    CallScope call(stream);
+    GKI_REQUIRE(ix && n_reads >= 0 && read_len >= 0, GKI_ERR_INVALID, "gki_count_packed_reads: bad arguments");
+    GKI_REQUIRE(k >= 1 && k <= 31, GKI_ERR_INVALID, "gki_count_packed_reads: k must be in [1, 31], got %d", k);
+    if (n_reads == 0 || read_len < k) return GKI_OK;
+    GKI_REQUIRE(packed, GKI_ERR_INVALID, "gki_count_packed_reads: packed is NULL");
+    GKI_TRY(ensure_table(ix, k, call.stream));
+    DevIn d;
+    GKI_TRY(d.stage(packed, (size_t)n_reads * ((read_len + 31) / 32) * 8, call.stream));
+    GKI_TRY(launch_count_packed_reads(ix, d.as<uint64_t>(), n_reads, read_len, k, both_strands, call.stream));
+    return call.finish();
 }
 
 int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, gki_stream_t stream) {

@@ -65,10 +65,12 @@ struct gki_index {
     cudaEvent_t ready[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
     void *stage[2] = {nullptr, nullptr};
     size_t stage_bytes = 0;
+    // host-input pipeline with CPU packing lanes (count.cu, gki_count_reads): persistent worker threads, per lane a stream and buffers
+    void *pipeline = nullptr;
 
     gki::IndexView view() const { return gki::IndexView{cells, kmers, fm}; }
 };
 
 namespace gki {
-void destroy_count_table(gki_index *ix);   // count.cu
+void destroy_count_table(gki_index *ix);   // count.cu (also frees the packing lanes)
 }

@@ -1,0 +1,118 @@
+// ingest.cpp -- CPU 2-bit packing of read rows (see ingest.h).  The wide path handles 64 bases per step with AVX-512BW
+// (two multiply-adds fold four 2-bit codes into a byte, vpmovdb gathers the 16 bytes); the scalar path is a 256-entry
+// table.  Which one runs is decided once from cpuid; both produce identical words.
+#include "ingest.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define GKI_X86 1
+#endif
+
+namespace gki {
+
+namespace {
+
+struct Lut {
+    uint8_t v[256];   // bits 0-1 code, bit 2 valid
+    Lut() {
+        for (int i = 0; i < 256; i++) v[i] = 0;
+        const char *letters = "acgt";
+        for (int c = 0; c < 4; c++) {
+            v[(uint8_t)letters[c]] = (uint8_t)(c | 4);
+            v[(uint8_t)(letters[c] - 32)] = (uint8_t)(c | 4);
+        }
+    }
+};
+const Lut lut;
+
+bool pack_row_scalar(const uint8_t *row, int32_t read_len, int words, uint64_t *out) {
+    unsigned ok = 4;
+    for (int w = 0; w < words; w++) {
+        const int first = w * 32, nb = read_len - first < 32 ? read_len - first : 32;
+        uint64_t cw = 0;
+        for (int i = 0; i < nb; i++) {
+            const unsigned e = lut.v[row[first + i]];
+            ok &= e;
+            cw |= (uint64_t)(e & 3u) << (2 * i);
+        }
+        out[w] = cw;
+    }
+    return ok != 0;
+}
+
+#if GKI_X86
+__attribute__((target("avx512f,avx512bw"))) bool pack_row_avx512(const uint8_t *row, int32_t read_len, int words, uint64_t *out) {
+    const __m512i lower = _mm512_set1_epi8(0x20), three = _mm512_set1_epi8(3);
+    const __m512i letters = _mm512_broadcast_i32x4(_mm_setr_epi8('a', 'c', 'g', 't', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i w8 = _mm512_set1_epi16(0x0401);        // bytes (1, 4): code pairs -> 4 bits per 16-bit lane
+    const __m512i w16 = _mm512_set1_epi32(0x00100001);   // words (1, 16): -> 8 bits (4 bases) per 32-bit lane
+    __mmask64 bad = 0;
+    for (int c = 0; c < read_len; c += 64) {
+        const int n = read_len - c < 64 ? read_len - c : 64;
+        const __mmask64 in = n == 64 ? ~0ull : ((1ull << n) - 1ull);
+        const __m512i lc = _mm512_or_si512(n == 64 ? _mm512_loadu_si512(row + c) : _mm512_maskz_loadu_epi8(in, row + c), lower);
+        // (bit1 ^ bit2, bit2 ^ bit3) of the lower-case letter is a0 c1 g2 t3; the 16-bit shifts only leak into bits that are masked off
+        const __m512i code = _mm512_and_si512(_mm512_xor_si512(_mm512_srli_epi16(lc, 1), _mm512_srli_epi16(lc, 2)), three);
+        bad |= _mm512_cmpneq_epi8_mask(lc, _mm512_shuffle_epi8(letters, code)) & in;
+        const __m512i clean = _mm512_maskz_mov_epi8(in, code);                       // bytes past the read pack to zero
+        const __m128i bits = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(clean, w8), w16));   // 64 bases -> 128 bits
+        const int w = c >> 5;
+        if (w + 1 < words) _mm_storeu_si128((__m128i *)(out + w), bits);
+        else _mm_storel_epi64((__m128i *)(out + w), bits);
+    }
+    return bad == 0;
+}
+
+bool have_avx512() {
+    static const bool have = !getenv("GKI_PACK_SCALAR") && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+    return have;
+}
+#else
+bool have_avx512() { return false; }
+#endif
+
+}  // namespace
+
+const char *pack_rows_isa() { return have_avx512() ? "avx512" : "scalar"; }
+
+int64_t pack_rows(const uint8_t *reads, int64_t row_stride, int32_t read_len, int64_t r0, int64_t r1, uint64_t *packed,
+                  uint8_t *dirty_rows, int64_t *dirty_index, int64_t dirty_cap, int64_t *n_dirty, int force_scalar) {
+    const int words = (read_len + 31) / 32;
+    const bool wide = have_avx512() && !force_scalar;
+    int64_t clean = 0, dirty = 0;
+    for (int64_t r = r0; r < r1; r++) {
+        const uint8_t *row = reads + r * row_stride;
+        uint64_t *out = packed + clean * words;
+        bool ok;
+#if GKI_X86
+        ok = wide ? pack_row_avx512(row, read_len, words, out) : pack_row_scalar(row, read_len, words, out);
+#else
+        ok = pack_row_scalar(row, read_len, words, out);
+#endif
+        if (ok) {
+            clean++;
+        } else {
+            if (dirty_rows && dirty < dirty_cap) memcpy(dirty_rows + dirty * read_len, row, (size_t)read_len);
+            if (dirty_index && dirty < dirty_cap) dirty_index[dirty] = r;
+            dirty++;
+        }
+    }
+    if (n_dirty) *n_dirty = dirty;
+    return clean;
+}
+
+int default_pack_threads() {
+    if (const char *e = getenv("GKI_PACK_THREADS")) {
+        int v = atoi(e);
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }
+    int hw = (int)std::thread::hardware_concurrency();
+    int v = hw - 2;
+    return v < 0 ? 0 : (v > 30 ? 30 : v);
+}
+
+}  // namespace gki

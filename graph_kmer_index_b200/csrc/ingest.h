@@ -1,0 +1,22 @@
+// ingest.h -- host side of read ingestion: 2-bit packing of ASCII read rows on the CPU.
+// Plain C++ (compiled by the host compiler, no CUDA), shared by count.cu's host-input pipeline and gki_pack_reads.
+#pragma once
+#include <cstdint>
+
+namespace gki {
+
+// Pack rows [r0, r1) of an ASCII read matrix.  A clean row (every byte one of ACGTacgt) becomes `words` = ceil(read_len/32)
+// 64-bit words -- base i at bits 2*(i%32) of word i/32, a0 c1 g2 t3 (flat_kmers.py:134-145), unused high bits zero --
+// appended to `packed`; a row with any other byte is appended to `dirty_rows` (read_len ASCII bytes, dense) when that is
+// non-NULL and its index to `dirty_index` when that is non-NULL -- the first dirty_cap of them; the rest are only counted.
+// Returns the number of clean rows; *n_dirty the others.  force_scalar != 0 selects the table-driven path (tests).
+int64_t pack_rows(const uint8_t *reads, int64_t row_stride, int32_t read_len, int64_t r0, int64_t r1, uint64_t *packed,
+                  uint8_t *dirty_rows, int64_t *dirty_index, int64_t dirty_cap, int64_t *n_dirty, int force_scalar);
+
+// "avx512" or "scalar": which implementation pack_rows dispatches to on this CPU
+const char *pack_rows_isa();
+
+// number of packing threads the host-input pipeline uses (GKI_PACK_THREADS, default hardware threads - 2, at most 30)
+int default_pack_threads();
+
+}  // namespace gki

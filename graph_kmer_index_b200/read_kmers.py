@@ -51,6 +51,23 @@ def hash_ragged_reads(reads, k, reverse=True):
     return fwd, rc, out_offsets
 
 
+def pack_reads(reads, n_threads=0, force_scalar=False):
+    """(n_reads, L) uint8 ASCII host array -> (packed, dirty_index): the rows made only of ACGTacgt as 2-bit codes,
+    ceil(L/32) uint64 words each (base i at bits 2*(i%32) of word i/32, a0 c1 g2 t3), in input order, and the indices of
+    the other rows.  Runs on the host cores (csrc/ingest.cpp: AVX-512 + BMI2 when the CPU has them); the packed rows feed
+    ``DeviceIndex.count_packed_reads`` at a quarter of the PCIe bytes of the ASCII form."""
+    import ctypes
+    reads = np.asarray(reads)
+    assert reads.dtype == np.uint8 and reads.ndim == 2 and (reads.shape[0] < 2 or reads.strides[1] == 1)
+    n, L = reads.shape
+    packed = np.empty((n, (L + 31) // 32), dtype=np.uint64)
+    dirty = np.empty(n, dtype=np.int64)
+    n_clean, n_dirty = ctypes.c_int64(), ctypes.c_int64()
+    _lib.call("gki_pack_reads", reads.ctypes.data, n, L, reads.strides[0] if n > 1 else L, _lib.ptr(packed), _lib.ptr(dirty), n,
+              ctypes.byref(n_clean), ctypes.byref(n_dirty), int(n_threads), 1 if force_scalar else 0)
+    return packed[:n_clean.value], dirty[:n_dirty.value]
+
+
 def _k_from_power_vector(power_vector):
     k = len(power_vector)
     if not np.array_equal(np.asarray(power_vector, dtype=np.uint64), power_array(k)):

@@ -164,6 +164,21 @@ int gki_count_reads(gki_index_t *index, const uint8_t *reads, int64_t n_reads, i
 
 #define GKI_COUNTS_WRAP_UINT16 1 /* weight = counter mod 2^16 (the reference's uint16 Counter, cfki:27) */
 
+/* Read ingestion ahead of K1 (the reference's own form is the per-line Python loop of read_kmers.py:14-49).
+ * gki_pack_reads (host only, no device needed): 2-bit packing of an ASCII read matrix on the CPU with n_threads threads
+ * (<= 0: all but one hardware thread).  Clean rows -- every byte one of ACGTacgt -- are appended to `packed` in input order,
+ * ceil(read_len/32) 64-bit words each, base i at bits 2*(i%32) of word i/32, a0 c1 g2 t3 (flat_kmers.py:134-145), unused
+ * bits zero; rows holding any other byte are skipped and their indices written to dirty_index (first dirty_cap of them, in
+ * order; may be NULL).  packed must hold n_reads rows.  flags: GKI_PACK_FORCE_SCALAR selects the table-driven path.
+ * gki_count_packed_reads: gki_count_reads for such clean packed rows (host or device pointer).
+ * gki_count_reads on a large host batch uses the same packing internally: GKI_PACK_THREADS lanes (default hardware
+ * threads - 2; 0 disables) pack chunks into pinned buffers while the copy engine moves other chunks as ASCII. */
+#define GKI_PACK_FORCE_SCALAR 1
+int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, uint64_t *packed,
+                   int64_t *dirty_index, int64_t dirty_cap, int64_t *n_clean, int64_t *n_dirty, int32_t n_threads, int32_t flags);
+int gki_count_packed_reads(gki_index_t *index, const uint64_t *packed, int64_t n_reads, int32_t read_len, int32_t k,
+                           int32_t both_strands, gki_stream_t stream);
+
 /* cfki:39-40 CounterKmerIndex.get_node_counts: out[node] = sum over entries e with nodes[e]==node of
  * counter[kmers[e]], as float64.  n_out must be >= max(min_nodes, max_node+1); out is overwritten. */
 int gki_node_counts(gki_index_t *index, double *out, int64_t n_out, int32_t flags, gki_stream_t stream);

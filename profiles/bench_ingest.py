@@ -1,0 +1,60 @@
+"""Host-side read ingestion: CPU packing rate, and gki_count_reads on a pinned host batch with
+0..N packing lanes.  Usage: python profiles/bench_ingest.py [entries] [reads]"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from graph_kmer_index_b200 import DeviceIndex, _lib, synthetic  # noqa: E402
+from graph_kmer_index_b200.read_kmers import pack_reads  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 60_000_000
+R = int(sys.argv[2]) if len(sys.argv) > 2 else 10_000_000
+modulo, k, L, n_nodes = 452_930_477, 31, 150, max(n // 10, 1)
+dev = torch.device("cuda")
+glen = synthetic.genome_length(n, k)
+genome = torch.empty(glen, dtype=torch.uint8, device=dev)
+_lib.call("gki_synth_genome", _lib.ptr(genome), glen, None)
+hashes = torch.empty(n, dtype=torch.int64, device=dev)
+nodes = torch.empty(n, dtype=torch.int32, device=dev)
+_lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(hashes), _lib.ptr(nodes), None, None, None)
+h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+nkm = torch.empty(modulo, dtype=torch.int32, device=dev)
+s_k, s_n = torch.empty_like(hashes), torch.empty_like(nodes)
+_lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, 1, _lib.ptr(h2i), _lib.ptr(nkm),
+          _lib.ptr(s_k), _lib.ptr(s_n), None, None, None, None, None)
+reads = torch.empty((R, L), dtype=torch.uint8, device=dev)
+_lib.call("gki_synth_reads", _lib.ptr(genome), glen, 0, R, L, 100, 0, _lib.ptr(reads), None)
+host = reads.cpu().pin_memory()
+host_np = host.numpy()
+torch.cuda.synchronize()
+
+for threads in (1, 4, 8, 14, 16):
+    best = 1e9
+    for _ in range(3):
+        t = time.perf_counter()
+        packed, dirty = pack_reads(host_np, n_threads=threads)
+        best = min(best, time.perf_counter() - t)
+    print(json.dumps(dict(stage="pack_reads", threads=threads, ms=best * 1e3, ascii_gbs=R * L / best / 1e9, dirty=len(dirty))), flush=True)
+
+index = DeviceIndex(h2i, nkm, s_k, s_n, modulo)
+index.prepare_counting(k)
+index.count_reads(reads, k)
+want = index.node_counts(n_nodes).sum()
+for lanes in (0, 1, 2, 4, 8, 12, 14):
+    os.environ["GKI_PACK_THREADS"] = str(lanes)
+    best = 1e9
+    for _ in range(4):
+        index.reset_counts()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        index.count_reads(host, k)
+        torch.cuda.synchronize()
+        best = min(best, time.perf_counter() - t)
+    assert index.node_counts(n_nodes).sum() == want
+    print(json.dumps(dict(stage="count_reads_host", pack_lanes=lanes, ms=best * 1e3, gkmers_per_s=R * 240 / best / 1e9,
+                          ascii_gbs=R * L / best / 1e9)), flush=True)

@@ -1,0 +1,95 @@
+"""GPU parity of the read-ingestion path: 2-bit packed reads through gki_count_packed_reads, and large
+host batches through gki_count_reads' packing lanes + copy engine, against the oracle and the plain device path."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gki():
+    import graph_kmer_index_b200 as g
+    return g
+
+
+def make_index(gki, n, k, modulo, table_k=None):
+    from graph_kmer_index_b200 import synthetic
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 997, k)
+    idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo)
+    dev.prepare_counting(k if table_k is None else table_k)
+    return idx, dev
+
+
+@pytest.mark.parametrize("n,modulo,n_reads,L,k,table_k", [(40000, 200003, 3001, 150, 31, None), (40000, 4099, 1500, 128, 31, None),
+                                                           (5000, 7, 300, 100, 15, None), (40000, 200003, 777, 33, 31, None),
+                                                           (3000, 1009, 400, 90, 16, None), (40000, 200003, 900, 150, 31, 30)])
+def test_count_packed_reads_vs_oracle(gki, n, modulo, n_reads, L, k, table_k):
+    import torch
+    from graph_kmer_index_b200 import synthetic
+    from graph_kmer_index_b200.read_kmers import pack_reads
+    idx, dev = make_index(gki, n, k, modulo, table_k)
+    reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=400, n_permille=10)
+    packed, dirty = pack_reads(reads, n_threads=3)
+    clean = np.ones(n_reads, dtype=bool)
+    clean[dirty] = False
+    assert 0 < len(dirty) < n_reads and len(packed) == clean.sum()
+    want = c_oracle.read_node_counts(idx, reads[clean], k, 1000)
+    assert want.sum() > 0
+    dev.count_packed_reads(packed, L, k)                                    # host rows
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dpacked = torch.from_numpy(packed.view(np.int64)).cuda()
+    dev.count_packed_reads(dpacked, L, k)                                   # device rows
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dev.count_packed_reads(dpacked[1:], L, k)                               # unaligned start: no bulk copies
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[clean][1:], k, 1000))
+    dev.reset_counts()
+    dev.count_packed_reads(dpacked, L, k, both_strands=False)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[clean], k, 1000, both_strands=False))
+    # packed + the dirty rows as ASCII == the whole batch
+    dev.reset_counts()
+    dev.count_packed_reads(dpacked, L, k)
+    dev.count_reads(np.ascontiguousarray(reads[dirty]), k)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads, k, 1000))
+    dev.close()
+
+
+@pytest.mark.parametrize("threads", ["3", "1", "0"])
+def test_host_pipeline_vs_device_path(gki, monkeypatch, threads):
+    """a host batch large enough for the packing lanes: same node counts as the device-resident path and the oracle"""
+    import torch
+    from graph_kmer_index_b200 import synthetic
+    monkeypatch.setenv("GKI_PACK_THREADS", threads)
+    n, k, L, modulo = 200000, 31, 150, 1000003
+    idx, dev = make_index(gki, n, k, modulo)
+    n_reads = 5 * 131072 + 777
+    reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=300, n_permille=2)
+    reads[131072 * 2:131072 * 2 + 30000, 7] = ord("N")          # one chunk with > 1/16 dirty reads: deferred to the ASCII lane
+    reads[-1, -1] = ord("n")
+    dev.count_reads(torch.from_numpy(reads).cuda(), k)
+    want = dev.node_counts(1000)
+    sample = slice(0, 20000)
+    dev.reset_counts()
+    dev.count_reads(reads, k)                                    # host numpy (pageable)
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    pinned = torch.from_numpy(reads).pin_memory()
+    dev.count_reads(pinned, k)                                   # pinned host tensor
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    padded = np.full((n_reads, L + 10), ord("A"), dtype=np.uint8)
+    padded[:, :L] = reads
+    dev.count_reads(padded[:, :L], k, both_strands=False)        # strided rows, forward only
+    fwd = dev.node_counts(1000)
+    dev.reset_counts()
+    dev.count_reads(torch.from_numpy(reads).cuda(), k, both_strands=False)
+    assert np.array_equal(fwd, dev.node_counts(1000))
+    # the oracle on a slice
+    dev.reset_counts()
+    dev.count_reads(reads[sample], k)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[sample], k, 1000))
+    dev.close()

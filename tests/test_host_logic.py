@@ -85,3 +85,36 @@ def test_world_size_2_allreduce_gloo(tmp_path):
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-3000:]
     assert "OK 2" in out.stdout
+
+
+def test_pack_reads_host_matches_numpy():
+    """csrc/ingest.cpp (no device needed): the AVX-512 and the table-driven packers against a numpy restatement of
+    flat_kmers.py:134-145 at 2 bits per base; dirty rows are listed, clean rows keep their order"""
+    from graph_kmer_index_b200.read_kmers import pack_reads
+    rng = np.random.default_rng(0)
+    alphabet = np.frombuffer(b"ACGTacgt", dtype=np.uint8)
+    for L in (150, 64, 31, 200, 1):
+        n = 20000
+        reads = alphabet[rng.integers(0, 8, (n, L))].copy()
+        bad = rng.choice(n, 300, replace=False)
+        reads[bad, rng.integers(0, L, 300)] = np.frombuffer(b"NnX-", dtype=np.uint8)[rng.integers(0, 4, 300)]
+        words = (L + 31) // 32
+        lut = np.zeros(256, dtype=np.uint64)
+        for i, c in enumerate(b"acgt"):
+            lut[c] = lut[c - 32] = i
+        valid = np.isin(reads, alphabet).all(axis=1)
+        codes = lut[reads[valid]]
+        want = np.zeros((int(valid.sum()), words), dtype=np.uint64)
+        for i in range(L):
+            want[:, i // 32] |= codes[:, i] << np.uint64(2 * (i % 32))
+        for force_scalar in (False, True):
+            for threads in (1, 3):
+                packed, dirty = pack_reads(reads, n_threads=threads, force_scalar=force_scalar)
+                assert np.array_equal(packed, want), (L, force_scalar, threads)
+                assert np.array_equal(dirty, np.flatnonzero(~valid))
+        padded = np.full((n, L + 7), ord("N"), dtype=np.uint8)
+        padded[:, :L] = reads
+        packed, dirty = pack_reads(padded[:, :L])
+        assert np.array_equal(packed, want) and np.array_equal(dirty, np.flatnonzero(~valid))
+    packed, dirty = pack_reads(np.zeros((0, 150), dtype=np.uint8))
+    assert packed.shape == (0, 5) and len(dirty) == 0
