@@ -345,7 +345,8 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = {"value": total_kmers_per_step * e2e_steps / (float(t.item()) / 1e3), "unit": "kmers/s",
                "h2d_bytes_per_step": int(R * L), "d2h_bytes_per_step": int(counts.shape[0] * 8), "steps": e2e_steps,
-               "host_memory": "pinned", "pack_lanes": int(os.environ.get("GKI_PACK_THREADS", max((os.cpu_count() or 2) - 2, 0))),
+               "host_memory": "pinned", "pack_lanes": int(os.environ.get("GKI_PACK_THREADS", max((os.cpu_count() or 2) - 2, 0) if world == 1 else
+                                                 max((os.cpu_count() or 2) // int(os.environ.get("LOCAL_WORLD_SIZE", world)) - 1, 0))),
                "note": "per GPU bytes of the caller's ASCII reads (1 byte per base); inside the call pack_lanes host threads re-encode "
                        "chunks to 2 bits per base before the bus while the copy engine moves the other chunks as ASCII (csrc/count.cu)"}
         assert float(host_counts.sum().item()) == (total_counts if world == 1 else float(counts.sum().item()))

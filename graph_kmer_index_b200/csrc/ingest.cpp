@@ -111,7 +111,9 @@ int default_pack_threads() {
         return v < 0 ? 0 : (v > 64 ? 64 : v);
     }
     int hw = (int)std::thread::hardware_concurrency();
-    int v = hw - 2;
+    int ranks = 1;   // one process per GPU under torchrun: the ranks of a node share its cores
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    int v = hw / ranks - (ranks == 1 ? 2 : 1);
     return v < 0 ? 0 : (v > 30 ? 30 : v);
 }
 

@@ -16,7 +16,8 @@ int64_t pack_rows(const uint8_t *reads, int64_t row_stride, int32_t read_len, in
 // "avx512" or "scalar": which implementation pack_rows dispatches to on this CPU
 const char *pack_rows_isa();
 
-// number of packing threads the host-input pipeline uses (GKI_PACK_THREADS, default hardware threads - 2, at most 30)
+// number of packing threads the host-input pipeline uses: GKI_PACK_THREADS, else hardware threads - 2 (at most 30);
+// under torchrun (LOCAL_WORLD_SIZE ranks on the node) each rank takes its share of the cores minus one
 int default_pack_threads();
 
 }  // namespace gki
