@@ -57,11 +57,13 @@ __device__ __forceinline__ uint32_t filter_word(const TableView &t, const Hash &
     g ^= g >> 15;
     return __umulhi(g, t.filter_words);
 }
+// FK: bits per key when known at compile time (the fused kernel is instantiated for 3), 0: read t.filter_k
+template <int FK = 0>
 __device__ __forceinline__ uint32_t filter_mask(const TableView &t, const Hash &h) {
     uint32_t b = h.hi * 0xC2B2AE35u;     // bit positions from the high half, word from the fold: 64 bits of the product are used
     uint32_t mask = 1u << (b >> 27);
-    if (t.filter_k > 1) mask |= 1u << ((b >> 22) & 31);
-    if (t.filter_k > 2) mask |= 1u << ((b >> 17) & 31);
+    if (FK ? FK > 1 : t.filter_k > 1) mask |= 1u << ((b >> 22) & 31);
+    if (FK ? FK > 2 : t.filter_k > 2) mask |= 1u << ((b >> 17) & 31);
     return mask;
 }
 
@@ -264,11 +266,14 @@ struct WarpBatch {
 };
 
 constexpr int WPL = 4;   // consecutive windows per lane
-constexpr int QCAP = 128;  // survivor queue capacity per warp (32 in flight + < 32 waiting + <= 32 pushed per ballot)
+// survivor queue capacity per warp (< 32 waiting + <= 32 pushed per ballot).  Kept as small as the scheme allows: shared memory
+// comes out of the L1 that tracks the outstanding gathers, and a 4x larger queue measurably slowed the launch (9.2 -> 9.5 ms)
+constexpr int QCAP = 64;
 
 // PACKED: the batch is already 2 bits per base (gki_pack_reads layout: read r owns b.words 64-bit words, every byte was
 // one of ACGTacgt) -- the tile lands straight in the code words, double-buffered, and the pack phase disappears.
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false>
+// KODD: k is odd, no k-mer equals its own reverse complement (no palindrome bookkeeping).  FK: filter bits per key (0: runtime).
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
     const unsigned long long pol_last = (HINTS & 1) ? l2_policy_evict_last() : 0ull;
     const unsigned long long pol_first = (HINTS & 2) ? l2_policy_evict_first() : 0ull;
@@ -293,40 +298,6 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
     const uint64_t mask = kmer_mask(b.k);
     const uint32_t tile_bytes = PACKED ? (uint32_t)b.rpw * (uint32_t)b.words * 8u : (uint32_t)b.rpw * (uint32_t)b.read_len;
     uint32_t qn = 0, qhead = 0;   // warp-uniform: entries pushed / consumed so far
-    // HINTS bit 5: the probe is split in two -- the bucket keys of 32 survivors are requested (probe_issue) and only
-    // compared when the next 32 are ready (probe_complete), so the HBM round trip is covered by the warp's own filter work
-    constexpr bool PIPE = (HINTS & 32) != 0;
-    unsigned long long pk[SLOTS_PER_BUCKET] = {0, 0, 0, 0};
-    uint32_t n_flight = 0;        // warp-uniform: entries [qhead, qhead + n_flight) have their bucket load in flight
-    auto probe_issue = [&](uint32_t n) {
-        if ((uint32_t)lane < n) load_bucket_keys(t.buckets + (qmeta[(qhead + lane) & (QCAP - 1)] & 0x7fffffffu), pk);
-        n_flight = n;
-    };
-    auto probe_complete = [&]() {
-        if ((uint32_t)lane < n_flight) {
-            const uint32_t idx = (qhead + lane) & (QCAP - 1);
-            const unsigned long long key = qkey[idx];
-            const uint32_t meta = qmeta[idx], home = meta & 0x7fffffffu;
-            uint32_t *cnt = nullptr;
-            bool full = true;
-#pragma unroll
-            for (int i = 0; i < SLOTS_PER_BUCKET; i++) {
-                if (full && pk[i] == key) {
-                    cnt = t.buckets[home].cnt[i];
-                    full = false;
-                }
-                if (pk[i] == SLOT_EMPTY) full = false;
-            }
-            if (full) cnt = find_slot_from(t, key, next_bucket(t, home, 0), 0ull, 1);   // rare: continue with the line mate
-            if (cnt) {
-                if (meta >> 31) atomicAdd(cnt, 2u);
-                else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);
-            }
-        }
-        qhead += n_flight;
-        n_flight = 0;
-        __syncwarp();
-    };
     auto probe_queue = [&](uint32_t n) {   // the first n queued survivors, one per lane: bucket line from HBM, compare, RED
         if (!(HINTS & 16) && (uint32_t)lane < n) {   // HINTS bit 4: experiment only, survivors are dropped
             const uint32_t idx = (qhead + lane) & (QCAP - 1);
@@ -334,7 +305,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             const uint32_t meta = qmeta[idx];
             uint32_t *cnt = find_slot_from<(HINTS & 2) ? 1 : ((HINTS & 64) ? 2 : 0)>(t, key, meta & 0x7fffffffu, pol_first);
             if (cnt) {
-                if (meta >> 31) atomicAdd(cnt, 2u);                                              // palindrome (even k)
+                if (!KODD && (meta >> 31)) atomicAdd(cnt, 2u);                                   // palindrome (even k)
                 else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);                // +1 on both orientations
             }
         }
@@ -442,8 +413,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         rc = revcomp_hash(x, b.k);
                     }
                     unsigned long long c[WPL];
-                    Hash h[WPL];
-                    uint32_t fw[WPL], fm[WPL];
+                    uint32_t home[WPL], fw[WPL], fm[WPL];
                     uint32_t live = 0, pal = 0;
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
@@ -454,36 +424,31 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         }
                         bool ok = i0 + u < b.nk;
                         c[u] = x < rc ? x : rc;
-                        pal |= (uint32_t)(x == rc) << u;
-                        h[u] = hash_key(c[u]);
-                        fm[u] = filter_mask(t, h[u]);
-                        fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + filter_word(t, h[u]), pol_last) : __ldg(t.filter + filter_word(t, h[u])))
+                        if (!KODD) pal |= (uint32_t)(x == rc) << u;
+                        const Hash h = hash_key(c[u]);
+                        home[u] = home_bucket(t, h);
+                        fm[u] = filter_mask<FK>(t, h);
+                        fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + filter_word(t, h), pol_last) : __ldg(t.filter + filter_word(t, h)))
                                                  : 0xffffffffu;
                         live |= (uint32_t)ok << u;
                     }
 #pragma unroll
                     for (int u = 0; u < WPL; u++) live &= ~((uint32_t)((fw[u] & fm[u]) != fm[u]) << u);
-                    // survivors (few, scattered over lanes) are compacted into the warp's queue; the table is probed
-                    // 32 survivors at a time, so every HBM round trip is shared by a full warp
+                    // survivors (few, scattered over lanes) are compacted into the warp's queue by ballot (a shuffle prefix sum
+                    // over the four windows needs fewer instructions, but its dependent chain made the launch slower), and the
+                    // table is probed 32 survivors at a time, so every HBM round trip is shared by a full warp
+                    const uint32_t below = (1u << lane) - 1u;
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
                         const bool mine = (live >> u) & 1u;
                         const uint32_t votes = __ballot_sync(0xffffffffu, mine);
                         if (mine) {
-                            uint32_t slot_idx = (qn + __popc(votes & ((1u << lane) - 1u))) & (QCAP - 1);
-                            const uint32_t home = home_bucket(t, h[u]);
+                            const uint32_t slot_idx = (qn + __popc(votes & below)) & (QCAP - 1);
                             qkey[slot_idx] = c[u];
-                            qmeta[slot_idx] = home | (((pal >> u) & 1u) << 31);
-                            if (HINTS & 8) asm volatile("prefetch.global.L2 [%0];" ::"l"(t.buckets + home));   // line is in L2 by the time the queue is probed
+                            qmeta[slot_idx] = KODD ? home[u] : (home[u] | (((pal >> u) & 1u) << 31));
                         }
                         qn += __popc(votes);
-                        if (PIPE) {
-                            if (qn - qhead - n_flight >= 32) {
-                                __syncwarp();
-                                probe_complete();
-                                probe_issue(32);
-                            }
-                        } else if (qn - qhead >= 32) {
+                        if (qn - qhead >= 32) {
                             __syncwarp();
                             probe_queue(32);
                         }
@@ -502,7 +467,6 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
         __syncwarp();
     }
     __syncwarp();
-    if (PIPE) probe_complete();
     if (qn != qhead) probe_queue(qn - qhead);   // drain the queue
 }
 
@@ -685,22 +649,29 @@ static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cud
 
 static std::mutex g_launch_mutex;   // the packing lanes launch from their own host threads
 
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false>
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0>
 static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_launch_mutex);
     const size_t smem = (size_t)b.warp_bytes * COUNT_WARPS;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
+    count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
+}
+
+// the production instantiations of the both-strands kernel: odd k and 3 filter bits (the defaults) are compile-time facts
+template <bool PACKED> static int launch_paired(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
+    const bool fk3 = ix->table.filter && ix->table.filter_k == 3;
+    if (b.k & 1) return fk3 ? launch_count_reads_t<true, true, 4, 0, PACKED, true, 3>(ix, b, s) : launch_count_reads_t<true, true, 4, 0, PACKED, true, 0>(ix, b, s);
+    return launch_count_reads_t<true, true, 4, 0, PACKED, false, 0>(ix, b, s);
 }
 
 // reads: device rows
@@ -730,25 +701,12 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     b.bulk_ok = (stride == read_len) && (((uintptr_t)dreads & 15) == 0) && (((int64_t)rpw * read_len) % 16 == 0);
     if (!both) return launch_count_reads_t<false, false, 4>(ix, b, s);
     if (ix->table.k != k) return launch_count_reads_t<true, false, 4>(ix, b, s);
-    int minb = 4;
-    if (const char *e = getenv("GKI_MINB")) minb = atoi(e);
-    int hints = 0;
+    int hints = 0;   // experiment knobs (profiles/tune_count.py): 7 = L2 eviction hints, 16 = drop the survivors, 64 = 64-byte L2 fills
     if (const char *e = getenv("GKI_HINTS")) hints = atoi(e);
-    if (hints == 1) return launch_count_reads_t<true, true, 4, 1>(ix, b, s);
-    if (hints == 2) return launch_count_reads_t<true, true, 4, 2>(ix, b, s);
-    if (hints == 3) return launch_count_reads_t<true, true, 4, 3>(ix, b, s);
-    if (hints == 4) return launch_count_reads_t<true, true, 4, 4>(ix, b, s);
-    if (hints == 5) return launch_count_reads_t<true, true, 4, 5>(ix, b, s);
-    if (hints == 8) return launch_count_reads_t<true, true, 4, 8>(ix, b, s);
-    if (hints == 9) return launch_count_reads_t<true, true, 4, 9>(ix, b, s);
+    if (hints == 7) return launch_count_reads_t<true, true, 4, 7>(ix, b, s);
     if (hints == 16) return launch_count_reads_t<true, true, 4, 16>(ix, b, s);
-    if (hints == 32 && minb == 3) return launch_count_reads_t<true, true, 3, 32>(ix, b, s);
-    if (hints == 32) return launch_count_reads_t<true, true, 4, 32>(ix, b, s);
     if (hints == 64) return launch_count_reads_t<true, true, 4, 64>(ix, b, s);
-    if (minb == 5) return launch_count_reads_t<true, true, 5>(ix, b, s);
-    if (minb == 6) return launch_count_reads_t<true, true, 6>(ix, b, s);
-    if (minb == 3) return launch_count_reads_t<true, true, 3>(ix, b, s);
-    return launch_count_reads_t<true, true, 4>(ix, b, s);
+    return launch_paired<false>(ix, b, s);
 }
 
 // packed reads (gki_pack_reads layout): device rows of ceil(read_len / 32) 64-bit words
@@ -776,7 +734,7 @@ static int launch_count_packed_reads(gki_index *ix, const uint64_t *dpacked, int
     b.bulk_ok = (((uintptr_t)dpacked & 15) == 0) && (((int64_t)rpw * b.words * 8) % 16 == 0);
     if (!both) return launch_count_reads_t<false, false, 4, 0, true>(ix, b, s);
     if (ix->table.k != k) return launch_count_reads_t<true, false, 4, 0, true>(ix, b, s);
-    return launch_count_reads_t<true, true, 4, 0, true>(ix, b, s);
+    return launch_paired<true>(ix, b, s);
 }
 
 // ---- host reads through CPU packing lanes + the copy engine ----
