@@ -42,10 +42,15 @@ def test_no_cpu_fallback(have_cuda):
 
 
 def test_product_never_imports_oracle():
+    """the oracle is test infrastructure: no product source imports, loads or executes anything under oracle/"""
+    import re
     pkg = os.path.join(ROOT, "graph_kmer_index_b200")
+    forbidden = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)|oracle[./](_ref|gki_oracle|c_oracle|numpy_oracle|finder_oracle)|liboracle", re.M)
+    checked = 0
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
-                assert "oracle" not in src.replace("oracle/", "").lower() or f == "synthetic.py" or "import oracle" not in src, f
-                assert "from oracle" not in src and "import oracle" not in src, f
+                assert not forbidden.search(src), f
+                checked += 1
+    assert checked > 15

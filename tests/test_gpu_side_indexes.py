@@ -113,3 +113,39 @@ def test_group_by_key_errors(gki):
         group_by_key(np.array([1, 2, 9], dtype=np.uint32), 5)            # key >= n_keys
     with pytest.raises(_lib.GkiError):
         group_by_key(np.zeros(0, dtype=np.uint32), 5)                    # empty (np.max of an empty array raises in the reference)
+
+
+def test_cli_subcommands(gki, tmp_path):
+    """make_from_flat / add_reverse_complements / make_reverse / make_reference_kmer_index (cli:156-193, 656-667) write the
+    files the reference's classes would: checked against the golden index and the oracle"""
+    from conftest import golden_index
+    from graph_kmer_index_b200.command_line_interface import run_argument_parser
+    g = load_golden("index_small")
+    flat = gki.FlatKmers(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"])
+    flat.to_file(str(tmp_path / "flat"))
+    want = golden_index(g)
+    run_argument_parser(["make_from_flat", "-f", str(tmp_path / "flat.npz"), "-o", str(tmp_path / "index"), "-m", str(want["_modulo"])])
+    index = gki.CollisionFreeKmerIndex.from_file(str(tmp_path / "index"))
+    for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_frequencies", "_allele_frequencies"):
+        assert np.array_equal(getattr(index, key), want[key]), key
+    k = int(g["k"])
+    run_argument_parser(["add_reverse_complements", "-f", str(tmp_path / "flat.npz"), "-o", str(tmp_path / "flat_rc"), "-k", str(k)])
+    both = gki.FlatKmers.from_file(str(tmp_path / "flat_rc.npz"))
+    hashes = np.asarray(flat._hashes).astype(np.uint64)
+    assert np.array_equal(both._hashes, np.concatenate([hashes, no.revcomp_hashes(hashes, k)]))
+    assert np.array_equal(both._nodes, np.concatenate([flat._nodes, flat._nodes]))
+    run_argument_parser(["make_reverse", "-f", str(tmp_path / "flat.npz"), "-o", str(tmp_path / "reverse")])
+    rev = gki.ReverseKmerIndex.from_file(str(tmp_path / "reverse.npz"))
+    for got, wanted in zip((rev.nodes_to_index_positions, rev.nodes_to_n_hashes, rev.hashes, rev.ref_positions),
+                           no.reverse_index(flat._hashes, flat._nodes, flat._ref_offsets)):
+        same(got, wanted, "make_reverse")
+    run_argument_parser(["make_reference_kmer_index", "-f", str(tmp_path / "flat.npz"), "-o", str(tmp_path / "refidx")])
+    refi = gki.ReferenceKmerIndex.from_file(str(tmp_path / "refidx"))
+    for got, wanted in zip((refi.ref_position_to_index, refi.kmers, refi.ref_positions, refi.nodes),
+                           no.reference_index(flat._hashes, flat._nodes, flat._ref_offsets)):
+        same(got, wanted, "make_reference_kmer_index")
+    fasta = tmp_path / "ref.fa"
+    fasta.write_text(">other\nACGT\n>ref some description\nACGTTGCAAC\nGGTTAACC\n")
+    run_argument_parser(["make_reference_kmer_index", "-r", str(fasta), "-n", "ref", "-k", "5", "-o", str(tmp_path / "linear")])
+    lin = gki.ReferenceKmerIndex.from_file(str(tmp_path / "linear"))
+    same(lin.kmers, no.read_kmer_hashes("ACGTTGCAACGGTTAACC", 5).astype(np.uint32), "linear reference")
