@@ -90,6 +90,7 @@ _SIGNATURES = {
     "gki_synth_flat_kmers": [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gki_synth_reads": [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp],
     "gki_calibrate_random_gather": [c_i64, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
+    "gki_calibrate_scatter": [c_i64, c_i32, c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_copy": [c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_critical_paths": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp],
     "gki_finder_prepare": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32,

@@ -261,6 +261,7 @@ struct WarpBatch {
     int32_t words;          // ceil(read_len / 32) + 1
     int32_t rpw;            // reads per warp tile
     int32_t bulk_ok;        // dense + aligned: full tiles are one TMA bulk copy
+    uint32_t inv_halves;    // ceil(65536 / (2 * words)): task / (2 * words) == task * inv_halves >> 16 for every task of a tile
     uint32_t stage_bytes;   // bytes of one ASCII stage (16-byte multiple, incl. slack)
     uint32_t warp_bytes;    // shared memory per warp
 };
@@ -364,35 +365,38 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
         // ---- pack to 2 bits per base (+ validity), flag reads that contain a non-ACGT byte ----
         if (!PACKED && lane < n_here) dirty[lane] = 0;
         __syncwarp();
-        for (int task = lane; !PACKED && task < n_here * b.words; task += 32) {
-            int r = task / b.words, w = task - r * b.words;
-            int first = w * 32;
-            int nb = min(32, b.read_len - first);
-            uint64_t cw = 0, vw = 0;
+        // one task = 16 bases = one 32-bit half of a code word (the pad word included): 8 reads x 12 halves fill the warp
+        // three times over, where whole-word tasks left half of it idle in their second round
+        const int halves = 2 * b.words;
+        for (int task = lane; !PACKED && task < n_here * halves; task += 32) {
+            const int r = (int)(((uint32_t)task * b.inv_halves) >> 16), h = task - r * halves;   // task / halves (exact, checked on the host)
+            const int first = h * 16;
+            const int nb = min(16, b.read_len - first);
+            uint32_t c32 = 0, v32 = 0;
             if (nb > 0) {
-                uint32_t addr = (uint32_t)r * (uint32_t)b.read_len + (uint32_t)first;
+                const uint32_t addr = (uint32_t)r * (uint32_t)b.read_len + (uint32_t)first;
                 const uint32_t *aligned = (const uint32_t *)(ascii + (addr & ~3u));
-                uint32_t sh = (addr & 3u) * 8u;
+                const uint32_t sh = (addr & 3u) * 8u;
                 uint32_t lo = aligned[0];
-                int nq = (nb + 3) >> 2;
+                const int nq = (nb + 3) >> 2;
 #pragma unroll
-                for (int q = 0; q < 8; q++) {
+                for (int q = 0; q < 4; q++) {
                     if (q < nq) {
-                        uint32_t hi = aligned[q + 1];
+                        const uint32_t hi = aligned[q + 1];
                         uint32_t c8, v8;
                         encode4(__funnelshift_r(lo, hi, sh), c8, v8);
                         lo = hi;
-                        cw |= (uint64_t)c8 << (8 * q);
-                        vw |= (uint64_t)v8 << (8 * q);
+                        c32 |= c8 << (8 * q);
+                        v32 |= v8 << (8 * q);
                     }
                 }
-                uint64_t m = nb < 32 ? ((1ull << (2 * nb)) - 1ull) : ~0ull;
-                cw &= m;
-                vw &= m;
-                if (vw != m) dirty[r] = 1;
+                const uint32_t m = nb < 16 ? ((1u << (2 * nb)) - 1u) : ~0u;
+                c32 &= m;
+                v32 &= m;
+                if (v32 != m) dirty[r] = 1;
             }
-            codes[(size_t)r * b.words + w] = cw;
-            valid[(size_t)r * b.words + w] = vw;
+            ((uint32_t *)codes)[(size_t)r * halves + h] = c32;
+            ((uint32_t *)valid)[(size_t)r * halves + h] = v32;
         }
         __syncwarp();
         if (!PACKED && next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next, 0);   // prefetch: overlaps the walk below
@@ -428,8 +432,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         const Hash h = hash_key(c[u]);
                         home[u] = home_bucket(t, h);
                         fm[u] = filter_mask<FK>(t, h);
-                        fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + filter_word(t, h), pol_last) : __ldg(t.filter + filter_word(t, h)))
-                                                 : 0xffffffffu;
+                        const uint32_t word = filter_word(t, h);
+                        fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + word, pol_last) : __ldg(t.filter + word)) : 0xffffffffu;
                         live |= (uint32_t)ok << u;
                     }
 #pragma unroll
@@ -677,7 +681,7 @@ template <bool PACKED> static int launch_paired(gki_index *ix, const WarpBatch &
 // reads: device rows
 static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_reads, int32_t read_len, int64_t stride, int32_t k,
                               int32_t both, cudaStream_t s) {
-    WarpBatch b;
+    WarpBatch b{};
     b.reads = dreads;
     b.n_reads = n_reads;
     b.row_stride = stride;
@@ -695,6 +699,9 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
     GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
     b.rpw = rpw;
+    b.inv_halves = 65536u / (2u * (uint32_t)b.words) + 1u;
+    for (uint32_t task = 0; task < (uint32_t)rpw * 2u * (uint32_t)b.words; task++)
+        GKI_REQUIRE(((task * b.inv_halves) >> 16) == task / (2u * (uint32_t)b.words), GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
     b.stage_bytes = (uint32_t)((((size_t)rpw * read_len + 15) & ~(size_t)15) + 16);
     b.warp_bytes = (uint32_t)warp_bytes(rpw);
     b.n_wtiles = (n_reads + rpw - 1) / rpw;
@@ -712,7 +719,7 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
 // packed reads (gki_pack_reads layout): device rows of ceil(read_len / 32) 64-bit words
 static int launch_count_packed_reads(gki_index *ix, const uint64_t *dpacked, int64_t n_reads, int32_t read_len, int32_t k, int32_t both,
                                      cudaStream_t s) {
-    WarpBatch b;
+    WarpBatch b{};
     b.reads = (const uint8_t *)dpacked;
     b.n_reads = n_reads;
     b.read_len = read_len;

@@ -96,6 +96,41 @@ __global__ void random_gather_kernel(const uint64_t *__restrict__ table, uint32_
     if (acc == 0x123456789abcdefull) *sink = acc;
 }
 
+// ---- calibration of random stores / atomics (the measurements the K2 design rests on) ----
+__global__ void scatter_store_kernel(uint4 *__restrict__ dst, uint32_t n_slots, int64_t n, int bytes) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t s = gather_slot((uint32_t)i, n_slots);
+        const uint4 v = make_uint4((uint32_t)i, s, 1u, 2u);
+        if (bytes == 32) {
+            dst[2 * (size_t)s] = v;
+            dst[2 * (size_t)s + 1] = v;
+        } else if (bytes == 16) {
+            dst[(size_t)s] = v;
+        } else {
+            ((uint2 *)dst)[(size_t)s] = make_uint2(v.x, v.y);
+        }
+    }
+}
+__global__ void atomic_rank_kernel(uint32_t *__restrict__ bins, uint32_t n_bins, int64_t n, int returning, uint32_t *__restrict__ sink) {
+    uint32_t acc = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t *p = bins + gather_slot((uint32_t)i, n_bins);
+        if (returning) acc += atomicAdd(p, 1u);
+        else atomicAdd(p, 1u);
+    }
+    if (acc == 0xdeadbeefu) *sink = acc;
+}
+__global__ void atomic_scatter_kernel(uint32_t *__restrict__ bins, uint32_t n_bins, uint32_t per_bin, uint4 *__restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t b = gather_slot((uint32_t)i, n_bins);
+        const uint32_t r = atomicAdd(bins + b, 1u);
+        const size_t s = (size_t)b * per_bin + (r % per_bin);
+        const uint4 v = make_uint4((uint32_t)i, b, r, 2u);
+        dst[2 * s] = v;
+        dst[2 * s + 1] = v;
+    }
+}
+
 __global__ void fill_kernel(uint64_t *__restrict__ t, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t[i] = splitmix64(i);
 }
@@ -191,6 +226,48 @@ int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t 
     cudaEventDestroy(a);
     cudaEventDestroy(b);
     cudaFree(table);
+    cudaFree(sink);
+    return GKI_OK;
+}
+
+int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms) {
+    GKI_REQUIRE(n >= 1 && n < (1ll << 31) && ms && mode >= 0 && mode <= 5 && n_bins >= 0 && n_bins < (1ll << 31), GKI_ERR_INVALID,
+                "gki_calibrate_scatter: bad arguments");
+    GKI_REQUIRE(mode < 3 || n_bins >= 1, GKI_ERR_INVALID, "gki_calibrate_scatter: the atomic modes need n_bins");
+    uint4 *dst = nullptr;
+    uint32_t *bins = nullptr, *sink = nullptr;
+    const uint32_t per_bin = mode == 5 ? (uint32_t)(n / n_bins) + 1 : 0;
+    const size_t dst_bytes = mode == 5 ? (size_t)n_bins * per_bin * 32 : (size_t)n * 32;
+    if (mode <= 2 || mode == 5) GKI_CUDA(cudaMalloc((void **)&dst, dst_bytes));
+    if (mode >= 3) {
+        GKI_CUDA(cudaMalloc((void **)&bins, (size_t)n_bins * 4));
+        GKI_CUDA(cudaMemset(bins, 0, (size_t)n_bins * 4));
+    }
+    GKI_CUDA(cudaMalloc((void **)&sink, 4));
+    const int grid = device_info().sms * 16;
+    auto run = [&]() {
+        if (mode == 0) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 32);
+        else if (mode == 1) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 16);
+        else if (mode == 2) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 8);
+        else if (mode == 3) atomic_rank_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, n, 1, sink);
+        else if (mode == 4) atomic_rank_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, n, 0, sink);
+        else atomic_scatter_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, per_bin, dst, n);
+    };
+    cudaEvent_t a, b;
+    GKI_CUDA(cudaEventCreate(&a));
+    GKI_CUDA(cudaEventCreate(&b));
+    run();   // warm-up
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(a));
+    run();
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(b));
+    GKI_CUDA(cudaEventSynchronize(b));
+    GKI_CUDA(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(dst);
+    cudaFree(bins);
     cudaFree(sink);
     return GKI_OK;
 }
