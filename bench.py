@@ -378,7 +378,10 @@ def main():
     positions = kmers_per_launch / 2.0
     h_pos = 2.0 * h                                         # hit positions / positions (a position hits on one strand)
     filter_resident = info["has_filter"] and (n // 2) <= (32 << 20)
-    filter_lines = 0.0 if filter_resident else (1.0 if info["has_filter"] else 0.0)
+    # a filter larger than L2 is addressed by minimizer (csrc/count.cu, filter_m): consecutive windows share a line as long as
+    # their minimizer does, on average (w + 1) / 2 = 9 windows for the 17 m-mers of a k-mer
+    minimizer_filter = (not filter_resident) and k in (27, 29, 31) and os.environ.get("GKI_FILTER_MZ", "1") != "0"
+    filter_lines = 0.0 if (filter_resident or not info["has_filter"]) else (2.0 / 18.0 if minimizer_filter else 1.0)
     bytes_per_position = 2.0 * L / nk_per_read + LINE * filter_lines + (LINE + 32.0) * h_pos
     bytes_per_kmer = bytes_per_position / 2.0
     achieved = kmers_per_launch * bytes_per_kmer / (kernel_ms / 1e3) / 1e9
@@ -396,7 +399,7 @@ def main():
     # per-thread global requests through L1TEX (1 sector per cycle per SM) and random HBM line fetches
     requests = positions * (1.0 + 2.0 * h_pos + 0.05)      # filter word + (keys load + RED) per hit + ~5 % false positives
     hbm_lines = positions * (h_pos + filter_lines + 0.05)
-    roofline = {"bound": "hbm", "kernel": "count_reads_kernel<both=true,paired=true> (L2 Bloom filter: %s)" % str(info["has_filter"]).lower(),
+    roofline = {"bound": "hbm", "kernel": "count_reads_kernel<both=true,paired=true> (Bloom filter: %s)" % ("none" if not info["has_filter"] else ("L2-resident" if filter_resident else ("HBM, minimizer-addressed" if minimizer_filter else "HBM"))),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms * args.steps / elapsed_ms,
                 "algorithmic_bytes_per_kmer": bytes_per_kmer, "hit_fraction_of_kmers": h, "positions_per_launch": positions,

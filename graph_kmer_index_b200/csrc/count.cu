@@ -67,6 +67,48 @@ __device__ __forceinline__ uint32_t filter_mask(const TableView &t, const Hash &
     return mask;
 }
 
+// ---- minimizer-addressed filter words ----
+// A filter that does not fit L2 costs one HBM line per probe when the word is chosen by the key's hash (C3: 4.5 G lines per
+// step).  Choosing the 32-byte sector by the k-mer's minimizer instead -- the canonical m-mer, m = k - 16, with the smallest
+// hash among the 17 the k-mer holds -- makes the ~9 consecutive windows of a read that share a minimizer probe the same
+// sector; the word inside the sector and the bits still come from the key's hash.  Strand-symmetric: a k-mer and its
+// reverse complement hold the same canonical m-mers.
+constexpr int MZ_W = 17;
+__device__ __forceinline__ uint32_t revcomp_m(uint32_t x, int m) {   // m <= 15 bases in 32 bits
+    uint32_t y = __brev(~x);
+    y = ((y >> 1) & 0x55555555u) | ((y & 0x55555555u) << 1);
+    return y >> (2 * (16 - m));
+}
+__device__ __forceinline__ uint32_t mmer_hash(uint32_t fwd, uint32_t rc) {
+    uint32_t c = (fwd < rc ? fwd : rc) * 0x9E3779B1u;
+    return c ^ (c >> 16);
+}
+__device__ __forceinline__ uint32_t kmer_minimizer(unsigned long long x, int m) {   // smallest mmer_hash over the k-mer's 17 m-mers
+    const uint32_t mmask = (1u << (2 * m)) - 1u;
+    uint32_t fwd = (uint32_t)x & mmask, rc = revcomp_m(fwd, m);
+    uint32_t best = mmer_hash(fwd, rc);
+    x >>= 2 * m;
+#pragma unroll 4
+    for (int j = 1; j < MZ_W; j++) {
+        const uint32_t nb = (uint32_t)x & 3u;
+        x >>= 2;
+        fwd = (fwd >> 2) | (nb << (2 * (m - 1)));
+        rc = ((rc << 2) | (3u - nb)) & mmask;
+        best = min(best, mmer_hash(fwd, rc));
+    }
+    return best;
+}
+__device__ __forceinline__ uint32_t filter_word_mz(const TableView &t, const Hash &h, uint32_t minimizer) {
+    uint32_t s = minimizer * 0x85EBCA6Bu;   // the minimum of 17 hashes is far from uniform: mix again before the range reduction
+    s ^= s >> 13;
+    s *= 0xC2B2AE35u;
+    s ^= s >> 16;
+    return __umulhi(s, t.filter_words >> 3) * 8u + (h.f >> 29);
+}
+__device__ __forceinline__ uint32_t filter_word_of(const TableView &t, const Hash &h, unsigned long long key) {
+    return t.filter_m ? filter_word_mz(t, h, kmer_minimizer(key, t.filter_m)) : filter_word(t, h);
+}
+
 struct Key {
     unsigned long long c;   // table key
     uint32_t o;             // orientation (0: the query is the key itself)
@@ -179,7 +221,7 @@ __device__ __forceinline__ void count_one(const TableView &t, uint64_t q) {
     Hash h = hash_key(key.c);
     if (t.filter) {
         uint32_t m = filter_mask(t, h);
-        if ((__ldg(t.filter + filter_word(t, h)) & m) != m) return;
+        if ((__ldg(t.filter + filter_word_of(t, h, key.c)) & m) != m) return;
     }
     uint32_t *cnt = find_slot(t, key.c, h);
     if (cnt) atomicAdd(cnt + key.o, 1u);
@@ -221,7 +263,7 @@ __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ km
             continue;
         }
         Hash h = hash_key(key.c);
-        if (filter) atomicOr(filter + filter_word(t, h), filter_mask(t, h));
+        if (filter) atomicOr(filter + filter_word_of(t, h, key.c), filter_mask(t, h));
         uint32_t b = home_bucket(t, h);
         bool placed = false;
         for (uint32_t tries = 0; tries < t.n_buckets && !placed; tries++) {
@@ -261,6 +303,8 @@ struct WarpBatch {
     int32_t words;          // ceil(read_len / 32) + 1
     int32_t rpw;            // reads per warp tile
     int32_t bulk_ok;        // dense + aligned: full tiles are one TMA bulk copy
+    uint32_t mz_off;        // minimizer filters: byte offset (16-aligned) of the per-warp m-mer hash array, mz_len entries
+    uint32_t mz_len;
     uint32_t inv_halves;    // ceil(65536 / (2 * words)): task / (2 * words) == task * inv_halves >> 16 for every task of a tile
     uint32_t stage_bytes;   // bytes of one ASCII stage (16-byte multiple, incl. slack)
     uint32_t warp_bytes;    // shared memory per warp
@@ -274,7 +318,9 @@ constexpr int QCAP = 64;
 // PACKED: the batch is already 2 bits per base (gki_pack_reads layout: read r owns b.words 64-bit words, every byte was
 // one of ACGTacgt) -- the tile lands straight in the code words, double-buffered, and the pack phase disappears.
 // KODD: k is odd, no k-mer equals its own reverse complement (no palindrome bookkeeping).  FK: filter bits per key (0: runtime).
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0>
+// MINZ: the filter is minimizer-addressed (t.filter_m): per read the hashes of all canonical m-mers go to shared memory
+// and every window takes the minimum of its 17.
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0, bool MINZ = false>
 __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableView t, WarpBatch b) {
     const unsigned long long pol_last = (HINTS & 1) ? l2_policy_evict_last() : 0ull;
     const unsigned long long pol_first = (HINTS & 2) ? l2_policy_evict_first() : 0ull;
@@ -296,6 +342,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                                       : (unsigned long long *)(valid + (size_t)b.rpw * b.words);   // survivor queue: keys
     uint32_t *qmeta = (uint32_t *)(qkey + QCAP);                                           //   home bucket | palindrome << 31
     uint32_t *dirty = qmeta + QCAP;
+    uint32_t *mzh = (uint32_t *)(wbase + b.mz_off);
     const uint64_t mask = kmer_mask(b.k);
     const uint32_t tile_bytes = PACKED ? (uint32_t)b.rpw * (uint32_t)b.words * 8u : (uint32_t)b.rpw * (uint32_t)b.read_len;
     uint32_t qn = 0, qhead = 0;   // warp-uniform: entries pushed / consumed so far
@@ -407,8 +454,50 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             if (PAIRED && (PACKED || !dirty[r])) {
                 // clean read: lane owns WPL consecutive windows, rolled from one extraction; the reverse-complement
                 // hash is rolled alongside (kmer_hashing.py:24-28 == bit reversal of the complemented window)
+                if (MINZ) {   // hashes of the read's canonical m-mers, five consecutive positions per lane
+                    const int m = t.filter_m, n_pos = b.read_len - m + 1;
+                    const uint32_t mmask = (1u << (2 * m)) - 1u;
+                    __syncwarp();   // the previous read's windows are done with the array
+                    for (int p0 = lane * 5; p0 < (int)b.mz_len; p0 += 160) {
+                        uint32_t hv[5] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+                        if (p0 < n_pos) {
+                            uint64_t win = extract_window(cw, p0, (1ull << (2 * (m + 4))) - 1ull);
+                            uint32_t fwd = (uint32_t)win & mmask, rcm = revcomp_m(fwd, m);
+                            hv[0] = mmer_hash(fwd, rcm);
+                            win >>= 2 * m;
+#pragma unroll
+                            for (int j = 1; j < 5; j++) {
+                                const uint32_t nb = (uint32_t)win & 3u;
+                                win >>= 2;
+                                fwd = (fwd >> 2) | (nb << (2 * (m - 1)));
+                                rcm = ((rcm << 2) | (3u - nb)) & mmask;
+                                if (p0 + j < n_pos) hv[j] = mmer_hash(fwd, rcm);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < 5; j++)
+                            if (p0 + j < (int)b.mz_len) mzh[p0 + j] = hv[j];
+                    }
+                    __syncwarp();
+                }
                 for (int base = 0; base < b.nk; base += 32 * WPL) {
                     const int i0 = base + lane * WPL;
+                    uint32_t mz[WPL] = {0, 0, 0, 0};   // MINZ: minimizer of each of the lane's windows
+                    if (MINZ && i0 < b.nk) {
+                        uint32_t v[MZ_W + 3];
+#pragma unroll
+                        for (int j = 0; j < (MZ_W + 3) / 4; j++) {
+                            const uint4 q = *(const uint4 *)(mzh + i0 + 4 * j);
+                            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                        }
+                        uint32_t common = v[3];
+#pragma unroll
+                        for (int j = 4; j < MZ_W; j++) common = min(common, v[j]);
+                        mz[0] = min(common, min(v[0], min(v[1], v[2])));
+                        mz[1] = min(common, min(v[1], min(v[2], v[MZ_W])));
+                        mz[2] = min(common, min(v[2], min(v[MZ_W], v[MZ_W + 1])));
+                        mz[3] = min(common, min(v[MZ_W], min(v[MZ_W + 1], v[MZ_W + 2])));
+                    }
                     uint64_t x = 0, rc = 0;
                     uint32_t nxt = 0;
                     if (i0 < b.nk) {
@@ -432,7 +521,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         const Hash h = hash_key(c[u]);
                         home[u] = home_bucket(t, h);
                         fm[u] = filter_mask<FK>(t, h);
-                        const uint32_t word = filter_word(t, h);
+                        const uint32_t word = MINZ ? filter_word_mz(t, h, mz[u]) : filter_word(t, h);
                         fw[u] = (t.filter && ok) ? ((HINTS & 1) ? ld_u32_hint(t.filter + word, pol_last) : __ldg(t.filter + word)) : 0xffffffffu;
                         live |= (uint32_t)ok << u;
                     }
@@ -584,7 +673,7 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     // from a compact region instead of a bucket line from the 32x larger table.
     if (!getenv("GKI_FILTER_MAX_MB") && (size_t)distinct > budget) budget = (size_t)distinct;
     size_t fbytes = want < budget ? want : budget;
-    fbytes = (fbytes + 3) & ~(size_t)3;
+    fbytes = (fbytes + 31) & ~(size_t)31;   // whole 32-byte sectors
     if (fbytes < 64) fbytes = 64;
     double bits_per_key = distinct ? (double)fbytes * 8.0 / (double)distinct : 16.0;
     uint32_t *filter = nullptr;
@@ -593,6 +682,11 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
         GKI_CUDA(cudaMemsetAsync(filter, 0, fbytes, s));
         t.filter = filter;
         t.filter_words = (uint32_t)(fbytes / 4);
+        // a filter that cannot stay in L2 is addressed by minimizer (odd k in 27..31: 17 m-mers of m = k - 16 <= 15 bases)
+        const bool mz_possible = k >= 27 && k <= 31 && (k & 1);
+        bool mz = mz_possible && fbytes > ((size_t)48 << 20);
+        if (const char *e = getenv("GKI_FILTER_MZ")) mz = mz_possible && atoi(e) != 0;
+        t.filter_m = mz ? k - 16 : 0;
         t.filter_k = bits_per_key >= 5.0 ? 3 : (bits_per_key >= 3.0 ? 2 : 1);
         if (const char *e = getenv("GKI_FILTER_K")) t.filter_k = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
         ix->filter_bytes = fbytes;
@@ -653,20 +747,20 @@ static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cud
 
 static std::mutex g_launch_mutex;   // the packing lanes launch from their own host threads
 
-template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0>
+template <bool BOTH, bool PAIRED, int MINB, int HINTS = 0, bool PACKED = false, bool KODD = false, int FK = 0, bool MINZ = false>
 static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
     std::lock_guard<std::mutex> lock(g_launch_mutex);
     const size_t smem = (size_t)b.warp_bytes * COUNT_WARPS;
     static size_t attr_smem = 0;
     if (smem > attr_smem) {
-        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GKI_CUDA(cudaFuncSetAttribute(count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
     int blocks_per_sm = 0;
-    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK>, COUNT_THREADS, smem));
+    GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
-    count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
+    count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
 }
@@ -674,6 +768,9 @@ static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t 
 // the production instantiations of the both-strands kernel: odd k and 3 filter bits (the defaults) are compile-time facts
 template <bool PACKED> static int launch_paired(gki_index *ix, const WarpBatch &b, cudaStream_t s) {
     const bool fk3 = ix->table.filter && ix->table.filter_k == 3;
+    if (ix->table.filter && ix->table.filter_m) {   // minimizer-addressed filter: odd k in 27..31 by construction (ensure_table)
+        return fk3 ? launch_count_reads_t<true, true, 4, 0, PACKED, true, 3, true>(ix, b, s) : launch_count_reads_t<true, true, 4, 0, PACKED, true, 0, true>(ix, b, s);
+    }
     if (b.k & 1) return fk3 ? launch_count_reads_t<true, true, 4, 0, PACKED, true, 3>(ix, b, s) : launch_count_reads_t<true, true, 4, 0, PACKED, true, 0>(ix, b, s);
     return launch_count_reads_t<true, true, 4, 0, PACKED, false, 0>(ix, b, s);
 }
@@ -689,16 +786,20 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     b.k = k;
     b.nk = read_len - k + 1;
     b.words = (read_len + 31) / 32 + 1;
-    auto warp_bytes = [&](int rpw) {
+    const bool minz = both && ix->table.k == k && ix->table.filter && ix->table.filter_m;
+    b.mz_len = minz ? (uint32_t)((read_len + 8) & ~3) : 0u;   // m-mer positions of a read, padded so that every window's 20 loads stay inside
+    auto mz_offset = [&](int rpw) {
         size_t stage = (((size_t)rpw * read_len + 15) & ~(size_t)15) + 16;
         size_t bytes = 16 + stage + 2 * (size_t)rpw * b.words * 8 + (size_t)QCAP * 12 + (size_t)rpw * 4;
         return (bytes + 15) & ~(size_t)15;
     };
+    auto warp_bytes = [&](int rpw) { return mz_offset(rpw) + (size_t)b.mz_len * 4; };
     int rpw = 8;
     if (const char *e = getenv("GKI_RPW")) rpw = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
     while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
     GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
     b.rpw = rpw;
+    b.mz_off = (uint32_t)mz_offset(rpw);
     b.inv_halves = 65536u / (2u * (uint32_t)b.words) + 1u;
     for (uint32_t task = 0; task < (uint32_t)rpw * 2u * (uint32_t)b.words; task++)
         GKI_REQUIRE(((task * b.inv_halves) >> 16) == task / (2u * (uint32_t)b.words), GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
@@ -727,14 +828,18 @@ static int launch_count_packed_reads(gki_index *ix, const uint64_t *dpacked, int
     b.nk = read_len - k + 1;
     b.words = (read_len + 31) / 32;
     b.row_stride = (int64_t)b.words * 8;
-    auto warp_bytes = [&](int rpw) {
+    const bool minz = both && ix->table.k == k && ix->table.filter && ix->table.filter_m;
+    b.mz_len = minz ? (uint32_t)((read_len + 8) & ~3) : 0u;
+    auto mz_offset = [&](int rpw) {
         size_t stage = (size_t)rpw * b.words * 8 + 16;
         return (16 + 2 * stage + (size_t)QCAP * 12 + 15) & ~(size_t)15;
     };
+    auto warp_bytes = [&](int rpw) { return mz_offset(rpw) + (size_t)b.mz_len * 4; };
     int rpw = 8;
     while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
     GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_packed_reads: read_len %d too long for the tile path", read_len);
     b.rpw = rpw;
+    b.mz_off = (uint32_t)mz_offset(rpw);
     b.stage_bytes = (uint32_t)((size_t)rpw * b.words * 8 + 16);
     b.warp_bytes = (uint32_t)warp_bytes(rpw);
     b.n_wtiles = (n_reads + rpw - 1) / rpw;

@@ -33,6 +33,8 @@ struct TableView {
     uint32_t n_buckets;
     uint32_t filter_words;
     int32_t filter_k;         // bits set per key (1..3)
+    int32_t filter_m;         // 0: the filter word is chosen by the key's hash; m > 0: by the k-mer's minimizer (canonical m-mer with
+                              // the smallest hash), so consecutive windows of a read share 32-byte sectors (filters larger than L2)
     int32_t k;                // canonical k-mer length, 0 = raw keys
 };
 

@@ -173,7 +173,7 @@ def test_lookup_and_counts_golden(gki, name):
     assert np.array_equal(counter.get_node_counts(n_nodes), g["read_node_counts"])
 
 
-@pytest.mark.parametrize("mode", ["canonical", "raw", "nofilter", "tinyfilter", "k_mismatch"])
+@pytest.mark.parametrize("mode", ["canonical", "raw", "nofilter", "tinyfilter", "k_mismatch", "minimizer", "minimizer_k_mismatch"])
 @pytest.mark.parametrize("n,modulo,n_reads,L,k", [(40000, 200003, 3000, 150, 31), (40000, 4099, 1500, 150, 31), (5000, 7, 300, 100, 15),
                                                    (40000, 200003, 777, 64, 31), (3000, 1009, 400, 90, 16)])
 def test_count_reads_vs_oracle(gki, monkeypatch, mode, n, modulo, n_reads, L, k):
@@ -197,8 +197,10 @@ def test_count_reads_vs_oracle(gki, monkeypatch, mode, n, modulo, n_reads, L, k)
         monkeypatch.setenv("GKI_FILTER_MAX_MB", "0")
     elif mode == "tinyfilter":
         monkeypatch.setenv("GKI_FILTER_K", "1")
+    elif mode.startswith("minimizer"):                 # filter words addressed by minimizer (odd k in 27..31, else it stays off)
+        monkeypatch.setenv("GKI_FILTER_MZ", "1")
     dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo)
-    dev.prepare_counting((k + 1 if k < 31 else k - 1) if mode == "k_mismatch" else (0 if mode == "raw" else k))
+    dev.prepare_counting((k + 1 if k < 31 else k - 1) if mode == "k_mismatch" else (29 if mode == "minimizer_k_mismatch" else (0 if mode == "raw" else k)))
     assert dev.info()["has_filter"] == (mode != "nofilter")
     want = c_oracle.read_node_counts(idx, reads, k, 1000)
     assert want.sum() > 0

@@ -26,8 +26,10 @@ def make_index(gki, n, k, modulo, table_k=None):
 @pytest.mark.parametrize("n,modulo,n_reads,L,k,table_k", [(40000, 200003, 3001, 150, 31, None), (40000, 4099, 1500, 128, 31, None),
                                                            (5000, 7, 300, 100, 15, None), (40000, 200003, 777, 33, 31, None),
                                                            (3000, 1009, 400, 90, 16, None), (40000, 200003, 900, 150, 31, 30)])
-def test_count_packed_reads_vs_oracle(gki, n, modulo, n_reads, L, k, table_k):
+@pytest.mark.parametrize("minimizer_filter", ["0", "1"])
+def test_count_packed_reads_vs_oracle(gki, monkeypatch, minimizer_filter, n, modulo, n_reads, L, k, table_k):
     import torch
+    monkeypatch.setenv("GKI_FILTER_MZ", minimizer_filter)
     from graph_kmer_index_b200 import synthetic
     from graph_kmer_index_b200.read_kmers import pack_reads
     idx, dev = make_index(gki, n, k, modulo, table_k)
