@@ -434,7 +434,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "index_build": {"entries_per_s": n / (build_ms / 1e3), "ms": build_ms, "entries": n,
                             "compulsory_gbs": (50.0 * n + 8.0 * modulo) / (build_ms / 1e3) / 1e9,
-                            "note": "gki_index_build (skip_frequencies, kmers+nodes), device-resident, second of two runs"},
+                            "note": "gki_index_build (skip_frequencies, kmers+nodes), device-resident, second of two runs; binned path (one scatter + per-bin ordering, csrc/build.cu)"},
             "index_build_partitioned": part_build,
             "index": {"device_bytes": info["device_bytes"], "has_filter": info["has_filter"], "nonempty_buckets": info["nonempty_buckets"]}}
     print(json.dumps(line), flush=True)

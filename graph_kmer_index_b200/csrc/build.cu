@@ -277,14 +277,283 @@ template <typename T> __global__ void gather_kernel(const T *__restrict__ src, c
         out[i] = __ldg(src + __ldg(perm + i));
 }
 
+// ---- binned build: one scatter pass, then every bin is ordered on its own --------------------------------------------------
+// Bucket ids of an index are hashes, close to uniform over [0, modulo): a bin of 2^shift consecutive buckets receives a
+// predictable handful of entries.  So instead of three radix passes plus a random gather: (1) histogram of the bins (RED on an
+// L2-resident counter array), exclusive scan; (2) every entry is written once, as a whole record, to the next free slot of its
+// bin (returning atomic on the bin's cursor; the measured ceiling for random 32-byte stores is ~20 G/s,
+// profiles/r1/calibrate_scatter.jsonl); (3) one warp per bin brings its records into (bucket, input index) order in shared
+// memory -- the canonical stable order, whatever order the atomics produced -- and streams out the payload columns and BOTH
+// dense tables, empty buckets included (no memset, no random table scatter).  Bins that overflow the per-warp capacity (tiny
+// modulo, one k-mer repeated hundreds of times) send the whole build to the radix path.
+constexpr int BIN_CAP = 512;          // records per bin the finish kernel can order
+constexpr int BIN_MAX_SHIFT = 8;      // at most 256 buckets per bin
+constexpr int BIN_WARPS = 4;
+struct BinParams {
+    FastMod fm;
+    uint32_t bucket_lo, shift, n_bins;
+    uint64_t table_len;
+};
+__device__ __forceinline__ uint32_t bin_of(uint64_t kmer, const BinParams &p) { return (fastmod(kmer, p.fm) - p.bucket_lo) >> p.shift; }
+
+__global__ void bin_hist_kernel(const uint64_t *__restrict__ kmers, int64_t n, BinParams p, uint32_t *__restrict__ counts) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(counts + bin_of(__ldg(kmers + i), p), 1u);
+}
+__global__ void bin_max_kernel(const uint32_t *__restrict__ counts, uint32_t n_bins, uint32_t *__restrict__ max_out) {
+    uint32_t m = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_bins; i += gridDim.x * blockDim.x) m = max(m, counts[i]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(max_out, m);
+}
+// record = {kmer, node, index} (16 B) or, WIDE, {kmer, ref_offset | node, af, index, -} (32 B)
+template <bool WIDE>
+__global__ void bin_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes,
+                                   const uint64_t *__restrict__ ref, const float *__restrict__ af, BinParams p,
+                                   const uint32_t *__restrict__ bin_start, uint32_t *__restrict__ cursor, uint4 *__restrict__ rec) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t km = __ldg(kmers + i);
+        const uint32_t bin = bin_of(km, p);
+        const size_t pos = (size_t)__ldg(bin_start + bin) + atomicAdd(cursor + bin, 1u);
+        const uint32_t nd = nodes ? __ldg(nodes + i) : 0u;
+        if (WIDE) {
+            const uint64_t r = ref ? __ldg(ref + i) : 0ull;
+            rec[2 * pos] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), (uint32_t)r, (uint32_t)(r >> 32));
+            rec[2 * pos + 1] = make_uint4(nd, af ? __float_as_uint(__ldg(af + i)) : 0u, (uint32_t)i, 0u);
+        } else {
+            rec[pos] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), nd, (uint32_t)i);
+        }
+    }
+}
+template <bool WIDE>
+__global__ void __launch_bounds__(BIN_WARPS * 32)
+bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uint4 *__restrict__ rec, int32_t *__restrict__ h2i,
+                  uint32_t *__restrict__ nk, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o, uint64_t *__restrict__ ref_o,
+                  float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
+    __shared__ uint32_t s_cnt[BIN_WARPS][1 << BIN_MAX_SHIFT], s_excl[BIN_WARPS][1 << BIN_MAX_SHIFT], s_idx[BIN_WARPS][BIN_CAP];
+    __shared__ uint16_t s_bucket[BIN_WARPS][BIN_CAP], s_order[BIN_WARPS][BIN_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *cnt = s_cnt[warp], *excl = s_excl[warp], *idx = s_idx[warp];
+    uint16_t *bucket = s_bucket[warp], *order = s_order[warp];
+    const uint32_t B = 1u << p.shift;
+    for (uint32_t bin = blockIdx.x * BIN_WARPS + warp; bin < p.n_bins; bin += gridDim.x * BIN_WARPS) {
+        const uint32_t start = __ldg(bin_start + bin), c = __ldg(bin_start + bin + 1) - start;
+        const uint64_t first_bucket = (uint64_t)bin << p.shift;
+        for (uint32_t b = lane; b < B; b += 32) cnt[b] = 0;
+        __syncwarp();
+        for (uint32_t j = lane; j < c; j += 32) {
+            const uint4 a = __ldg(rec + (WIDE ? 2 * (size_t)(start + j) : (size_t)(start + j)));
+            const uint64_t km = ((uint64_t)a.y << 32) | a.x;
+            const uint32_t bl = (uint32_t)((fastmod(km, p.fm) - p.bucket_lo) - first_bucket);
+            bucket[j] = (uint16_t)bl;
+            idx[j] = WIDE ? __ldg(rec + 2 * (size_t)(start + j) + 1).z : a.w;
+            atomicAdd(cnt + bl, 1u);
+        }
+        __syncwarp();
+        // exclusive scan of the bucket counts: every lane owns B/32 consecutive buckets (all of them in lane 0.. when B < 32)
+        const uint32_t per = (B + 31) / 32;
+        uint32_t mine = 0;
+        for (uint32_t q = 0; q < per; q++) {
+            const uint32_t b = lane * per + q;
+            if (b < B) mine += cnt[b];
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += up;
+        }
+        uint32_t run = incl - mine;
+        for (uint32_t q = 0; q < per; q++) {
+            const uint32_t b = lane * per + q;
+            if (b < B) {
+                excl[b] = run;
+                run += cnt[b];
+            }
+        }
+        __syncwarp();
+        // both tables, every bucket of the bin (cfki:444-457): position of the run head, run length; 0 / 0 when empty
+        for (uint32_t b = lane; b < B; b += 32) {
+            const uint64_t g = first_bucket + b;
+            if (g < p.table_len) {
+                const uint32_t len = cnt[b];
+                nk[g] = len;
+                h2i[g] = len ? (int32_t)(start + excl[b]) : 0;
+            }
+        }
+        // group the records by bucket (any order), then order every bucket's run by input index: the stable order
+        __syncwarp();
+        for (uint32_t j = lane; j < c; j += 32) order[atomicAdd(excl + bucket[j], 1u)] = (uint16_t)j;   // excl[b] becomes the run's end
+        __syncwarp();
+        for (uint32_t b = lane; b < B; b += 32) {
+            const uint32_t len = cnt[b], lo = excl[b] - len;
+            for (uint32_t a = 1; a < len; a++) {   // insertion sort: runs are a handful of entries
+                const uint16_t moving = order[lo + a];
+                const uint32_t key = idx[moving];
+                uint32_t q = a;
+                while (q > 0 && idx[order[lo + q - 1]] > key) {
+                    order[lo + q] = order[lo + q - 1];
+                    q--;
+                }
+                order[lo + q] = moving;
+            }
+        }
+        __syncwarp();
+        for (uint32_t q = lane; q < c; q += 32) {
+            const size_t src = (size_t)start + order[q], dst = (size_t)start + q;
+            const uint4 a = __ldg(rec + (WIDE ? 2 * src : src));
+            if (kmers_o) kmers_o[dst] = ((uint64_t)a.y << 32) | a.x;
+            if (WIDE) {
+                const uint4 b2 = __ldg(rec + 2 * src + 1);
+                if (ref_o) ref_o[dst] = ((uint64_t)a.w << 32) | a.z;
+                if (nodes_o) nodes_o[dst] = b2.x;
+                if (af_o) af_o[dst] = __uint_as_float(b2.y);
+                if (perm_o) perm_o[dst] = b2.z;
+            } else {
+                if (nodes_o) nodes_o[dst] = a.z;
+                if (perm_o) perm_o[dst] = a.w;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// The common case -- at most 64 records in every bin, usually under 32 -- needs no per-bucket arrays: with one record per lane
+// the rank of a record in (bucket, input index) order comes from eight ballots over the bits of its bucket id (lanes with a
+// smaller bucket, lanes with the same one) plus a walk over the one or two lanes that share its bucket.  Records stay in
+// registers from the single load to the final stores; both tables are zero-filled for the bin's buckets first and the run heads
+// then overwrite their entries.  Bins with 33..64 records take two records per lane and count ranks against shared memory.
+constexpr int BIN_SMALL_CAP = 64;
+template <bool WIDE>
+__global__ void __launch_bounds__(BIN_WARPS * 32)
+bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uint4 *__restrict__ rec, int32_t *__restrict__ h2i,
+                        uint32_t *__restrict__ nk, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o,
+                        uint64_t *__restrict__ ref_o, float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
+    __shared__ unsigned long long s_comp[BIN_WARPS][BIN_SMALL_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *comp = s_comp[warp];
+    const uint32_t B = 1u << p.shift;
+    auto emit = [&](size_t dst, const uint4 &a, const uint4 &b2) {
+        if (kmers_o) kmers_o[dst] = ((uint64_t)a.y << 32) | a.x;
+        if (WIDE) {
+            if (ref_o) ref_o[dst] = ((uint64_t)a.w << 32) | a.z;
+            if (nodes_o) nodes_o[dst] = b2.x;
+            if (af_o) af_o[dst] = __uint_as_float(b2.y);
+            if (perm_o) perm_o[dst] = b2.z;
+        } else {
+            if (nodes_o) nodes_o[dst] = a.z;
+            if (perm_o) perm_o[dst] = a.w;
+        }
+    };
+    for (uint32_t bin = blockIdx.x * BIN_WARPS + warp; bin < p.n_bins; bin += gridDim.x * BIN_WARPS) {
+        const uint32_t start = __ldg(bin_start + bin), c = __ldg(bin_start + bin + 1) - start;
+        const uint64_t first_bucket = (uint64_t)bin << p.shift;
+        // zero both tables over the bin's buckets (cfki:451-452: np.zeros)
+        if (B >= 4 && first_bucket + B <= p.table_len) {
+            for (uint32_t q = lane; q < B / 4; q += 32) {
+                ((uint4 *)(h2i + first_bucket))[q] = make_uint4(0u, 0u, 0u, 0u);
+                ((uint4 *)(nk + first_bucket))[q] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        } else {
+            for (uint32_t b = lane; b < B; b += 32)
+                if (first_bucket + b < p.table_len) {
+                    h2i[first_bucket + b] = 0;
+                    nk[first_bucket + b] = 0u;
+                }
+        }
+        uint4 a0 = make_uint4(0u, 0u, 0u, 0u), b0 = a0, a1 = a0, b1 = a0;
+        uint32_t bl0 = 0xffffu, bl1 = 0xffffu, id0 = 0, id1 = 0;
+        const bool have0 = (uint32_t)lane < c, have1 = (uint32_t)lane + 32u < c;
+        if (have0) {
+            a0 = __ldg(rec + (WIDE ? 2 * (size_t)(start + lane) : (size_t)(start + lane)));
+            if (WIDE) b0 = __ldg(rec + 2 * (size_t)(start + lane) + 1);
+            bl0 = (uint32_t)((fastmod(((uint64_t)a0.y << 32) | a0.x, p.fm) - p.bucket_lo) - first_bucket);
+            id0 = WIDE ? b0.z : a0.w;
+        }
+        if (have1) {
+            a1 = __ldg(rec + (WIDE ? 2 * (size_t)(start + 32 + lane) : (size_t)(start + 32 + lane)));
+            if (WIDE) b1 = __ldg(rec + 2 * (size_t)(start + 32 + lane) + 1);
+            bl1 = (uint32_t)((fastmod(((uint64_t)a1.y << 32) | a1.x, p.fm) - p.bucket_lo) - first_bucket);
+            id1 = WIDE ? b1.z : a1.w;
+        }
+        __syncwarp();   // the zero fill is ordered before the run heads' stores below
+        if (c <= 32) {
+            const uint32_t active = __ballot_sync(0xffffffffu, have0);
+            uint32_t eq = active, lt = 0;
+#pragma unroll
+            for (int bit = BIN_MAX_SHIFT - 1; bit >= 0; bit--) {   // MSB first: lanes with a smaller bucket id, lanes with mine
+                const uint32_t ones = __ballot_sync(0xffffffffu, (bl0 >> bit) & 1u);
+                if ((bl0 >> bit) & 1u) {
+                    lt |= eq & ~ones;
+                    eq &= ones;
+                } else {
+                    eq &= ~ones;
+                }
+            }
+            uint32_t lower_same = 0;   // lanes of my bucket whose record came earlier in the input
+            // every lane walks the lanes of its own bucket (one or two of them, itself included)
+            uint32_t walk = have0 ? eq : 0u;
+            while (__any_sync(0xffffffffu, walk != 0u)) {
+                const int src = walk ? __ffs(walk) - 1 : 0;
+                const uint32_t other = __shfl_sync(0xffffffffu, id0, src);
+                if (walk) {
+                    lower_same += other < id0;
+                    walk &= walk - 1u;
+                }
+            }
+            if (have0) {
+                const uint32_t rank = __popc(lt & active) + lower_same;
+                if (lower_same == 0) {
+                    nk[first_bucket + bl0] = __popc(eq);
+                    h2i[first_bucket + bl0] = (int32_t)(start + rank);
+                }
+                emit((size_t)start + rank, a0, b0);
+            }
+        } else {
+            comp[lane] = have0 ? (((unsigned long long)bl0 << 32) | id0) : ~0ull;
+            comp[32 + lane] = have1 ? (((unsigned long long)bl1 << 32) | id1) : ~0ull;
+            __syncwarp();
+            const unsigned long long c0 = comp[lane], c1 = comp[32 + lane];
+            uint32_t r0 = 0, r1 = 0, len0 = 0, len1 = 0, low0 = 0, low1 = 0;
+            for (uint32_t i = 0; i < c; i++) {
+                const unsigned long long ci = comp[i];
+                const uint32_t bi = (uint32_t)(ci >> 32);
+                r0 += ci < c0;
+                r1 += ci < c1;
+                len0 += bi == bl0;
+                len1 += bi == bl1;
+                low0 += (bi == bl0) & (ci < c0);
+                low1 += (bi == bl1) & (ci < c1);
+            }
+            if (have0) {
+                if (low0 == 0) {
+                    nk[first_bucket + bl0] = len0;
+                    h2i[first_bucket + bl0] = (int32_t)(start + r0);
+                }
+                emit((size_t)start + r0, a0, b0);
+            }
+            if (have1) {
+                if (low1 == 0) {
+                    nk[first_bucket + bl1] = len1;
+                    h2i[first_bucket + bl1] = (int32_t)(start + r1);
+                }
+                emit((size_t)start + r1, a1, b1);
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
 // (k-mer, ref_offset) pair
+// (the bucket of entry e is the key of its sort element, or, after the binned build, kmers[e] % modulo - bucket_lo)
 __global__ void freq_first_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
                                   const uint64_t *__restrict__ ref, const int32_t *__restrict__ h2i, int64_t n,
-                                  uint8_t *__restrict__ first) {
+                                  uint8_t *__restrict__ first, FastMod fm, uint32_t bucket_lo) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = h2i[elem_key(__ldg(sorted + e))];
         uint64_t km = __ldg(kmers + e);
+        int64_t s = h2i[sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo];
         uint64_t ro = ref ? __ldg(ref + e) : 0ull;
         uint8_t f = 1;
         for (int64_t c = e - 1; c >= s; c--) {
@@ -299,11 +568,11 @@ __global__ void freq_first_kernel(const unsigned long long *__restrict__ sorted,
 // pass 2: frequency[e] = number of first-flagged entries of the bucket with the same k-mer (uint16, wraps)
 __global__ void freq_count_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
                                   const int32_t *__restrict__ h2i, const uint32_t *__restrict__ nk, const uint8_t *__restrict__ first,
-                                  int64_t n, uint16_t *__restrict__ freq) {
+                                  int64_t n, uint16_t *__restrict__ freq, FastMod fm, uint32_t bucket_lo) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t b = elem_key(__ldg(sorted + e));
-        int64_t s = h2i[b], t = s + nk[b];
         uint64_t km = __ldg(kmers + e);
+        uint32_t b = sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo;
+        int64_t s = h2i[b], t = s + nk[b];
         uint32_t c = 0;
         for (int64_t a = s; a < t; a++) c += (__ldg(kmers + a) == km) & first[a];
         freq[e] = (uint16_t)c;
@@ -448,24 +717,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     GKI_TRY(o_freq.prepare(freq_out, (size_t)n * 2, s));
     GKI_TRY(o_perm.prepare(perm_out, (size_t)n * 4, s));
 
-    SortBuffers bufs;
-    const unsigned long long *sorted;
-    // (a k-mer outside [bucket_lo, bucket_hi) would wrap to a huge key; the caller routes entries by range first)
-    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, (uint32_t)bucket_lo, 0u, table_len - 1, bufs, &sorted, s));
-
     const int grid_n = grid_for(n, 256 * 4, device_info().sms * 16);
-    GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)table_len * 4, s));
-    GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)table_len * 4, s));
-    Scratch long_runs;
-    GKI_TRY(long_runs.alloc(4, s));
-    GKI_CUDA(cudaMemsetAsync(long_runs.ptr, 0, 4, s));
-    run_heads_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
-    GKI_CHECK_LAUNCH();
-    // buckets holding more than RUN_WALK entries (tiny modulo, or one heavily repeated k-mer): the tails pass exits
-    // immediately unless the heads pass flagged one
-    run_tails_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
-    GKI_CHECK_LAUNCH();
-
     // the frequency pass needs sorted k-mers (and ref offsets) even if the caller did not ask for them
     Scratch tmp_kmers, tmp_ref;
     uint64_t *kmers_sorted = o_kmers.as<uint64_t>();
@@ -478,6 +730,88 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         GKI_TRY(tmp_ref.alloc((size_t)n * 8, s));
         ref_sorted = tmp_ref.as<uint64_t>();
     }
+    const FastMod fm = make_fastmod(modulo);
+
+    // ---- binned path (see bin_finish_kernel): applies when every bin of 2^shift buckets holds at most BIN_CAP entries ----
+    bool binned = false;
+    SortBuffers bufs;
+    const unsigned long long *sorted = nullptr;
+    if (n >= (1 << 15) && !getenv("GKI_BUILD_RADIX")) {
+        BinParams bp;
+        bp.fm = fm;
+        bp.bucket_lo = (uint32_t)bucket_lo;
+        bp.table_len = table_len;
+        bp.shift = 0;   // about 16 entries per bin (one record per lane in the finish kernel), and few enough bins for their
+                        // counters to stay in L2
+        while (bp.shift < (uint32_t)BIN_MAX_SHIFT &&
+               ((((uint64_t)n << bp.shift) / table_len) < 16 || ((table_len + (1ull << bp.shift) - 1) >> bp.shift) > (8ull << 20)))
+            bp.shift++;
+        const uint64_t n_bins = (table_len + (1ull << bp.shift) - 1) >> bp.shift;
+        if (n_bins <= (8ull << 20) || bp.shift == (uint32_t)BIN_MAX_SHIFT) {
+            bp.n_bins = (uint32_t)n_bins;
+            Scratch counts, starts, cursor, maxbuf;
+            GKI_TRY(counts.alloc((size_t)(n_bins + 1) * 4, s));
+            GKI_TRY(starts.alloc((size_t)(n_bins + 1) * 4, s));
+            GKI_TRY(maxbuf.alloc(4, s));
+            GKI_CUDA(cudaMemsetAsync(counts.ptr, 0, (size_t)(n_bins + 1) * 4, s));
+            GKI_CUDA(cudaMemsetAsync(maxbuf.ptr, 0, 4, s));
+            bin_hist_kernel<<<grid_n, 256, 0, s>>>(d_kmers.as<uint64_t>(), n, bp, counts.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+            bin_max_kernel<<<grid_for((int64_t)n_bins, 256 * 4, device_info().sms * 8), 256, 0, s>>>(counts.as<uint32_t>(), bp.n_bins, maxbuf.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+            uint32_t max_bin = 0;
+            GKI_CUDA(cudaMemcpyAsync(&max_bin, maxbuf.ptr, 4, cudaMemcpyDeviceToHost, s));
+            GKI_CUDA(cudaStreamSynchronize(s));
+            if (max_bin <= (uint32_t)BIN_CAP) {
+                binned = true;
+                GKI_TRY(exclusive_scan_u32(counts.as<uint32_t>(), starts.as<uint32_t>(), (int64_t)n_bins + 1, nullptr, s));   // starts[n_bins] = n
+                GKI_TRY(cursor.alloc((size_t)n_bins * 4, s));
+                GKI_CUDA(cudaMemsetAsync(cursor.ptr, 0, (size_t)n_bins * 4, s));
+                const bool wide = ref_sorted != nullptr || o_af.dptr != nullptr;
+                Scratch records;
+                GKI_TRY(records.alloc((size_t)n * (wide ? 32 : 16), s));
+                const int finish_grid = grid_for((int64_t)n_bins, BIN_WARPS, device_info().sms * 16);
+                const bool small = max_bin <= (uint32_t)BIN_SMALL_CAP;
+                if (wide) {
+                    bin_scatter_kernel<true><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), bp,
+                                                                    starts.as<uint32_t>(), cursor.as<uint32_t>(), records.as<uint4>());
+                    GKI_CHECK_LAUNCH();
+                    if (small) bin_finish_small_kernel<true><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                                                      kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
+                    else bin_finish_kernel<true><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                                          kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
+                    GKI_CHECK_LAUNCH();
+                } else {
+                    bin_scatter_kernel<false><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), nullptr, nullptr, bp, starts.as<uint32_t>(),
+                                                                     cursor.as<uint32_t>(), records.as<uint4>());
+                    GKI_CHECK_LAUNCH();
+                    if (small) bin_finish_small_kernel<false><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                                                       kmers_sorted, o_nodes.as<uint32_t>(), nullptr, nullptr, o_perm.as<uint32_t>());
+                    else bin_finish_kernel<false><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                                           kmers_sorted, o_nodes.as<uint32_t>(), nullptr, nullptr, o_perm.as<uint32_t>());
+                    GKI_CHECK_LAUNCH();
+                }
+            }
+        }
+    }
+
+    if (!binned) {
+    // ---- radix path: stable LSD sort of (bucket << 32 | index) elements, run heads, payload gather ----
+    // (a k-mer outside [bucket_lo, bucket_hi) would wrap to a huge key; the caller routes entries by range first)
+    GKI_TRY(sort_by_bucket(d_kmers.as<uint64_t>(), n, modulo, (uint32_t)bucket_lo, 0u, table_len - 1, bufs, &sorted, s));
+
+    GKI_CUDA(cudaMemsetAsync(o_h2i.dptr, 0, (size_t)table_len * 4, s));
+    GKI_CUDA(cudaMemsetAsync(o_nk.dptr, 0, (size_t)table_len * 4, s));
+    Scratch long_runs;
+    GKI_TRY(long_runs.alloc(4, s));
+    GKI_CUDA(cudaMemsetAsync(long_runs.ptr, 0, 4, s));
+    run_heads_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
+    GKI_CHECK_LAUNCH();
+    // buckets holding more than RUN_WALK entries (tiny modulo, or one heavily repeated k-mer): the tails pass exits
+    // immediately unless the heads pass flagged one
+    run_tails_kernel<<<grid_n, 256, 0, s>>>(sorted, n, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), long_runs.as<unsigned int>());
+    GKI_CHECK_LAUNCH();
+
     const int payload_columns = (kmers_sorted != nullptr) + (o_nodes.dptr != nullptr) + (ref_sorted != nullptr) + (o_af.dptr != nullptr);
     if (payload_columns >= 2) {   // one interleaved record per entry: one random HBM fetch instead of one per column
         const bool with_ref = ref_sorted != nullptr;
@@ -500,6 +834,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
                                                      o_perm.as<uint32_t>());
         GKI_CHECK_LAUNCH();
     }
+    }
 
     if (freq_out) {
         if (!want_freq) {
@@ -507,10 +842,10 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         } else {
             Scratch first;
             GKI_TRY(first.alloc((size_t)n, s));
-            freq_first_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>());
+            freq_first_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>(), fm, (uint32_t)bucket_lo);
             GKI_CHECK_LAUNCH();
             freq_count_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), first.as<uint8_t>(), n,
-                                                     o_freq.as<uint16_t>());
+                                                     o_freq.as<uint16_t>(), fm, (uint32_t)bucket_lo);
             GKI_CHECK_LAUNCH();
         }
     }

@@ -91,6 +91,44 @@ def test_build_vs_oracle(gki, n, modulo, skip):
     assert np.all(np.diff((index._kmers % np.uint64(modulo)).astype(np.int64)) >= 0)        # sortedness
 
 
+@pytest.mark.parametrize("n,modulo,skip,dup", [(400000, 19999999, False, 20), (400000, 19999999, True, 1), (250000, 1000003, False, 6),
+                                               (100000, 65521, False, 3), (2000000, 452930477 // 8, False, 40)])
+def test_build_binned_path_vs_oracle_and_radix(gki, monkeypatch, n, modulo, skip, dup):
+    """the one-scatter binned build (bin_finish_kernel) against the oracle and against the radix path it replaces: moderate
+    repeats of a k-mer (several nodes / ref offsets), all columns, frequencies, and the permutation output"""
+    import ctypes
+    from graph_kmer_index_b200 import _lib, synthetic
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, max(n // 10, 1), 31)
+    rng = np.random.default_rng(n + dup)
+    if dup > 1:                                        # groups of up to `dup` entries share a k-mer, with 1-3 distinct ref offsets
+        hashes = hashes.copy()
+        src = (np.arange(n) // dup) * dup
+        pick = rng.random(n) < 0.3
+        hashes[pick] = hashes[src[pick]]
+        ref = (ref // np.uint64(3)).astype(np.uint64)
+    af = rng.random(n).astype(np.float32)
+    want = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=skip)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo, skip_frequencies=skip)
+    assert_index_equal(index, want)
+    # kmers + nodes only (16-byte records) and the permutation, binned vs radix
+    outs = {}
+    for mode in ("binned", "radix"):
+        if mode == "radix":
+            monkeypatch.setenv("GKI_BUILD_RADIX", "1")
+        h2i, nk = np.empty(modulo, np.int32), np.empty(modulo, np.uint32)
+        k_o, n_o, perm = np.empty(n, np.uint64), np.empty(n, np.uint32), np.empty(n, np.uint32)
+        _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, 1, _lib.ptr(h2i), _lib.ptr(nk),
+                  _lib.ptr(k_o), _lib.ptr(n_o), None, None, None, _lib.ptr(perm), None)
+        outs[mode] = (h2i, nk, k_o, n_o, perm)
+    monkeypatch.delenv("GKI_BUILD_RADIX")
+    for a, b in zip(outs["binned"], outs["radix"]):
+        assert np.array_equal(a, b)
+    h2i, nk, k_o, n_o, perm = outs["binned"]
+    assert np.array_equal(h2i, want["_hashes_to_index"]) and np.array_equal(nk, want["_n_kmers"])
+    assert np.array_equal(k_o, hashes[perm]) and np.array_equal(n_o, nodes[perm]) and np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+
+
 def test_build_dtypes_and_defaults(gki):
     """payload columns keep whatever dtype the caller had (cfki:436-440 are plain fancy-indexing)"""
     rng = np.random.default_rng(2)
