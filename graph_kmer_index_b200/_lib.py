@@ -76,6 +76,10 @@ _SIGNATURES = {
     "gki_prepare_counting": [c_vp, c_i32, c_vp],
     "gki_pack_reads": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32, c_i32],
     "gki_count_packed_reads": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp],
+    "gki_fastx_open": [ctypes.c_char_p, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)],
+    "gki_fastx_lines": [c_vp, c_vp, c_vp],
+    "gki_count_fastx": [c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(c_i64), c_vp],
+    "gki_fastx_close": [c_vp],
     "gki_reset_counts": [c_vp, c_vp],
     "gki_count_kmers": [c_vp, c_vp, c_i64, c_vp],
     "gki_count_reads": [c_vp, c_vp, c_i64, c_i32, c_i64, c_i32, c_i32, c_vp],

@@ -107,6 +107,20 @@ class DeviceIndex:
         _lib.call("gki_count_packed_reads", self.handle, _lib.ptr(packed), int(packed.shape[0]), int(read_len), k, int(both_strands),
                   _lib.current_stream())
 
+    def count_fastx(self, fastx, k, both_strands=True):
+        """Count every sequence line of a FASTA / FASTQ file (path or read_kmers.FastxFile); returns the number of k-mers looked up."""
+        import ctypes
+        from .read_kmers import FastxFile
+        own = not isinstance(fastx, FastxFile)
+        f = FastxFile(fastx) if own else fastx
+        try:
+            n_kmers = ctypes.c_int64()
+            _lib.call("gki_count_fastx", self.handle, f.handle, int(k), int(both_strands), ctypes.byref(n_kmers), _lib.current_stream())
+            return n_kmers.value
+        finally:
+            if own:
+                f.close()
+
     def node_counts(self, min_nodes=0, out=None, wrap_uint16=False):
         n_out = max(int(min_nodes), self.max_node + 1)
         if out is None:
@@ -272,6 +286,11 @@ class CounterKmerIndex:
         if not update_counter:
             self.reset()
         self.counter._device.count_reads(reads, k, both_strands)
+
+    def count_fasta(self, fasta_file_name, k, both_strands=True):
+        """the reads of ReadKmers.from_fasta_file(fasta_file_name, k) (read_kmers.py:14-27: forward, then reverse complement)
+        counted without materialising their hashes; FASTQ files work too"""
+        return self.counter._device.count_fastx(fasta_file_name, k, both_strands)
 
     def get_node_counts(self, min_nodes=0):
         """cfki:39-40: np.bincount(nodes, counter[kmers], minlength=min_nodes) -> float64."""

@@ -867,6 +867,7 @@ struct PackLane {
 // one batch handed to the lanes
 struct PackJob {
     const uint8_t *reads = nullptr;
+    const int64_t *row_offsets = nullptr;   // sequence lines of a file: row r starts at reads + row_offsets[r]
     int64_t n_reads = 0, row_stride = 0, n_units = 0;
     int32_t read_len = 0, k = 0, both = 0;
 };
@@ -909,7 +910,7 @@ int Pipeline::lane_body(int li) {
         const int t = L.tog;
         if (L.used[t]) GKI_CUDA(cudaEventSynchronize(L.done[t]));
         int64_t n_dirty = 0;
-        const int64_t clean = pack_rows(j.reads, j.row_stride, j.read_len, r0, r1, L.h_packed[t], L.h_dirty[t], nullptr, dirty_cap, &n_dirty, 0);
+        const int64_t clean = pack_rows(j.reads, j.row_stride, j.row_offsets, j.read_len, r0, r1, L.h_packed[t], L.h_dirty[t], nullptr, dirty_cap, &n_dirty, 0);
         if (n_dirty > dirty_cap) {
             std::lock_guard<std::mutex> lock(mu);
             deferred.push_back(u);
@@ -1001,8 +1002,10 @@ static int ensure_pipeline(gki_index *ix, int n_lanes, int32_t read_len) {
     return GKI_OK;
 }
 
-static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, int32_t k,
-                                     int32_t both, cudaStream_t s, int n_lanes) {
+// row_offsets != NULL: the rows are sequence lines of a mapped file (reads + row_offsets[r]); they are not dense, so only the
+// packing lanes take units and the calling thread handles what they defer.
+static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const int64_t *row_offsets, int64_t n_reads, int32_t read_len,
+                                     int64_t row_stride, int32_t k, int32_t both, cudaStream_t s, int n_lanes) {
     GKI_TRY(ensure_pipeline(ix, n_lanes, read_len));
     Pipeline *p = (Pipeline *)ix->pipeline;
     GKI_TRY(ensure_staging(ix, (size_t)ASCII_UNITS * UNIT_READS * read_len + 16));
@@ -1011,6 +1014,7 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, int64_
     {
         std::lock_guard<std::mutex> lock(p->mu);
         p->job.reads = reads;
+        p->job.row_offsets = row_offsets;
         p->job.n_reads = n_reads;
         p->job.row_stride = row_stride;
         p->job.n_units = (n_reads + UNIT_READS - 1) / UNIT_READS;
@@ -1033,7 +1037,12 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, int64_
         const int64_t r1 = r0 + n_units * UNIT_READS < n_reads ? r0 + n_units * UNIT_READS : n_reads, cnt = r1 - r0;
         if (cnt <= 0) return GKI_OK;
         if (staged[slot]) GKI_CUDA(cudaEventSynchronize(ix->done[slot]));   // paces this lane at bus speed
-        if (row_stride == read_len)
+        if (row_offsets) {   // gather the lines into a dense block first (rare: only units the lanes deferred)
+            std::vector<uint8_t> dense((size_t)cnt * read_len);
+            for (int64_t r = 0; r < cnt; r++) memcpy(dense.data() + (size_t)r * read_len, reads + row_offsets[r0 + r], (size_t)read_len);
+            GKI_CUDA(cudaMemcpyAsync(ix->stage[slot], dense.data(), dense.size(), cudaMemcpyHostToDevice, ix->copy_stream));
+            GKI_CUDA(cudaStreamSynchronize(ix->copy_stream));   // the block goes out of scope
+        } else if (row_stride == read_len)
             GKI_CUDA(cudaMemcpyAsync(ix->stage[slot], reads + r0 * row_stride, (size_t)cnt * read_len, cudaMemcpyHostToDevice, ix->copy_stream));
         else
             GKI_CUDA(cudaMemcpy2DAsync(ix->stage[slot], read_len, reads + r0 * row_stride, row_stride, read_len, cnt, cudaMemcpyHostToDevice, ix->copy_stream));
@@ -1046,7 +1055,7 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, int64_
         return GKI_OK;
     };
     int rc = GKI_OK;
-    while (rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
+    while (!row_offsets && rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
         const int64_t u = p->next.fetch_add(ASCII_UNITS);
         if (u >= p->job.n_units) break;
         rc = ascii_units(u, u + ASCII_UNITS <= p->job.n_units ? ASCII_UNITS : p->job.n_units - u);
@@ -1122,7 +1131,7 @@ int gki_count_reads(gki_index_t *ix, const uint8_t *reads, int64_t n_reads, int3
     // host reads, large batch: CPU packing lanes + the copy engine share the chunks (count_reads_host_pipeline)
     {
         const int n_lanes = default_pack_threads();
-        if (n_lanes > 0 && n_reads >= 16 * UNIT_READS) return count_reads_host_pipeline(ix, reads, n_reads, read_len, row_stride, k, both_strands, s, n_lanes);
+        if (n_lanes > 0 && n_reads >= 16 * UNIT_READS) return count_reads_host_pipeline(ix, reads, nullptr, n_reads, read_len, row_stride, k, both_strands, s, n_lanes);
     }
     // host reads, small batch: rows are compacted to dense device rows (so every full tile is one TMA bulk copy) in
     // chunks; the copy of chunk c+1 overlaps the count kernel of chunk c
@@ -1162,7 +1171,7 @@ int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int6
         const int64_t r0 = n_reads * t / T, r1 = n_reads * (t + 1) / T;
         dirty[(size_t)t].resize((size_t)(r1 - r0 < dirty_cap ? r1 - r0 : dirty_cap));
         int64_t nd = 0;
-        clean[(size_t)t] = pack_rows(reads, row_stride, read_len, r0, r1, packed + r0 * words, nullptr, dirty[(size_t)t].data(),
+        clean[(size_t)t] = pack_rows(reads, row_stride, nullptr, read_len, r0, r1, packed + r0 * words, nullptr, dirty[(size_t)t].data(),
                                      (int64_t)dirty[(size_t)t].size(), &nd, flags & GKI_PACK_FORCE_SCALAR);
         if ((size_t)nd < dirty[(size_t)t].size()) dirty[(size_t)t].resize((size_t)nd);
         dirty[(size_t)t].push_back(nd);   // last element: the slice's dirty count
@@ -1197,6 +1206,80 @@ int gki_count_packed_reads(gki_index_t *ix, const uint64_t *packed, int64_t n_re
     GKI_TRY(d.stage(packed, (size_t)n_reads * ((read_len + 31) / 32) * 8, call.stream));
     GKI_TRY(launch_count_packed_reads(ix, d.as<uint64_t>(), n_reads, read_len, k, both_strands, call.stream));
     return call.finish();
+}
+
+struct gki_fastx {
+    gki::FastxFile *file;
+};
+
+int gki_fastx_open(const char *path, gki_fastx_t **out, int64_t *n_reads, int32_t *max_len, int32_t *format) {
+    GKI_REQUIRE(path && out, GKI_ERR_INVALID, "gki_fastx_open: bad arguments");
+    std::string err;
+    FastxFile *f = fastx_open(path, 0, err);
+    GKI_REQUIRE(f != nullptr, GKI_ERR_INVALID, "gki_fastx_open: %s", err.c_str());
+    *out = new gki_fastx{f};
+    if (n_reads) *n_reads = (int64_t)f->offsets.size();
+    if (max_len) *max_len = f->max_len;
+    if (format) *format = f->format;
+    return GKI_OK;
+}
+
+int gki_fastx_lines(const gki_fastx_t *fx, int64_t *offsets, int32_t *lengths) {
+    GKI_REQUIRE(fx && fx->file, GKI_ERR_INVALID, "gki_fastx_lines: bad handle");
+    if (offsets) memcpy(offsets, fx->file->offsets.data(), fx->file->offsets.size() * 8);
+    if (lengths) memcpy(lengths, fx->file->lengths.data(), fx->file->lengths.size() * 4);
+    return GKI_OK;
+}
+
+int gki_fastx_close(gki_fastx_t *fx) {
+    if (fx) {
+        fastx_close(fx->file);
+        delete fx;
+    }
+    return GKI_OK;
+}
+
+int gki_count_fastx(gki_index_t *ix, const gki_fastx_t *fx, int32_t k, int32_t both_strands, int64_t *n_kmers, gki_stream_t stream) {
+    GKI_REQUIRE(ix && fx && fx->file, GKI_ERR_INVALID, "gki_count_fastx: bad arguments");
+    GKI_REQUIRE(k >= 1 && k <= 31, GKI_ERR_INVALID, "gki_count_fastx: k must be in [1, 31], got %d", k);
+    cudaStream_t s = (cudaStream_t)stream;
+    const FastxFile &f = *fx->file;
+    int64_t total = 0;
+    // lines grouped by length: the fused kernel walks equal-length rows; sequencing runs have one or a handful of lengths
+    std::vector<int32_t> order_len;
+    std::vector<std::vector<int64_t>> groups;
+    const bool uniform = !f.offsets.empty() && f.min_len == f.max_len;   // the usual case: the file's own offset array is the group
+    if (uniform) {
+        if (f.max_len >= k) order_len.push_back(f.max_len);
+    } else {
+        std::vector<int32_t> slot((size_t)f.max_len + 1, -1);
+        for (size_t i = 0; i < f.offsets.size(); i++) {
+            const int32_t len = f.lengths[i];
+            if (len < k) continue;   // no k-mers (read_kmers.py:67-70 on a read shorter than k is documented as a deviation)
+            if (slot[(size_t)len] < 0) {
+                slot[(size_t)len] = (int32_t)groups.size();
+                groups.emplace_back();
+                order_len.push_back(len);
+            }
+            groups[(size_t)slot[(size_t)len]].push_back(f.offsets[i]);
+        }
+    }
+    if (!order_len.empty()) GKI_TRY(ensure_table(ix, k, s));
+    const int n_lanes = default_pack_threads();
+    for (size_t g = 0; g < order_len.size(); g++) {
+        const int32_t len = order_len[g];
+        const std::vector<int64_t> &rows = uniform ? f.offsets : groups[g];
+        total += (int64_t)rows.size() * (len - k + 1) * (both_strands ? 2 : 1);
+        if (n_lanes > 0 && (int64_t)rows.size() >= 4 * UNIT_READS) {
+            GKI_TRY(count_reads_host_pipeline(ix, f.data, rows.data(), (int64_t)rows.size(), len, 0, k, both_strands, s, n_lanes));
+        } else {   // few lines of this length: a dense copy through the ordinary host path
+            std::vector<uint8_t> dense(rows.size() * (size_t)len);
+            for (size_t r = 0; r < rows.size(); r++) memcpy(dense.data() + r * (size_t)len, f.data + rows[r], (size_t)len);
+            GKI_TRY(gki_count_reads(ix, dense.data(), (int64_t)rows.size(), len, len, k, both_strands, stream));
+        }
+    }
+    if (n_kmers) *n_kmers = total;
+    return GKI_OK;
 }
 
 int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, gki_stream_t stream) {

@@ -2,6 +2,8 @@
 // Plain C++ (compiled by the host compiler, no CUDA), shared by count.cu's host-input pipeline and gki_pack_reads.
 #pragma once
 #include <cstdint>
+#include <string>
+#include <vector>
 
 namespace gki {
 
@@ -10,11 +12,28 @@ namespace gki {
 // appended to `packed`; a row with any other byte is appended to `dirty_rows` (read_len ASCII bytes, dense) when that is
 // non-NULL and its index to `dirty_index` when that is non-NULL -- the first dirty_cap of them; the rest are only counted.
 // Returns the number of clean rows; *n_dirty the others.  force_scalar != 0 selects the table-driven path (tests).
-int64_t pack_rows(const uint8_t *reads, int64_t row_stride, int32_t read_len, int64_t r0, int64_t r1, uint64_t *packed,
-                  uint8_t *dirty_rows, int64_t *dirty_index, int64_t dirty_cap, int64_t *n_dirty, int force_scalar);
+// row_offsets (may be NULL): row r starts at reads + row_offsets[r] instead of reads + r * row_stride (sequence lines of a file).
+int64_t pack_rows(const uint8_t *reads, int64_t row_stride, const int64_t *row_offsets, int32_t read_len, int64_t r0, int64_t r1,
+                  uint64_t *packed, uint8_t *dirty_rows, int64_t *dirty_index, int64_t dirty_cap, int64_t *n_dirty, int force_scalar);
 
 // "avx512" or "scalar": which implementation pack_rows dispatches to on this CPU
 const char *pack_rows_isa();
+
+// A FASTA / FASTQ file mapped into memory with the positions of its sequence lines: FASTA -- every line that does not start
+// with '>' (what read_kmers.py:16-18 treats as a read), FASTQ (first byte '@') -- the second line of every four.  Lines are
+// stripped of surrounding blanks like the reference's line.strip().
+struct FastxFile {
+    int fd = -1;
+    const uint8_t *data = nullptr;
+    size_t bytes = 0;
+    int format = 0;                 // 0 FASTA, 1 FASTQ
+    std::vector<int64_t> offsets;   // start of every sequence line
+    std::vector<int32_t> lengths;   // its length after stripping
+    int32_t max_len = 0, min_len = 0;
+};
+// NULL on failure (message in err)
+FastxFile *fastx_open(const char *path, int n_threads, std::string &err);
+void fastx_close(FastxFile *f);
 
 // number of packing threads the host-input pipeline uses: GKI_PACK_THREADS, else hardware threads - 2 (at most 30);
 // under torchrun (LOCAL_WORLD_SIZE ranks on the node) each rank takes its share of the cores minus one

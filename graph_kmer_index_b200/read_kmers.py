@@ -68,6 +68,42 @@ def pack_reads(reads, n_threads=0, force_scalar=False):
     return packed[:n_clean.value], dirty[:n_dirty.value]
 
 
+class FastxFile:
+    """A FASTA / FASTQ file mapped by libgki with its sequence lines located by the host threads (csrc/ingest.cpp): FASTA -- every
+    line not starting with '>' (what read_kmers.py:16-18 treats as a read), FASTQ -- the second line of every record."""
+
+    def __init__(self, path):
+        import ctypes
+        self.path = str(path)
+        self.handle = ctypes.c_void_p()
+        n, max_len, fmt = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.call("gki_fastx_open", self.path.encode(), ctypes.byref(self.handle), ctypes.byref(n), ctypes.byref(max_len), ctypes.byref(fmt))
+        self.n_reads, self.max_len, self.format = n.value, max_len.value, ("fasta", "fastq")[fmt.value]
+
+    def lines(self):
+        """(offsets int64, lengths int32) of the sequence lines, blanks stripped."""
+        offsets, lengths = np.empty(self.n_reads, dtype=np.int64), np.empty(self.n_reads, dtype=np.int32)
+        _lib.call("gki_fastx_lines", self.handle, _lib.ptr(offsets), _lib.ptr(lengths))
+        return offsets, lengths
+
+    def close(self):
+        if self.handle:
+            _lib.load().gki_fastx_close(self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _k_from_power_vector(power_vector):
     k = len(power_vector)
     if not np.array_equal(np.asarray(power_vector, dtype=np.uint64), power_array(k)):

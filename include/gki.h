@@ -179,6 +179,19 @@ int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int6
 int gki_count_packed_reads(gki_index_t *index, const uint64_t *packed, int64_t n_reads, int32_t read_len, int32_t k,
                            int32_t both_strands, gki_stream_t stream);
 
+/* FASTA / FASTQ in front of the packer.  gki_fastx_open maps the file and finds its sequence lines with all host threads:
+ * FASTA -- every line that does not start with '>' (exactly what ReadKmers.from_fasta_file treats as a read,
+ * read_kmers.py:16-18, multi-line records included), FASTQ (first byte '@') -- the second line of every four; lines are
+ * stripped of surrounding blanks (line.strip(), read_kmers.py:21).  gki_fastx_lines copies out the n_reads (offset, length)
+ * pairs.  gki_count_fastx counts every sequence line of at least k bases like gki_count_reads would (lines are grouped by
+ * length; large groups are packed to 2 bits straight from the mapping by the packing lanes); *n_kmers receives the number
+ * of k-mers looked up. */
+typedef struct gki_fastx gki_fastx_t;
+int gki_fastx_open(const char *path, gki_fastx_t **out, int64_t *n_reads, int32_t *max_len, int32_t *format);
+int gki_fastx_lines(const gki_fastx_t *file, int64_t *offsets, int32_t *lengths);
+int gki_count_fastx(gki_index_t *index, const gki_fastx_t *file, int32_t k, int32_t both_strands, int64_t *n_kmers, gki_stream_t stream);
+int gki_fastx_close(gki_fastx_t *file);
+
 /* cfki:39-40 CounterKmerIndex.get_node_counts: out[node] = sum over entries e with nodes[e]==node of
  * counter[kmers[e]], as float64.  n_out must be >= max(min_nodes, max_node+1); out is overwritten. */
 int gki_node_counts(gki_index_t *index, double *out, int64_t n_out, int32_t flags, gki_stream_t stream);

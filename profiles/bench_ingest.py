@@ -58,3 +58,34 @@ for lanes in (0, 1, 2, 4, 8, 12, 14):
     assert index.node_counts(n_nodes).sum() == want
     print(json.dumps(dict(stage="count_reads_host", pack_lanes=lanes, ms=best * 1e3, gkmers_per_s=R * 240 / best / 1e9,
                           ascii_gbs=R * L / best / 1e9)), flush=True)
+
+# FASTQ file in front of the packer: fixed-size records written with numpy, parsed + counted by libgki
+import tempfile
+from graph_kmer_index_b200.read_kmers import FastxFile  # noqa: E402
+rec = np.empty((R, 3 + L + 3 + L + 1), dtype=np.uint8)
+rec[:, 0:3] = np.frombuffer(b"@r\n", dtype=np.uint8)
+rec[:, 3:3 + L] = host_np
+rec[:, 3 + L:6 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+rec[:, 6 + L:6 + 2 * L] = ord("I")
+rec[:, -1] = ord("\n")
+path = os.path.join(tempfile.gettempdir(), "gki_bench.fastq")
+rec.tofile(path)
+file_gb = rec.nbytes / 1e9
+del rec
+os.environ.pop("GKI_PACK_THREADS", None)
+for _ in range(2):
+    t = time.perf_counter()
+    fx = FastxFile(path)
+    t_open = time.perf_counter() - t
+    index.reset_counts()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    n_kmers = index.count_fastx(fx, k)
+    torch.cuda.synchronize()
+    t_count = time.perf_counter() - t
+    fx.close()
+    assert index.node_counts(n_nodes).sum() == want and n_kmers == R * 240
+    print(json.dumps(dict(stage="count_fastq_file", file_gb=file_gb, open_ms=t_open * 1e3, count_ms=t_count * 1e3,
+                          gkmers_per_s_count_only=n_kmers / t_count / 1e9, gkmers_per_s_open_and_count=n_kmers / (t_open + t_count) / 1e9,
+                          file_gbs_open=file_gb / t_open)), flush=True)
+os.remove(path)

@@ -95,3 +95,47 @@ def test_host_pipeline_vs_device_path(gki, monkeypatch, threads):
     dev.count_reads(reads[sample], k)
     assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[sample], k, 1000))
     dev.close()
+
+
+@pytest.mark.parametrize("fmt", ["fasta", "fastq"])
+def test_count_fastx_vs_oracle(gki, tmp_path, fmt):
+    """FASTA / FASTQ file -> node counts: equal to counting the file's sequence lines (as read_kmers.py:16-26 would hash them)
+    with the oracle; mixed read lengths, reads shorter than k, N bases, one long group that goes through the packing lanes"""
+    from test_host_logic import _write_fastx
+    from graph_kmer_index_b200 import synthetic
+    n, k, modulo = 100000, 31, 1000003
+    idx, dev = make_index(gki, n, k, modulo)
+    rng = np.random.default_rng(9)
+    big = synthetic.reads(5 * 32768 + 100, 150, n, k, p_hit_permille=300, n_permille=3)
+    other = synthetic.reads(3000, 151, n, k, p_hit_permille=300, n_permille=3)
+    reads = [row.tobytes().decode() for row in big] + [row.tobytes().decode() for row in other]
+    reads += [row[:int(m)].tobytes().decode() for row, m in zip(other[:500], rng.choice([100, 75, 31, 30, 5], size=500))]
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    path = tmp_path / ("reads." + fmt)
+    lines = _write_fastx(path, reads, fmt, rng)
+    want = np.zeros(1000, dtype=np.float64)
+    n_kmers = 0
+    by_len = {}
+    for line in lines:
+        by_len.setdefault(len(line), []).append(line)
+    for length, group in by_len.items():
+        if length < k:
+            continue
+        mat = np.frombuffer("".join(group).encode(), dtype=np.uint8).reshape(len(group), length)
+        want += c_oracle.read_node_counts(idx, mat, k, 1000)
+        n_kmers += 2 * len(group) * (length - k + 1)
+    got_kmers = dev.count_fastx(str(path), k)
+    assert got_kmers == n_kmers
+    assert np.array_equal(dev.node_counts(1000), want)
+    # through the reference-shaped class, forward strand only
+    counter = gki.CounterKmerIndex(idx["_kmers"].astype(np.int64), idx["_nodes"], gki.collision_free_kmer_index.DeviceCounter(dev))
+    counter.reset()
+    counter.count_fasta(str(path), k, both_strands=False)
+    want_fwd = np.zeros(1000, dtype=np.float64)
+    for length, group in by_len.items():
+        if length >= k:
+            mat = np.frombuffer("".join(group).encode(), dtype=np.uint8).reshape(len(group), length)
+            want_fwd += c_oracle.read_node_counts(idx, mat, k, 1000, both_strands=False)
+    assert np.array_equal(counter.get_node_counts(1000), want_fwd)
+    dev.close()

@@ -118,3 +118,59 @@ def test_pack_reads_host_matches_numpy():
         assert np.array_equal(packed, want) and np.array_equal(dirty, np.flatnonzero(~valid))
     packed, dirty = pack_reads(np.zeros((0, 150), dtype=np.uint8))
     assert packed.shape == (0, 5) and len(dirty) == 0
+
+
+def _write_fastx(path, reads, fmt, rng):
+    """reads: list of str.  FASTA: header + one line per read, with a few multi-line records, blank-padded and CRLF lines;
+    FASTQ: four lines per record.  Returns the sequence lines the reference's line filter would see (stripped)."""
+    lines_seen = []
+    with open(path, "w", newline="") as f:
+        for i, r in enumerate(reads):
+            if fmt == "fastq":
+                f.write("@read%d some text\n%s\n+\n%s\n" % (i, r, "@" * len(r)))       # '@' in the quality line on purpose
+                lines_seen.append(r)
+            else:
+                f.write(">read%d\n" % i)
+                if i % 7 == 3 and len(r) > 20:                                            # multi-line record: two reads for the reference
+                    f.write(r[:13] + "\n" + r[13:] + "\n")
+                    lines_seen += [r[:13], r[13:]]
+                elif i % 7 == 5:
+                    f.write("  " + r + " \r\n")                                           # blanks + CRLF are stripped
+                    lines_seen.append(r)
+                else:
+                    f.write(r + "\n")
+                    lines_seen.append(r)
+        if fmt == "fasta":
+            f.write(">last\nACGTACGTAC")                                                  # no newline at the end of the file
+            lines_seen.append("ACGTACGTAC")
+    return lines_seen
+
+
+def test_fastx_line_index(tmp_path, monkeypatch):
+    """csrc/ingest.cpp fastx_open (no device needed): the sequence lines are the ones read_kmers.py:16-21 would hash; files of
+    several MB so that the byte ranges of the parsing threads cut lines at arbitrary places"""
+    from graph_kmer_index_b200.read_kmers import FastxFile
+    rng = np.random.default_rng(5)
+    alphabet = np.frombuffer(b"ACGTacgtN", dtype=np.uint8)
+    reads = [alphabet[rng.integers(0, 9, int(n))].tobytes().decode() for n in rng.choice([150, 150, 150, 151, 75, 31, 5, 1], size=40000)]
+    for fmt in ("fasta", "fastq"):
+        path = tmp_path / ("reads." + fmt)
+        want = _write_fastx(path, reads, fmt, rng)
+        data = open(path, "rb").read()
+        ref_lines = [l.strip() for l in open(path).readlines() if not l.startswith(">")] if fmt == "fasta" else want
+        assert ref_lines == want
+        for threads in ("0", "2", "6", "13"):
+            monkeypatch.setenv("GKI_PACK_THREADS", threads)
+            with FastxFile(path) as f:
+                assert f.format == fmt and f.n_reads == len(want)
+                offsets, lengths = f.lines()
+            assert [data[o:o + n].decode() for o, n in zip(offsets, lengths)] == want, (fmt, threads)
+    monkeypatch.delenv("GKI_PACK_THREADS")
+    empty = tmp_path / "empty.fa"
+    empty.write_text("")
+    with FastxFile(empty) as f:
+        assert f.n_reads == 0
+    import pytest
+    from graph_kmer_index_b200 import _lib
+    with pytest.raises(_lib.GkiError):
+        FastxFile(tmp_path / "missing.fa")
