@@ -149,3 +149,21 @@ def test_cli_subcommands(gki, tmp_path):
     run_argument_parser(["make_reference_kmer_index", "-r", str(fasta), "-n", "ref", "-k", "5", "-o", str(tmp_path / "linear")])
     lin = gki.ReferenceKmerIndex.from_file(str(tmp_path / "linear"))
     same(lin.kmers, no.read_kmer_hashes("ACGTTGCAACGGTTAACC", 5).astype(np.uint32), "linear reference")
+
+
+def test_kmer_counter_from_kmers(gki):
+    """kmer_counter.py:33-43 (np.unique(kmers, return_counts=True) behind a key -> count table)"""
+    from graph_kmer_index_b200.kmer_counter import KmerCounter
+    rng = np.random.default_rng(12)
+    kmers = rng.integers(0, 5000, 200000).astype(np.uint64) * np.uint64(1000003) + np.uint64(7)
+    kmers[:70000] = kmers[0]                                    # one k-mer more often than a uint16 holds
+    counter = KmerCounter.from_kmers(kmers, 0)
+    unique, counts = np.unique(kmers, return_counts=True)
+    assert np.array_equal(counter.counter[unique], counts)
+    assert counter.get_frequency(int(unique[3]))[0] == counts[3]
+    assert len(counter.get_frequency(12345)) == 0 and counter.counter[np.array([12345, int(unique[0])])].tolist() == [0, int(counts[0])]
+    assert counter.score_kmers([int(unique[1]), 999]) == -int(counts[1]) and counter.score_kmers([999]) == 1
+    flat = gki.FlatKmers(kmers, np.zeros(len(kmers), dtype=np.uint32))
+    sub = KmerCounter.from_flat_kmersv2(flat, 19999999, subsample_ratio=3)
+    u3, c3 = np.unique(kmers[::3], return_counts=True)
+    assert np.array_equal(sub.counter[u3], c3)
