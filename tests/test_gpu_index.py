@@ -409,3 +409,22 @@ def test_partitioned_build_emulated_on_one_gpu(gki, world):
     assert np.array_equal(cat["kmers"].view(np.uint64), want["_kmers"]) and np.array_equal(cat["nodes"].view(np.uint32), want["_nodes"])
     assert np.array_equal(cat["ref"].view(np.uint64), want["_ref_offsets"]) and np.array_equal(cat["af"], want["_allele_frequencies"])
     assert np.array_equal(cat["freq"].view(np.uint16), want["_frequencies"])
+
+
+def test_node_counts_with_more_nodes_than_l2(gki):
+    """node ids spread over 12 M (96 MB of float64 counts, more than L2 keeps): same counts as the oracle"""
+    from graph_kmer_index_b200 import synthetic
+    n, k, modulo, n_nodes = 300000, 31, 1000003, 12_000_000
+    hashes, _, ref, af = synthetic.flat_kmers(n, 1000, k)
+    rng = np.random.default_rng(8)
+    nodes = rng.integers(0, n_nodes, n).astype(np.uint32)
+    nodes[0] = n_nodes - 1
+    idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    reads = synthetic.reads(20000, 150, n, k, p_hit_permille=500, n_permille=5)
+    want = c_oracle.read_node_counts(idx, reads, k, n_nodes)
+    assert want.sum() > 0
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo)
+    dev.prepare_counting(k)
+    dev.count_reads(reads, k)
+    assert np.array_equal(dev.node_counts(n_nodes), want)
+    dev.close()
