@@ -151,7 +151,8 @@ def run_reference(args, cfg, rank):
     hashes, nodes, ref, af = synthetic.flat_kmers(n, cfg["nodes"], k, codes=codes)
     idx = c_oracle.build_index(hashes, nodes, ref, af, cfg["modulo"], skip_frequencies=True)
     del hashes, ref, af
-    sample_reads = min(cfg["reads"], 200_000)
+    sample_reads = min(cfg["reads"], 2_000_000)   # a step of ~3.5 s on 16 threads: the per-step costs over the whole index (counter reset,
+                                                    # node counts over all entries) weigh as in a full step
     reads = synthetic.reads(sample_reads, L, n, k, cfg["p_hit"], codes=codes)
     prepared = c_oracle._index_args(idx)
     nk = (L - k + 1) * 2
