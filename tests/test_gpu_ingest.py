@@ -139,3 +139,27 @@ def test_count_fastx_vs_oracle(gki, tmp_path, fmt):
             want_fwd += c_oracle.read_node_counts(idx, mat, k, 1000, both_strands=False)
     assert np.array_equal(counter.get_node_counts(1000), want_fwd)
     dev.close()
+
+
+@pytest.mark.parametrize("L,k,table_k", [(101, 21, None), (250, 31, None), (64, 16, None), (150, 31, 27)])
+def test_host_pipeline_other_shapes(gki, monkeypatch, L, k, table_k):
+    """the packing lanes with read lengths that are not a multiple of 16 / 32 bases, even k (palindromes), and a table prepared
+    for another k (every strand an independent query): equal to the device-resident path"""
+    import torch
+    from graph_kmer_index_b200 import synthetic
+    monkeypatch.setenv("GKI_PACK_THREADS", "3")
+    n, modulo = 100000, 1000003
+    idx, dev = make_index(gki, n, k, modulo, table_k)
+    n_reads = 16 * 32768 + 5
+    reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=300, n_permille=2)
+    dev.count_reads(torch.from_numpy(reads).cuda(), k)
+    want = dev.node_counts(1000)
+    assert want.sum() > 0
+    dev.reset_counts()
+    dev.count_reads(reads, k)
+    assert np.array_equal(dev.node_counts(1000), want)
+    sample = slice(0, 5000)
+    dev.reset_counts()
+    dev.count_reads(reads[sample], k)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[sample], k, 1000))
+    dev.close()
