@@ -759,6 +759,10 @@ static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t 
     int blocks_per_sm = 0;
     GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
+    if (const char *e = getenv("GKI_COUNT_CTAS")) {   // experiment knob: fewer resident CTAs per SM (occupancy sensitivity)
+        const int v = atoi(e);
+        if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v;
+    }
     int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
     count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
