@@ -5,14 +5,18 @@
 // string), kmer_hashing.py:24-65 (hash -> bases, complement, reverse complement).
 //
 // Roofline: HBM-bound on the hash writes -- per read L bytes in, 2*(L-k+1)*8 bytes out
-// (L=150,k=31: 2070 B/read = 8.625 B per emitted hash).  A k-mer is a 2k-bit window of the packed read,
-// so each lane extracts its window from shared memory with one funnel shift instead of rolling a hash;
-// the reverse-complement hash of the same window is a bit reversal (reverse_pairs(~x & valid)).
+// (L=150,k=31: 2070 B/read = 8.625 B per emitted hash).  A k-mer is a 2k-bit window of the packed read: a lane
+// extracts the first of its four consecutive windows from shared memory with one funnel shift and rolls the other
+// three; the reverse-complement hash of a window is a bit reversal (reverse_pairs(~x & valid)) and rolls the other way.
 #include "reads_tile.cuh"
 
 namespace gki {
 
 constexpr int HASH_THREADS = 256;
+
+__device__ __forceinline__ void st_global_v4_u64(uint64_t *p, uint64_t a, uint64_t b, uint64_t c, uint64_t d) {   // one 256-bit store (sm_100)
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
 
 __global__ void __launch_bounds__(HASH_THREADS) hash_reads_kernel(ReadBatch b, uint64_t *__restrict__ fwd,
                                                                   uint64_t *__restrict__ rc) {
@@ -26,6 +30,42 @@ __global__ void __launch_bounds__(HASH_THREADS) hash_reads_kernel(ReadBatch b, u
             const uint64_t *vw = t.valid + (size_t)r * b.words;
             uint64_t *of = fwd ? fwd + (r0 + r) * (int64_t)b.nk : nullptr;
             uint64_t *orc = rc ? rc + (r0 + r) * (int64_t)b.nk : nullptr;
+            // a read made only of ACGTacgt (the usual case): every lane owns four consecutive windows, extracted once and
+            // rolled three times (x >> 2 | next base on top; the reverse complement rolls the other way), and stores each
+            // strand's four hashes with one 256-bit store
+            bool ok = true;
+            for (int w = lane; w < b.words - 1; w += 32) {
+                const int nb = min(32, b.read_len - w * 32);
+                ok &= vw[w] == (nb < 32 ? ((1ull << (2 * nb)) - 1ull) : ~0ull);
+            }
+            if (__all_sync(0xffffffffu, ok)) {
+                for (int i0 = lane * 4; i0 < b.nk; i0 += 128) {
+                    uint64_t x[4], y[4];
+                    x[0] = extract_window(cw, i0, mask);
+                    const uint32_t nxt = (uint32_t)extract_window(cw, i0 + b.k, 0x3Full);
+                    y[0] = revcomp_hash(x[0], b.k);
+#pragma unroll
+                    for (int u = 1; u < 4; u++) {
+                        const uint64_t nb = (nxt >> (2 * (u - 1))) & 3u;
+                        x[u] = (x[u - 1] >> 2) | (nb << (2 * (b.k - 1)));
+                        y[u] = ((y[u - 1] << 2) | (3u - nb)) & mask;
+                    }
+                    const int n_valid = min(4, b.nk - i0);
+                    if (of) {
+                        uint64_t *p = of + i0;
+                        if (n_valid == 4 && ((uintptr_t)p & 31) == 0) st_global_v4_u64(p, x[0], x[1], x[2], x[3]);
+                        else
+                            for (int u = 0; u < n_valid; u++) p[u] = x[u];
+                    }
+                    if (orc) {   // window i of the read is window nk-1-i of the reverse-complemented read
+                        uint64_t *q = orc + (b.nk - 4 - i0);
+                        if (n_valid == 4 && ((uintptr_t)q & 31) == 0) st_global_v4_u64(q, y[3], y[2], y[1], y[0]);
+                        else
+                            for (int u = 0; u < n_valid; u++) orc[b.nk - 1 - i0 - u] = y[u];
+                    }
+                }
+                continue;
+            }
             for (int i = lane; i < b.nk; i += 32) {
                 uint64_t x = extract_window(cw, i, mask);
                 if (of) of[i] = x;
