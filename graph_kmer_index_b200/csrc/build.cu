@@ -307,28 +307,33 @@ __global__ void bin_max_kernel(const uint32_t *__restrict__ counts, uint32_t n_b
     for (int d = 16; d; d >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, d));
     if ((threadIdx.x & 31) == 0 && m) atomicMax(max_out, m);
 }
-// record = {kmer, node, index} (16 B) or, WIDE, {kmer, ref_offset | node, af, index, -} (32 B)
-template <bool WIDE>
+// record = {kmer, ref_offset, node | af << 32, input index} = 32 bytes = one sector, written with ONE 256-bit store: random
+// full-sector stores issued as one instruction run at 42 G/s on this part, twice the rate of the same bytes issued as two
+// 128-bit stores or of 16-byte records (profiles/r1/calibrate_scatter.jsonl) -- so the record is 32 bytes even when only
+// k-mers and nodes are wanted.  The bin cursors start at the bins' first slots, so the returning atomic is the position.
+struct BinRecord {
+    unsigned long long kmer, ref, node_af, index;
+};
+__device__ __forceinline__ BinRecord load_record(const BinRecord *p) {
+    BinRecord r;
+    asm("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(r.kmer), "=l"(r.ref), "=l"(r.node_af), "=l"(r.index) : "l"(p));
+    return r;
+}
 __global__ void bin_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes,
                                    const uint64_t *__restrict__ ref, const float *__restrict__ af, BinParams p,
-                                   const uint32_t *__restrict__ bin_start, uint32_t *__restrict__ cursor, uint4 *__restrict__ rec) {
+                                   uint32_t *__restrict__ cursor, BinRecord *__restrict__ rec) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t km = __ldg(kmers + i);
-        const uint32_t bin = bin_of(km, p);
-        const size_t pos = (size_t)__ldg(bin_start + bin) + atomicAdd(cursor + bin, 1u);
-        const uint32_t nd = nodes ? __ldg(nodes + i) : 0u;
-        if (WIDE) {
-            const uint64_t r = ref ? __ldg(ref + i) : 0ull;
-            rec[2 * pos] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), (uint32_t)r, (uint32_t)(r >> 32));
-            rec[2 * pos + 1] = make_uint4(nd, af ? __float_as_uint(__ldg(af + i)) : 0u, (uint32_t)i, 0u);
-        } else {
-            rec[pos] = make_uint4((uint32_t)km, (uint32_t)(km >> 32), nd, (uint32_t)i);
-        }
+        const size_t pos = atomicAdd(cursor + bin_of(km, p), 1u);
+        const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
+        const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(rec + pos), "l"((unsigned long long)km),
+                     "l"((unsigned long long)(ref ? __ldg(ref + i) : 0ull)), "l"(nd | (a << 32)), "l"((unsigned long long)i)
+                     : "memory");
     }
 }
-template <bool WIDE>
 __global__ void __launch_bounds__(BIN_WARPS * 32)
-bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uint4 *__restrict__ rec, int32_t *__restrict__ h2i,
+bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const BinRecord *__restrict__ rec, int32_t *__restrict__ h2i,
                   uint32_t *__restrict__ nk, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o, uint64_t *__restrict__ ref_o,
                   float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
     __shared__ uint32_t s_cnt[BIN_WARPS][1 << BIN_MAX_SHIFT], s_excl[BIN_WARPS][1 << BIN_MAX_SHIFT], s_idx[BIN_WARPS][BIN_CAP];
@@ -343,11 +348,10 @@ bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uin
         for (uint32_t b = lane; b < B; b += 32) cnt[b] = 0;
         __syncwarp();
         for (uint32_t j = lane; j < c; j += 32) {
-            const uint4 a = __ldg(rec + (WIDE ? 2 * (size_t)(start + j) : (size_t)(start + j)));
-            const uint64_t km = ((uint64_t)a.y << 32) | a.x;
-            const uint32_t bl = (uint32_t)((fastmod(km, p.fm) - p.bucket_lo) - first_bucket);
+            const BinRecord a = load_record(rec + start + j);
+            const uint32_t bl = (uint32_t)((fastmod(a.kmer, p.fm) - p.bucket_lo) - first_bucket);
             bucket[j] = (uint16_t)bl;
-            idx[j] = WIDE ? __ldg(rec + 2 * (size_t)(start + j) + 1).z : a.w;
+            idx[j] = (uint32_t)a.index;
             atomicAdd(cnt + bl, 1u);
         }
         __syncwarp();
@@ -401,19 +405,13 @@ bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uin
         }
         __syncwarp();
         for (uint32_t q = lane; q < c; q += 32) {
-            const size_t src = (size_t)start + order[q], dst = (size_t)start + q;
-            const uint4 a = __ldg(rec + (WIDE ? 2 * src : src));
-            if (kmers_o) kmers_o[dst] = ((uint64_t)a.y << 32) | a.x;
-            if (WIDE) {
-                const uint4 b2 = __ldg(rec + 2 * src + 1);
-                if (ref_o) ref_o[dst] = ((uint64_t)a.w << 32) | a.z;
-                if (nodes_o) nodes_o[dst] = b2.x;
-                if (af_o) af_o[dst] = __uint_as_float(b2.y);
-                if (perm_o) perm_o[dst] = b2.z;
-            } else {
-                if (nodes_o) nodes_o[dst] = a.z;
-                if (perm_o) perm_o[dst] = a.w;
-            }
+            const size_t dst = (size_t)start + q;
+            const BinRecord a = load_record(rec + start + order[q]);
+            if (kmers_o) kmers_o[dst] = a.kmer;
+            if (ref_o) ref_o[dst] = a.ref;
+            if (nodes_o) nodes_o[dst] = (uint32_t)a.node_af;
+            if (af_o) af_o[dst] = __uint_as_float((uint32_t)(a.node_af >> 32));
+            if (perm_o) perm_o[dst] = (uint32_t)a.index;
         }
         __syncwarp();
     }
@@ -425,26 +423,20 @@ bin_finish_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uin
 // registers from the single load to the final stores; both tables are zero-filled for the bin's buckets first and the run heads
 // then overwrite their entries.  Bins with 33..64 records take two records per lane and count ranks against shared memory.
 constexpr int BIN_SMALL_CAP = 64;
-template <bool WIDE>
 __global__ void __launch_bounds__(BIN_WARPS * 32)
-bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const uint4 *__restrict__ rec, int32_t *__restrict__ h2i,
+bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, const BinRecord *__restrict__ rec, int32_t *__restrict__ h2i,
                         uint32_t *__restrict__ nk, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o,
                         uint64_t *__restrict__ ref_o, float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
     __shared__ unsigned long long s_comp[BIN_WARPS][BIN_SMALL_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long *comp = s_comp[warp];
     const uint32_t B = 1u << p.shift;
-    auto emit = [&](size_t dst, const uint4 &a, const uint4 &b2) {
-        if (kmers_o) kmers_o[dst] = ((uint64_t)a.y << 32) | a.x;
-        if (WIDE) {
-            if (ref_o) ref_o[dst] = ((uint64_t)a.w << 32) | a.z;
-            if (nodes_o) nodes_o[dst] = b2.x;
-            if (af_o) af_o[dst] = __uint_as_float(b2.y);
-            if (perm_o) perm_o[dst] = b2.z;
-        } else {
-            if (nodes_o) nodes_o[dst] = a.z;
-            if (perm_o) perm_o[dst] = a.w;
-        }
+    auto emit = [&](size_t dst, const BinRecord &a) {
+        if (kmers_o) kmers_o[dst] = a.kmer;
+        if (ref_o) ref_o[dst] = a.ref;
+        if (nodes_o) nodes_o[dst] = (uint32_t)a.node_af;
+        if (af_o) af_o[dst] = __uint_as_float((uint32_t)(a.node_af >> 32));
+        if (perm_o) perm_o[dst] = (uint32_t)a.index;
     };
     for (uint32_t bin = blockIdx.x * BIN_WARPS + warp; bin < p.n_bins; bin += gridDim.x * BIN_WARPS) {
         const uint32_t start = __ldg(bin_start + bin), c = __ldg(bin_start + bin + 1) - start;
@@ -462,20 +454,18 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
                     nk[first_bucket + b] = 0u;
                 }
         }
-        uint4 a0 = make_uint4(0u, 0u, 0u, 0u), b0 = a0, a1 = a0, b1 = a0;
+        BinRecord a0{0, 0, 0, 0}, a1{0, 0, 0, 0};
         uint32_t bl0 = 0xffffu, bl1 = 0xffffu, id0 = 0, id1 = 0;
         const bool have0 = (uint32_t)lane < c, have1 = (uint32_t)lane + 32u < c;
         if (have0) {
-            a0 = __ldg(rec + (WIDE ? 2 * (size_t)(start + lane) : (size_t)(start + lane)));
-            if (WIDE) b0 = __ldg(rec + 2 * (size_t)(start + lane) + 1);
-            bl0 = (uint32_t)((fastmod(((uint64_t)a0.y << 32) | a0.x, p.fm) - p.bucket_lo) - first_bucket);
-            id0 = WIDE ? b0.z : a0.w;
+            a0 = load_record(rec + start + lane);
+            bl0 = (uint32_t)((fastmod(a0.kmer, p.fm) - p.bucket_lo) - first_bucket);
+            id0 = (uint32_t)a0.index;
         }
         if (have1) {
-            a1 = __ldg(rec + (WIDE ? 2 * (size_t)(start + 32 + lane) : (size_t)(start + 32 + lane)));
-            if (WIDE) b1 = __ldg(rec + 2 * (size_t)(start + 32 + lane) + 1);
-            bl1 = (uint32_t)((fastmod(((uint64_t)a1.y << 32) | a1.x, p.fm) - p.bucket_lo) - first_bucket);
-            id1 = WIDE ? b1.z : a1.w;
+            a1 = load_record(rec + start + 32 + lane);
+            bl1 = (uint32_t)((fastmod(a1.kmer, p.fm) - p.bucket_lo) - first_bucket);
+            id1 = (uint32_t)a1.index;
         }
         __syncwarp();   // the zero fill is ordered before the run heads' stores below
         if (c <= 32) {
@@ -508,7 +498,7 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
                     nk[first_bucket + bl0] = __popc(eq);
                     h2i[first_bucket + bl0] = (int32_t)(start + rank);
                 }
-                emit((size_t)start + rank, a0, b0);
+                emit((size_t)start + rank, a0);
             }
         } else {
             comp[lane] = have0 ? (((unsigned long long)bl0 << 32) | id0) : ~0ull;
@@ -531,14 +521,14 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
                     nk[first_bucket + bl0] = len0;
                     h2i[first_bucket + bl0] = (int32_t)(start + r0);
                 }
-                emit((size_t)start + r0, a0, b0);
+                emit((size_t)start + r0, a0);
             }
             if (have1) {
                 if (low1 == 0) {
                     nk[first_bucket + bl1] = len1;
                     h2i[first_bucket + bl1] = (int32_t)(start + r1);
                 }
-                emit((size_t)start + r1, a1, b1);
+                emit((size_t)start + r1, a1);
             }
             __syncwarp();
         }
@@ -766,31 +756,20 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
                 binned = true;
                 GKI_TRY(exclusive_scan_u32(counts.as<uint32_t>(), starts.as<uint32_t>(), (int64_t)n_bins + 1, nullptr, s));   // starts[n_bins] = n
                 GKI_TRY(cursor.alloc((size_t)n_bins * 4, s));
-                GKI_CUDA(cudaMemsetAsync(cursor.ptr, 0, (size_t)n_bins * 4, s));
-                const bool wide = ref_sorted != nullptr || o_af.dptr != nullptr;
+                GKI_CUDA(cudaMemcpyAsync(cursor.ptr, starts.ptr, (size_t)n_bins * 4, cudaMemcpyDeviceToDevice, s));
                 Scratch records;
-                GKI_TRY(records.alloc((size_t)n * (wide ? 32 : 16), s));
+                GKI_TRY(records.alloc((size_t)n * sizeof(BinRecord), s));
                 const int finish_grid = grid_for((int64_t)n_bins, BIN_WARPS, device_info().sms * 16);
-                const bool small = max_bin <= (uint32_t)BIN_SMALL_CAP;
-                if (wide) {
-                    bin_scatter_kernel<true><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), bp,
-                                                                    starts.as<uint32_t>(), cursor.as<uint32_t>(), records.as<uint4>());
-                    GKI_CHECK_LAUNCH();
-                    if (small) bin_finish_small_kernel<true><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
-                                                                                                      kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
-                    else bin_finish_kernel<true><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
-                                                                                          kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
-                    GKI_CHECK_LAUNCH();
-                } else {
-                    bin_scatter_kernel<false><<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), nullptr, nullptr, bp, starts.as<uint32_t>(),
-                                                                     cursor.as<uint32_t>(), records.as<uint4>());
-                    GKI_CHECK_LAUNCH();
-                    if (small) bin_finish_small_kernel<false><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
-                                                                                                       kmers_sorted, o_nodes.as<uint32_t>(), nullptr, nullptr, o_perm.as<uint32_t>());
-                    else bin_finish_kernel<false><<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<uint4>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
-                                                                                           kmers_sorted, o_nodes.as<uint32_t>(), nullptr, nullptr, o_perm.as<uint32_t>());
-                    GKI_CHECK_LAUNCH();
-                }
+                bin_scatter_kernel<<<grid_n, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), bp,
+                                                          cursor.as<uint32_t>(), records.as<BinRecord>());
+                GKI_CHECK_LAUNCH();
+                if (max_bin <= (uint32_t)BIN_SMALL_CAP)
+                    bin_finish_small_kernel<<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<BinRecord>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                                     kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
+                else
+                    bin_finish_kernel<<<finish_grid, BIN_WARPS * 32, 0, s>>>(bp, starts.as<uint32_t>(), records.as<BinRecord>(), o_h2i.as<int32_t>(), o_nk.as<uint32_t>(),
+                                                                               kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>());
+                GKI_CHECK_LAUNCH();
             }
         }
     }

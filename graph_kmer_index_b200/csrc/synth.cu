@@ -101,7 +101,11 @@ __global__ void scatter_store_kernel(uint4 *__restrict__ dst, uint32_t n_slots, 
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t s = gather_slot((uint32_t)i, n_slots);
         const uint4 v = make_uint4((uint32_t)i, s, 1u, 2u);
-        if (bytes == 32) {
+        if (bytes == 256) {   // one 256-bit store of a 32-byte record
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * (size_t)s), "l"((unsigned long long)v.x), "l"((unsigned long long)v.y),
+                         "l"((unsigned long long)v.z), "l"((unsigned long long)v.w)
+                         : "memory");
+        } else if (bytes == 32) {
             dst[2 * (size_t)s] = v;
             dst[2 * (size_t)s + 1] = v;
         } else if (bytes == 16) {
@@ -231,22 +235,23 @@ int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t 
 }
 
 int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms) {
-    GKI_REQUIRE(n >= 1 && n < (1ll << 31) && ms && mode >= 0 && mode <= 5 && n_bins >= 0 && n_bins < (1ll << 31), GKI_ERR_INVALID,
+    GKI_REQUIRE(n >= 1 && n < (1ll << 31) && ms && mode >= 0 && mode <= 6 && n_bins >= 0 && n_bins < (1ll << 31), GKI_ERR_INVALID,
                 "gki_calibrate_scatter: bad arguments");
-    GKI_REQUIRE(mode < 3 || n_bins >= 1, GKI_ERR_INVALID, "gki_calibrate_scatter: the atomic modes need n_bins");
+    GKI_REQUIRE(mode < 3 || mode == 6 || n_bins >= 1, GKI_ERR_INVALID, "gki_calibrate_scatter: the atomic modes need n_bins");
     uint4 *dst = nullptr;
     uint32_t *bins = nullptr, *sink = nullptr;
     const uint32_t per_bin = mode == 5 ? (uint32_t)(n / n_bins) + 1 : 0;
     const size_t dst_bytes = mode == 5 ? (size_t)n_bins * per_bin * 32 : (size_t)n * 32;
-    if (mode <= 2 || mode == 5) GKI_CUDA(cudaMalloc((void **)&dst, dst_bytes));
-    if (mode >= 3) {
+    if (mode <= 2 || mode >= 5) GKI_CUDA(cudaMalloc((void **)&dst, dst_bytes));
+    if (mode >= 3 && mode <= 5) {
         GKI_CUDA(cudaMalloc((void **)&bins, (size_t)n_bins * 4));
         GKI_CUDA(cudaMemset(bins, 0, (size_t)n_bins * 4));
     }
     GKI_CUDA(cudaMalloc((void **)&sink, 4));
     const int grid = device_info().sms * 16;
     auto run = [&]() {
-        if (mode == 0) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 32);
+        if (mode == 6) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 256);
+        else if (mode == 0) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 32);
         else if (mode == 1) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 16);
         else if (mode == 2) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 8);
         else if (mode == 3) atomic_rank_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, n, 1, sink);

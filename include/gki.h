@@ -268,7 +268,8 @@ int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t fir
 int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms);
 /* n random stores or atomics (the measurements the index-build design rests on).  mode 0/1/2: 32/16/8-byte stores to random
  * slots of an n-slot array; 3: returning atomicAdd on n_bins random counters; 4: the same without a return value; 5: returning
- * atomicAdd picks a slot inside the counter's own bin of a (n_bins x n/n_bins) array and a 32-byte record is stored there. */
+ * atomicAdd picks a slot inside the counter's own bin of a (n_bins x n/n_bins) array and a 32-byte record is stored there;
+ * 6: 32-byte records to random slots with one 256-bit store each. */
 int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms);
 int gki_calibrate_copy(int64_t bytes, float *ms);
 
