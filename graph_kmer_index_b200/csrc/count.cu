@@ -1059,7 +1059,13 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
         return GKI_OK;
     };
     int rc = GKI_OK;
-    while (!row_offsets && rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
+    // The copy engine and the packing threads read the same host memory.  With few threads (a rank's share of the cores under
+    // torchrun) the copy engine carries most of the batch; from about 12 threads on they saturate the host memory system by
+    // themselves and a concurrent ASCII transfer only takes bandwidth from them for a quarter of the effect per byte
+    // (measured, pinned input: 15.5 ms with the copy lane, 13.6 ms without; equal at 8 threads).  GKI_PIPELINE_DMA=0/1 overrides.
+    bool dma_lane = !row_offsets && n_lanes < 10;
+    if (const char *e = getenv("GKI_PIPELINE_DMA")) dma_lane = !row_offsets && atoi(e) != 0;
+    while (dma_lane && rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
         const int64_t u = p->next.fetch_add(ASCII_UNITS);
         if (u >= p->job.n_units) break;
         rc = ascii_units(u, u + ASCII_UNITS <= p->job.n_units ? ASCII_UNITS : p->job.n_units - u);

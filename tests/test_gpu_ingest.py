@@ -60,7 +60,7 @@ def test_count_packed_reads_vs_oracle(gki, monkeypatch, minimizer_filter, n, mod
     dev.close()
 
 
-@pytest.mark.parametrize("threads", ["3", "1", "0"])
+@pytest.mark.parametrize("threads", ["12", "3", "1", "0"])     # 12: packing lanes only, no copy-engine lane
 def test_host_pipeline_vs_device_path(gki, monkeypatch, threads):
     """a host batch large enough for the packing lanes: same node counts as the device-resident path and the oracle"""
     import torch
