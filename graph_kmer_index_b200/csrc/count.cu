@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <string>
@@ -896,6 +897,8 @@ struct Pipeline {
     PackJob job;
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
+    uint64_t calls = 0;              // large host batches seen; rate[d]: bytes/s of the last one run without (0) / with (1) the copy lane
+    double rate[2] = {0.0, 0.0};
     std::vector<int64_t> deferred;   // units left to the ASCII path (too many dirty reads); guarded by mu
     std::string error;               // guarded by mu
 
@@ -1059,12 +1062,21 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
         return GKI_OK;
     };
     int rc = GKI_OK;
-    // The copy engine and the packing threads read the same host memory.  With few threads (a rank's share of the cores under
-    // torchrun) the copy engine carries most of the batch; from about 12 threads on they saturate the host memory system by
-    // themselves and a concurrent ASCII transfer only takes bandwidth from them for a quarter of the effect per byte
-    // (measured, pinned input: 15.5 ms with the copy lane, 13.6 ms without; equal at 8 threads).  GKI_PIPELINE_DMA=0/1 overrides.
-    bool dma_lane = !row_offsets && n_lanes < 10;
+    // The copy engine and the packing threads read the same host memory, and whether an ASCII transfer next to the packers pays
+    // depends on the host: on the 16-thread bench box 14 packers alone are faster (13.7 ms vs 15.5 ms per 1.5 GB), on the
+    // 24-thread two-GPU box the copy lane adds 19 %.  So the pipeline tries both on its first two large calls and keeps the faster
+    // (bytes per second of the whole call), looking at the other again every 64th call.  GKI_PIPELINE_DMA=0/1 overrides.
+    bool dma_lane = !row_offsets;
+    const bool adaptive = !row_offsets && !getenv("GKI_PIPELINE_DMA");
     if (const char *e = getenv("GKI_PIPELINE_DMA")) dma_lane = !row_offsets && atoi(e) != 0;
+    if (adaptive) {
+        const uint64_t call_no = p->calls++;
+        if (call_no == 0) dma_lane = true;                                                   // first call: warm-up, not recorded
+        else if (p->rate[0] == 0.0 || p->rate[1] == 0.0) dma_lane = p->rate[1] == 0.0;       // then with, then without
+        else if (call_no % 64 == 63) dma_lane = !(p->rate[1] >= p->rate[0]);                 // a look at the losing side
+        else dma_lane = p->rate[1] >= p->rate[0];
+    }
+    const auto t_start = std::chrono::steady_clock::now();
     while (dma_lane && rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
         const int64_t u = p->next.fetch_add(ASCII_UNITS);
         if (u >= p->job.n_units) break;
@@ -1078,6 +1090,10 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
     for (size_t i = 0; rc == GKI_OK && !p->failed.load() && i < p->deferred.size(); i++) rc = ascii_units(p->deferred[i], 1);
     for (PackLane &L : p->lanes) cudaStreamSynchronize(L.stream);
     cudaStreamSynchronize(s);
+    if (adaptive && rc == GKI_OK && !p->failed.load()) {
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        if (secs > 0 && p->calls > 1) p->rate[dma_lane ? 1 : 0] = (double)n_reads * read_len / secs;
+    }
     if (rc == GKI_OK && p->failed.load()) {
         set_error("%s", p->error.empty() ? "gki_count_reads: a packing lane failed" : p->error.c_str());
         rc = GKI_ERR_CUDA;

@@ -172,8 +172,8 @@ int gki_count_reads(gki_index_t *index, const uint8_t *reads, int64_t n_reads, i
  * order; may be NULL).  packed must hold n_reads rows.  flags: GKI_PACK_FORCE_SCALAR selects the table-driven path.
  * gki_count_packed_reads: gki_count_reads for such clean packed rows (host or device pointer).
  * gki_count_reads on a large host batch uses the same packing internally: GKI_PACK_THREADS lanes (default hardware
- * threads - 2; 0 disables) pack chunks into pinned buffers; with fewer than 10 lanes the copy engine moves other chunks as
- * ASCII at the same time (GKI_PIPELINE_DMA=0/1 overrides). */
+ * threads - 2; 0 disables) pack chunks into pinned buffers; whether the copy engine moves other chunks as ASCII at the same
+ * time is decided per handle from the measured rate of the first calls (GKI_PIPELINE_DMA=0/1 overrides). */
 #define GKI_PACK_FORCE_SCALAR 1
 int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int64_t row_stride, uint64_t *packed,
                    int64_t *dirty_index, int64_t dirty_cap, int64_t *n_clean, int64_t *n_dirty, int32_t n_threads, int32_t flags);
