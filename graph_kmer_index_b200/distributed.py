@@ -156,3 +156,45 @@ def build_index_partitioned(hashes, nodes, ref_offsets, allele_frequencies, modu
         pos += totals[r]
     full.update(bucket_range=(0, int(modulo)), position_offset=0, n_total=n_total)
     return full
+
+
+def critical_path_chunks(n_paths, n_chunks):
+    """(start, end) chunks of the critical paths exactly as `graph_kmer_index index -t T` cuts them
+    (command_line_interface.py:588-603: n_paths // n_chunks paths per chunk, the remainder in further chunks)."""
+    n_chunks = max(1, min(int(n_chunks), int(n_paths)))
+    per = n_paths // n_chunks
+    starts = list(range(0, n_paths, per))
+    ends = starts[1:] + [n_paths]
+    return list(zip(starts, ends))
+
+
+def find_kmers_sharded(graph, k, critical_graph_paths=None, n_chunks=None, rank=None, world_size=None, gather=True, **finder_kwargs):
+    """DenseKmerFinder over all critical paths, chunked as the reference's multi-process `index` command does
+    (command_line_interface.py:575-617) with the chunks dealt round-robin to the ranks (one process per GPU; the graph is
+    replicated).  Every chunk is an independent DenseKmerFinder run with start/stop_at_critical_path_number; the result is the
+    chunks' FlatKmers concatenated in chunk order (FlatKmers.from_multiple_flat_kmers, cli:608) -- identical to what the
+    reference produces for the same n_chunks.  With gather=False every rank returns only its own chunks [(chunk_no, FlatKmers)]."""
+    import torch.distributed as dist
+    from .flat_kmers import FlatKmers
+    from .kmer_finder import CriticalGraphPaths, DenseKmerFinder, graph_arrays
+    if rank is None:
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        world_size = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    arrays = graph_arrays(graph)
+    if critical_graph_paths is None:
+        critical_graph_paths = CriticalGraphPaths.from_graph(arrays, k)
+    chunks = critical_path_chunks(len(critical_graph_paths), n_chunks if n_chunks is not None else world_size * 20)
+    mine = []
+    for c in range(rank, len(chunks), world_size):
+        finder = DenseKmerFinder(arrays, k, critical_graph_paths=critical_graph_paths, start_at_critical_path_number=chunks[c][0],
+                                 stop_at_critical_path_number=chunks[c][1], **finder_kwargs)
+        finder.find()
+        mine.append((c, finder.get_flat_kmers(v="0")))
+    if not gather:
+        return mine
+    if world_size > 1:
+        everyone = [None] * world_size
+        dist.all_gather_object(everyone, mine)
+        mine = [item for part in everyone for item in part]
+    mine.sort(key=lambda item: item[0])
+    return FlatKmers.from_multiple_flat_kmers([flat for _, flat in mine])

@@ -84,3 +84,45 @@ def test_random_graphs_vs_oracle(seed, n_variants, spacing, k, kw):
     assert len(want["kmers"]) > 1000
     for key in KEYS:
         assert np.array_equal(finder._results[key], want[key]), (key, len(finder._results[key]), len(want[key]))
+
+
+def load_chunk_case(g, i):
+    p = "c%d_" % i
+    arrays = {key[len(p) + 2:]: g[key] for key in g.files if key.startswith(p + "g_")}
+    chunks = [tuple(int(x) for x in row) for row in g[p + "chunks"]]
+    results = [{key: g[p + "r%d_%s" % (j, key)] for key in KEYS} for j in range(len(chunks))]
+    return arrays, int(g[p + "k"]), int(g[p + "max_variant_nodes"]), (g[p + "crit_nodes"], g[p + "crit_offsets"]), chunks, results
+
+
+def test_chunked_runs_match_the_reference():
+    """start/stop_at_critical_path_number (kf:186-226) per chunk of critical paths, the way `graph_kmer_index index -t T` runs the
+    finder (cli:588-608): ordered equality with the unmodified reference for every chunk (tests/golden/finder_chunks.npz), and the
+    sharded helper returns the chunks concatenated in order whatever rank computed them"""
+    import graph_kmer_index_b200 as gki
+    from graph_kmer_index_b200 import distributed
+    g = load_golden("finder_chunks")
+    assert int(g["n_cases"]) >= 20
+    for i in range(int(g["n_cases"])):
+        arrays, k, mvn, (cn, co), chunks, results = load_chunk_case(g, i)
+        crit = gki.CriticalGraphPaths(cn, co)
+        requested = [n for n in (2, 3, 5) if distributed.critical_path_chunks(len(crit), n) == chunks]
+        assert requested, (i, chunks)                        # the helper cuts chunks like cli:588-603 (the fixture's own cutter)
+        for (s, e), ref in zip(chunks, results):
+            finder = gki.DenseKmerFinder(arrays, k, critical_graph_paths=gki.CriticalGraphPaths(cn, co), max_variant_nodes=mvn,
+                                         start_at_critical_path_number=s, stop_at_critical_path_number=e)
+            finder.find()
+            for key in KEYS:
+                assert np.array_equal(finder._results[key], ref[key]), (i, (s, e), key)
+        # two emulated ranks, chunks dealt round-robin, gathered by hand
+        n_chunks = requested[0]
+        parts = []
+        for rank in range(2):
+            parts += distributed.find_kmers_sharded(arrays, k, critical_graph_paths=gki.CriticalGraphPaths(cn, co), n_chunks=n_chunks, rank=rank,
+                                                    world_size=2, gather=False, max_variant_nodes=mvn)
+        parts.sort(key=lambda item: item[0])
+        assert [c for c, _ in parts] == list(range(len(chunks)))
+        assert np.array_equal(np.concatenate([np.asarray(f._hashes) for _, f in parts]).astype(np.int64), np.concatenate([r["kmers"] for r in results]))
+        assert np.array_equal(np.concatenate([f._nodes for _, f in parts]), np.concatenate([r["nodes"] for r in results]))
+        whole = distributed.find_kmers_sharded(arrays, k, critical_graph_paths=gki.CriticalGraphPaths(cn, co), n_chunks=n_chunks, rank=0, world_size=1,
+                                               max_variant_nodes=mvn)
+        assert len(whole._hashes) == sum(len(f._hashes) for _, f in parts)

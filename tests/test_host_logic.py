@@ -174,3 +174,18 @@ def test_fastx_line_index(tmp_path, monkeypatch):
     from graph_kmer_index_b200 import _lib
     with pytest.raises(_lib.GkiError):
         FastxFile(tmp_path / "missing.fa")
+
+
+def test_critical_path_chunks_like_the_reference_cli():
+    """command_line_interface.py:588-603: n_paths // n_chunks paths per chunk, the remainder in further chunks"""
+    def reference(n_paths, n_chunks):
+        if n_chunks >= n_paths:
+            n_chunks = n_paths
+        per = n_paths // n_chunks
+        starts = list(range(0, n_paths, per))
+        return list(zip(starts, starts[1:] + [n_paths]))
+    for n_paths in (1, 2, 7, 9, 40, 1001):
+        for n_chunks in (1, 2, 3, 5, 20, 160, 5000):
+            chunks = distributed.critical_path_chunks(n_paths, n_chunks)
+            assert chunks == reference(n_paths, n_chunks)
+            assert chunks[0][0] == 0 and chunks[-1][1] == n_paths and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
