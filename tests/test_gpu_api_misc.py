@@ -1,0 +1,83 @@
+"""The smaller methods of the hot-path classes against outputs of the unmodified reference (tests/golden/api_misc.npz from
+make_golden_api.py): get_grouped_nodes, get_frequency, the max_hits gate of get, set_frequencies_using_other_index,
+FlatKmers.sum_of_kmer_frequencies / maximum_kmer_frequency, kmer_hashes_to_complement_bases, ReadKmers.from_list_of_string_kmers,
+convert_kmers_to_complement (against the oracle: the reference's own chunking fails below 10 M k-mers, cfki:473)."""
+import numpy as np
+import pytest
+
+from conftest import golden_index, load_golden
+from oracle import numpy_oracle as no
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gki():
+    import graph_kmer_index_b200 as g
+    return g
+
+
+@pytest.fixture(scope="module")
+def index(gki):
+    g = load_golden("index_small")
+    flat = gki.FlatKmers(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"])
+    return gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=int(g["stable_modulo"])), flat, int(g["k"])
+
+
+def test_frequency_and_grouped_nodes(gki, index):
+    idx, flat, k = index
+    a = load_golden("api_misc")
+    sizes, nodes = a["grouped_sizes"], a["grouped_nodes"]
+    s_at = n_at = 0
+    for i, q in enumerate(a["queries"]):
+        assert idx.get_frequency(int(q), include_reverse_complement=True, k=k) == a["freq_rc"][i]
+        assert idx.get_frequency(int(q), include_reverse_complement=False, k=k) == a["freq_fwd"][i]
+        assert (idx.get(int(q), max_hits=1)[0] is None) == bool(a["get_max_hits_1_is_none"][i])
+        groups = idx.get_grouped_nodes(int(q), max_hits=10 ** 9)
+        assert (groups is None) == bool(a["grouped_none"][i])
+        n_groups = int(a["grouped_n_groups"][i])
+        if groups is not None:
+            assert [len(x) for x in groups] == sizes[s_at:s_at + n_groups].tolist()
+            got = np.concatenate([np.sort(np.asarray(x)) for x in groups])
+            assert np.array_equal(got, nodes[n_at:n_at + len(got)])
+            n_at += len(got)
+        s_at += n_groups
+    small = gki.FlatKmers(flat._hashes[:200], flat._nodes[:200], flat._ref_offsets[:200], flat._allele_frequencies[:200])
+    assert small.sum_of_kmer_frequencies(idx) == int(a["sum_of_kmer_frequencies"])
+    assert small.maximum_kmer_frequency(idx) == int(a["maximum_kmer_frequency"])
+
+
+def test_set_frequencies_using_other_index(gki, index):
+    idx, _, _ = index
+    a = load_golden("api_misc")
+    target = idx.copy()
+    target._frequencies = target._frequencies.copy()
+    target.set_frequencies_using_other_index(idx.copy(), multiplier=3, min_frequency=2)
+    assert target._frequencies.dtype == a["set_from_other"].dtype and np.array_equal(target._frequencies, a["set_from_other"])
+    removed = idx.copy()
+    removed.remove_ref_offsets()
+    removed.remove_frequencies()
+    assert removed._ref_offsets.tolist() == [0] and removed._frequencies.tolist() == [0]       # cfki:246-250
+    before = removed._allele_frequencies.copy()
+    removed.set_allele_frequencies(np.arange(3))                                               # a no-op in the reference (cfki:234-235)
+    assert np.array_equal(removed._allele_frequencies, before)
+
+
+def test_complement_bases_and_string_kmers(gki, index):
+    _, _, k = index
+    from graph_kmer_index_b200.kmer_hashing import kmer_hashes_to_complement_bases
+    a = load_golden("api_misc")
+    got = kmer_hashes_to_complement_bases(a["queries"][:25], k)
+    assert got.dtype == a["complement_bases"].dtype and np.array_equal(got, a["complement_bases"])
+    rk = gki.ReadKmers.from_list_of_string_kmers([["ACGTA", "ttgca", "NACGT"], ["GGGGG"], []])
+    assert [len(read) for read in rk.kmers] == a["string_kmers_per_read"].tolist()
+    assert [int(h) for read in rk.kmers for h in read] == a["string_kmers"].tolist()
+
+
+def test_convert_kmers_to_complement(gki, index):
+    idx, _, k = index
+    comp = idx.convert_kmers_to_complement(k=k)
+    want = no.build_index(no.complement_hashes(idx._kmers, k), idx._nodes, idx._ref_offsets, idx._allele_frequencies, int(idx._modulo),
+                          skip_frequencies=True)
+    for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_allele_frequencies", "_frequencies"):
+        assert np.array_equal(getattr(comp, key), want[key]), key
