@@ -982,17 +982,7 @@ static void destroy_pipeline(gki_index *ix) {
     ix->pipeline = nullptr;
 }
 
-static int ensure_pipeline(gki_index *ix, int n_lanes, int32_t read_len) {
-    Pipeline *p = (Pipeline *)ix->pipeline;
-    if (p && p->n_lanes == n_lanes && p->read_len == read_len) return GKI_OK;
-    destroy_pipeline(ix);
-    p = new Pipeline();
-    ix->pipeline = p;
-    p->ix = ix;
-    p->n_lanes = n_lanes;
-    p->read_len = read_len;
-    p->dirty_cap = UNIT_READS / 16 + 1;
-    p->lanes.resize((size_t)n_lanes);
+static int allocate_pipeline(Pipeline *p, int32_t read_len) {
     const size_t words = (size_t)(read_len + 31) / 32;
     GKI_CUDA(cudaEventCreateWithFlags(&p->start, cudaEventDisableTiming));
     for (PackLane &L : p->lanes) {
@@ -1004,6 +994,25 @@ static int ensure_pipeline(gki_index *ix, int n_lanes, int32_t read_len) {
             GKI_CUDA(cudaMalloc((void **)&L.d_packed[j], (size_t)UNIT_READS * words * 8 + 16));
             GKI_CUDA(cudaMalloc((void **)&L.d_dirty[j], (size_t)p->dirty_cap * read_len + 16));
         }
+    }
+    return GKI_OK;
+}
+
+static int ensure_pipeline(gki_index *ix, int n_lanes, int32_t read_len) {
+    Pipeline *p = (Pipeline *)ix->pipeline;
+    if (p && p->n_lanes == n_lanes && p->read_len == read_len) return GKI_OK;
+    destroy_pipeline(ix);
+    p = new Pipeline();
+    ix->pipeline = p;
+    p->ix = ix;
+    p->n_lanes = n_lanes;
+    p->read_len = read_len;
+    p->dirty_cap = UNIT_READS / 16 + 1;
+    p->lanes.resize((size_t)n_lanes);
+    const int rc = allocate_pipeline(p, read_len);
+    if (rc != GKI_OK) {   // a half-built pipeline has no worker threads: never leave it behind
+        destroy_pipeline(ix);
+        return rc;
     }
     for (int i = 0; i < n_lanes; i++) p->threads.emplace_back(&Pipeline::worker, p, i);
     return GKI_OK;
