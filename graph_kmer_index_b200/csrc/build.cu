@@ -3,15 +3,19 @@
 // Reference: collision_free_kmer_index.py:422-467 (from_flat_kmers) and :267-293 (set_frequencies):
 //   hashes = kmers % modulo; sorting = argsort(hashes); gather 5 columns; run heads -> hashes_to_index,
 //   run lengths -> n_kmers; frequencies = #distinct ref_offsets per k-mer.
-// Here: (bucket key << 32 | index) elements -> STABLE LSD radix sort, up to 10 bits per pass, only as many
-// passes as modulo-1 has bits (3 at the default modulo) -> run heads / tails written straight into the zeroed dense tables ->
-// one fused gather of the payload columns through the permutation -> frequencies by bucket-local scans.
-// The sort is stable so the payload order inside a bucket is the input order (the canonical order of
-// SURVEY.md section 8c(ii)); numpy's default argsort is not stable, so the reference's own payload order is
-// only defined up to a permutation inside each bucket.
+// Two paths, same result (the canonical order of SURVEY.md section 8c(ii): inside a bucket the entries keep their input
+// order; numpy's default argsort is not stable, so the reference's own payload order is only defined up to a permutation
+// inside each bucket):
+//   * binned (the usual case, see bin_finish_small_kernel): bins of consecutive buckets -> histogram + scan -> ONE scatter of
+//     whole 32-byte records, each with one 256-bit store -> per-bin ordering by (bucket, input index) in registers -> payload
+//     columns and both dense tables streamed out.  24 (in) + 32 (records out) + 32 (records in) + 24 (out) bytes per entry
+//     + 8 * modulo for the tables.
+//   * radix (fallback for skewed inputs, and the machinery behind gki_group_by_key / gki_partition_by_bucket_range):
+//     (bucket key << 32 | index) elements -> stable LSD radix sort, up to 10 bits per pass (3 passes at the default modulo)
+//     -> run heads / tails into the zeroed dense tables -> one gather of interleaved payload records through the permutation.
+// Frequencies (cfki:267-293) are bucket-local scans over the sorted columns on both paths.
 //
-// Roofline: HBM streaming.  Compulsory traffic 50*N + 8*modulo bytes; this implementation moves
-// 16 (elements) + P*(8 hist + 16 scatter) + 8 (tables) + ~24 gather-in (sector-amplified) + 24 out per entry.
+// Roofline: HBM streaming, compulsory traffic 50*N + 8*modulo bytes.
 #include "common.cuh"
 
 namespace gki {

@@ -4,23 +4,26 @@
 // The reference keeps one counter per distinct index k-mer (npstructures.Counter keyed by k-mer, cfki:27) and
 // get_node_counts = bincount(nodes, weights=counter[kmers]) (cfki:39-40).  The counts only depend on k-mer
 // equality, so the device is free to key the counters however it likes.  Measured on B200 (profiles/r1):
-// random 8-byte gathers run at ~217 G/s while the table fits L2 (<= 48 MB) and at ~37 G/s from HBM (>= 4 GB
-// tables, 64-byte fetch granularity); the first version of this kernel, which probed the reference's
-// modulo-bucket tables behind a 56 MB bucket bitmap, was bound by exactly those two rates (132 GB of DRAM reads
-// per 2.4 G queries).  Hence this layout:
+// random 8-byte gathers run at ~290 G/s while the table fits L2 (L1TEX-bound, one sector request per clock per SM)
+// and at ~37 G/s from HBM, each HBM access filling a whole 128-byte line; the first version of this kernel, which
+// probed the reference's modulo-bucket tables behind a 56 MB bucket bitmap, was bound by exactly those rates
+// (132 GB of DRAM reads per 2.4 G queries).  Hence this layout:
 //
-//   * Bloom filter, register-blocked (one 32-bit word per key, filter_k bits), sized <= 48 MB so it stays in
-//     L2: one L2 access decides most absent k-mers.
-//   * bucketised open-addressing table over the distinct k-mers: bucket = key[4] | cnt[4][2] = one 64-byte line; a
-//     probe reads the four keys with ONE 256-bit load (one 32-byte sector from HBM), a hit adds one RED on the other half.
+//   * Bloom filter, register-blocked (one 32-bit word per key, filter_k bits), 32 MB so it stays in L2: one L2
+//     access decides most absent k-mers.  Filters of indexes too large for that live in HBM and are addressed by
+//     the k-mer's minimizer, so that consecutive windows of a read share a line (filter_m, kmer_minimizer).
+//   * bucketised open-addressing table over the distinct k-mers: bucket = key[4] | cnt[4][2] = 64 bytes, two buckets
+//     per 128-byte line (a full bucket overflows into its line mate first); a probe reads the four keys with ONE
+//     256-bit load, a hit adds one RED on the other half of the bucket.
 //   * canonical keys: key = min(x, revcomp_k(x)), cnt[o] with o = (x != key).  The forward and reverse-complement
 //     hashes of a read position share the key, so a position (2 queries) costs one filter access, at most one
 //     table access and one 64-bit RED (+1 on both orientations).
 //   * multiply-fold hash + multiply-high range reduction: no 64-bit modulo in the hot loop.
 //
 // The fused kernel is warp-autonomous: every warp streams its own tiles of reads into shared memory with TMA
-// bulk copies (double-buffered on per-warp mbarriers), packs them to 2 bits per base and walks them with a
+// bulk copies on its own mbarrier, packs them to 2 bits per base (or receives them packed) and walks them with a
 // rolling window -- no CTA-wide barrier anywhere, so a warp that waits on HBM never stalls its neighbours.
+// Host batches reach it through the packing lanes at the end of this file (count_reads_host_pipeline).
 #include <stdlib.h>
 
 #include <atomic>
