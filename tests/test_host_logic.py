@@ -189,3 +189,21 @@ def test_critical_path_chunks_like_the_reference_cli():
             chunks = distributed.critical_path_chunks(n_paths, n_chunks)
             assert chunks == reference(n_paths, n_chunks)
             assert chunks[0][0] == 0 and chunks[-1][1] == n_paths and all(a[1] == b[0] for a, b in zip(chunks, chunks[1:]))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (no GPU needed): one JSON line with the contract's keys, the oracle port on the host cores"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "2", "--warmup", "1"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "kmers/s" and d["value"] > 0 and d["vs_baseline"] is None
+    assert d["steps"] == 2 and d["warmup"] == 1 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
