@@ -290,9 +290,71 @@ __global__ void table_reset_kernel(Bucket *__restrict__ buckets, size_t n_bucket
 }
 
 // ------------------------------------------------------------------ counting kernels
+// CounterKmerIndex.count_kmers (cfki:33-37) on an array of hashes.  Same scheme as the fused kernel: a warp takes 4 x 32
+// queries at a time (coalesced loads, four filter words in flight per lane), the few that pass the filter are compacted into a
+// per-warp queue by ballot and the table is probed 32 survivors at a time -- a thread per query with the probe inline leaves
+// most of a warp waiting on HBM for the one lane in six that has a survivor (94 G queries/s; this form: see DESIGN.md).
+constexpr int CK_U = 4;       // queries per lane and round
+constexpr int CK_QCAP = 64;   // survivor queue capacity per warp
 __global__ void __launch_bounds__(COUNT_THREADS) count_kmers_kernel(TableView t, const uint64_t *__restrict__ queries, int64_t nq) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
-        count_one(t, __ldg(queries + i));
+    __shared__ unsigned long long s_key[COUNT_WARPS][CK_QCAP];
+    __shared__ uint32_t s_meta[COUNT_WARPS][CK_QCAP];   // home bucket | orientation << 31
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *qkey = s_key[warp];
+    uint32_t *qmeta = s_meta[warp];
+    uint32_t qn = 0, qhead = 0;
+    auto probe_queue = [&](uint32_t n) {
+        if ((uint32_t)lane < n) {
+            const uint32_t idx = (qhead + lane) & (CK_QCAP - 1);
+            const uint32_t meta = qmeta[idx];
+            uint32_t *cnt = find_slot_from(t, qkey[idx], meta & 0x7fffffffu);
+            if (cnt) atomicAdd(cnt + (meta >> 31), 1u);
+        }
+        qhead += n;
+        __syncwarp();
+    };
+    const int64_t round = 32 * CK_U;
+    const int64_t n_rounds = (nq + round - 1) / round;
+    const uint32_t below = (1u << lane) - 1u;
+    for (int64_t r = (int64_t)blockIdx.x * COUNT_WARPS + warp; r < n_rounds; r += (int64_t)gridDim.x * COUNT_WARPS) {
+        Key key[CK_U];
+        uint32_t home[CK_U], fw[CK_U], fm[CK_U];
+        uint32_t live = 0;
+#pragma unroll
+        for (int u = 0; u < CK_U; u++) {
+            const int64_t i = r * round + u * 32 + lane;
+            key[u] = make_key(i < nq ? __ldg(queries + i) : 0ull, t.k);
+            bool ok = i < nq && key[u].ok;
+            if (ok && key[u].c == SLOT_EMPTY) {   // raw mode only: the one value that collides with the empty marker
+                count_one(t, key[u].c);
+                ok = false;
+            }
+            const Hash h = hash_key(key[u].c);
+            home[u] = home_bucket(t, h);
+            fm[u] = filter_mask(t, h);
+            fw[u] = (t.filter && ok) ? __ldg(t.filter + filter_word_of(t, h, key[u].c)) : 0xffffffffu;
+            live |= (uint32_t)ok << u;
+        }
+#pragma unroll
+        for (int u = 0; u < CK_U; u++) live &= ~((uint32_t)((fw[u] & fm[u]) != fm[u]) << u);
+#pragma unroll
+        for (int u = 0; u < CK_U; u++) {
+            const bool mine = (live >> u) & 1u;
+            const uint32_t votes = __ballot_sync(0xffffffffu, mine);
+            if (mine) {
+                const uint32_t slot_idx = (qn + __popc(votes & below)) & (CK_QCAP - 1);
+                qkey[slot_idx] = key[u].c;
+                qmeta[slot_idx] = home[u] | (key[u].o << 31);
+            }
+            qn += __popc(votes);
+            if (qn - qhead >= 32) {
+                __syncwarp();
+                probe_queue(32);
+            }
+        }
+    }
+    __syncwarp();
+    if (qn != qhead) probe_queue(qn - qhead);
 }
 
 // ---- fused K1 -> K3, warp-autonomous ----
@@ -743,7 +805,7 @@ static int ensure_staging(gki_index *ix, size_t bytes) {
 
 static int launch_count_kmers(gki_index *ix, const uint64_t *dq, int64_t nq, cudaStream_t s) {
     if (nq <= 0) return GKI_OK;
-    int grid = grid_for(nq, COUNT_THREADS * 4, device_info().sms * 8);
+    int grid = grid_for((nq + 32 * CK_U - 1) / (32 * CK_U), COUNT_WARPS, device_info().sms * 8);
     count_kmers_kernel<<<grid, COUNT_THREADS, 0, s>>>(ix->table, dq, nq);
     GKI_CHECK_LAUNCH();
     return GKI_OK;
