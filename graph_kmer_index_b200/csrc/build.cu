@@ -446,7 +446,7 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
         const uint32_t start = __ldg(bin_start + bin), c = __ldg(bin_start + bin + 1) - start;
         const uint64_t first_bucket = (uint64_t)bin << p.shift;
         // zero both tables over the bin's buckets (cfki:451-452: np.zeros)
-        if (B >= 4 && first_bucket + B <= p.table_len) {
+        if (B >= 4 && first_bucket + B <= p.table_len && (((uintptr_t)h2i | (uintptr_t)nk) & 15) == 0) {   // caller's tables may be views
             for (uint32_t q = lane; q < B / 4; q += 32) {
                 ((uint4 *)(h2i + first_bucket))[q] = make_uint4(0u, 0u, 0u, 0u);
                 ((uint4 *)(nk + first_bucket))[q] = make_uint4(0u, 0u, 0u, 0u);

@@ -428,3 +428,29 @@ def test_node_counts_with_more_nodes_than_l2(gki):
     dev.count_reads(reads, k)
     assert np.array_equal(dev.node_counts(n_nodes), want)
     dev.close()
+
+
+def test_build_into_unaligned_table_views(gki):
+    """the dense tables handed to gki_index_build may be views that start on any 4-byte boundary (a rank's slice of a larger
+    tensor): same result as into fresh arrays"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    n, modulo = 200000, 1000003
+    hashes, nodes, _, _ = synthetic.flat_kmers(n, 1000, 31)
+    d_h, d_n = torch.from_numpy(hashes.view(np.int64)).cuda(), torch.from_numpy(nodes.view(np.int32)).cuda()
+    outs = []
+    for shift in (0, 1, 3):
+        big_h = torch.full((modulo + 8,), -7, dtype=torch.int32, device="cuda")
+        big_n = torch.full((modulo + 8,), -7, dtype=torch.int32, device="cuda")
+        h2i, nk = big_h[shift:shift + modulo], big_n[shift:shift + modulo]
+        k_o, n_o = torch.empty_like(d_h), torch.empty_like(d_n)
+        _lib.call("gki_index_build", _lib.ptr(d_h), _lib.ptr(d_n), None, None, n, modulo, 1, h2i.data_ptr(), nk.data_ptr(),
+                  _lib.ptr(k_o), _lib.ptr(n_o), None, None, None, None, None)
+        torch.cuda.synchronize()
+        assert int(big_h[:shift].eq(-7).all()) and int(big_h[shift + modulo:].eq(-7).all())      # nothing written outside the view
+        outs.append((h2i.cpu().numpy().copy(), nk.cpu().numpy().copy(), k_o.cpu().numpy(), n_o.cpu().numpy()))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
+    want = c_oracle.build_index(hashes, nodes, np.zeros(n, np.uint64), np.ones(n, np.float32), modulo, skip_frequencies=True)
+    assert np.array_equal(outs[0][0], want["_hashes_to_index"]) and np.array_equal(outs[0][1].view(np.uint32), want["_n_kmers"])
