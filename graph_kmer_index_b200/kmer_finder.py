@@ -5,7 +5,8 @@ The graph argument is an obgraph.Graph-like object.  The finder needs it as flat
 (`graph_arrays`): objects that offer ``to_arrays()`` are used directly, anything else is converted through the same
 methods the reference calls (kf:50,62,138,143,259,279,350,374,384; cgp:46-95).
 
-Not supported (raise NotImplementedError): ``whitelist`` and ``only_follow_nodes`` (kf:129-131, 385-388)."""
+``whitelist`` (kf:95-104, 130-132, 362-365) only decides which rows are stored, never the walk, so it is applied to the rows
+the device returns.  Not supported (raises NotImplementedError): ``only_follow_nodes`` (kf:385-388), which redirects the walk."""
 import ctypes
 import logging
 
@@ -100,8 +101,9 @@ class DenseKmerFinder:
     def __init__(self, graph, k, critical_graph_paths=None, position_id=None, only_save_one_node_per_kmer=False, max_variant_nodes=4,
                  only_store_variant_nodes=False, start_at_critical_path_number=None, stop_at_critical_path_number=None, whitelist=None,
                  only_store_nodes=None, only_follow_nodes=None):
-        if whitelist is not None or only_follow_nodes is not None:
-            raise NotImplementedError("whitelist / only_follow_nodes are not supported by the device finder")
+        if only_follow_nodes is not None:
+            raise NotImplementedError("only_follow_nodes is not supported by the device finder")
+        self._whitelist = None if whitelist is None else np.fromiter((int(x) for x in whitelist), dtype=np.int64)
         assert 1 <= k <= 31
         self._graph = graph
         self._arrays = graph_arrays(graph)
@@ -169,6 +171,9 @@ class DenseKmerFinder:
                           _lib.ptr(out["start_offsets"]), _lib.ptr(out["allele_frequencies"]), _lib.current_stream())
         finally:
             _lib.load().gki_finder_destroy(handle)
+        if self._whitelist is not None:              # kf:130-132, 362-365: rows of other k-mers are not stored
+            keep = np.isin(out["kmers"], self._whitelist)
+            out = {key: v[keep] for key, v in out.items()}
         # results accumulate over calls like the reference's NpLists do
         self._results = {key: np.concatenate([self._results[key], out[key]]) for key in out}
 

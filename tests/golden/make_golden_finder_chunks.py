@@ -54,10 +54,23 @@ def main():
                 results.append(dict(kmers=finder._kmers.get_nparray().copy(), nodes=finder._nodes.get_nparray().copy(),
                                     start_nodes=finder._start_nodes.get_nparray().copy(), start_offsets=finder._start_offsets.get_nparray().copy(),
                                     allele_frequencies=finder._allele_frequencies.get_nparray().copy()))
+            # whitelist (kf:95-104, 130-132, 362-365): only these k-mers are stored -- half of what an unrestricted run finds
+            full = DenseKmerFinder(graph, k=k, critical_graph_paths=crit, **kwargs)
+            full.find()
+            found = np.unique(full._kmers.get_nparray())
+            whitelist = found[rng.random(len(found)) < 0.5]
+            wl = DenseKmerFinder(graph, k=k, critical_graph_paths=crit, whitelist=set(int(x) for x in whitelist), **kwargs)
+            wl.find()
+            wl_result = dict(kmers=wl._kmers.get_nparray().copy(), nodes=wl._nodes.get_nparray().copy(),
+                             start_nodes=wl._start_nodes.get_nparray().copy(), start_offsets=wl._start_offsets.get_nparray().copy(),
+                             allele_frequencies=wl._allele_frequencies.get_nparray().copy())
         except Exception as e:                            # graphs the reference itself cannot process are skipped
             print("skip:", type(e).__name__, e)
             continue
         p = "c%d_" % kept
+        out[p + "whitelist"] = whitelist.astype(np.int64)
+        for key, v in wl_result.items():
+            out[p + "wl_" + key] = v
         for key, v in graph.to_arrays().items():
             out[p + "g_" + key] = v
         out[p + "k"] = np.int64(k)

@@ -113,6 +113,11 @@ def test_chunked_runs_match_the_reference():
             finder.find()
             for key in KEYS:
                 assert np.array_equal(finder._results[key], ref[key]), (i, (s, e), key)
+        wl_finder = gki.DenseKmerFinder(arrays, k, critical_graph_paths=gki.CriticalGraphPaths(cn, co), max_variant_nodes=mvn,
+                                        whitelist=set(int(x) for x in g["c%d_whitelist" % i]))
+        wl_finder.find()
+        for key in KEYS:                                     # whitelist (kf:130-132, 362-365) against the reference
+            assert np.array_equal(wl_finder._results[key], g["c%d_wl_%s" % (i, key)]), (i, "whitelist", key)
         # two emulated ranks, chunks dealt round-robin, gathered by hand
         n_chunks = requested[0]
         parts = []
