@@ -24,6 +24,7 @@
 // bulk copies on its own mbarrier, packs them to 2 bits per base (or receives them packed) and walks them with a
 // rolling window -- no CTA-wide barrier anywhere, so a warp that waits on HBM never stalls its neighbours.
 // Host batches reach it through the packing lanes at the end of this file (count_reads_host_pipeline).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <atomic>
@@ -1138,7 +1139,7 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
     int rc = GKI_OK;
     // The copy engine and the packing threads read the same host memory, and whether an ASCII transfer next to the packers pays
     // depends on the host: on the 16-thread bench box 14 packers alone are faster (13.7 ms vs 15.5 ms per 1.5 GB), on the
-    // 24-thread two-GPU box the copy lane adds 19 %.  So the pipeline tries both on its first two large calls and keeps the faster
+    // 24-thread two-GPU box the copy lane adds 19 %.  So the pipeline tries both twice on its first large calls and keeps the faster
     // (bytes per second of the whole call), looking at the other again every 64th call.  GKI_PIPELINE_DMA=0/1 overrides.
     bool dma_lane = !row_offsets;
     const bool adaptive = !row_offsets && !getenv("GKI_PIPELINE_DMA");
@@ -1146,7 +1147,7 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
     if (adaptive) {
         const uint64_t call_no = p->calls++;
         if (call_no == 0) dma_lane = true;                                                   // first call: warm-up, not recorded
-        else if (p->rate[0] == 0.0 || p->rate[1] == 0.0) dma_lane = p->rate[1] == 0.0;       // then with, then without
+        else if (call_no <= 4) dma_lane = (call_no & 1) != 0;                                // then with / without, twice each (best kept)
         else if (call_no % 64 == 63) dma_lane = !(p->rate[1] >= p->rate[0]);                 // a look at the losing side
         else dma_lane = p->rate[1] >= p->rate[0];
     }
@@ -1166,7 +1167,13 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
     cudaStreamSynchronize(s);
     if (adaptive && rc == GKI_OK && !p->failed.load()) {
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
-        if (secs > 0 && p->calls > 1) p->rate[dma_lane ? 1 : 0] = (double)n_reads * read_len / secs;
+        if (secs > 0 && p->calls > 1) {
+            const double rate = (double)n_reads * read_len / secs;
+            double &slot = p->rate[dma_lane ? 1 : 0];
+            slot = (p->calls <= 5 && slot > rate) ? slot : rate;   // exploration keeps the better of its two trials per mode
+            if (getenv("GKI_PIPELINE_DEBUG")) fprintf(stderr, "[gki pipeline] call %llu dma=%d %.1f GB/s (best: without %.1f, with %.1f)\n",
+                                                      (unsigned long long)p->calls, (int)dma_lane, rate / 1e9, p->rate[0] / 1e9, p->rate[1] / 1e9);
+        }
     }
     if (rc == GKI_OK && p->failed.load()) {
         set_error("%s", p->error.empty() ? "gki_count_reads: a packing lane failed" : p->error.c_str());
