@@ -34,59 +34,57 @@ def gather(column, perm):
 
 
 class ReverseKmerIndex:
-    """reverse_kmer_index.py:5-84."""
+    """reverse_kmer_index.py:5-84: for every node the k-mers (and their reference positions) that touch it, stored as one run per
+    node of `hashes` / `ref_positions`; `nodes_to_index_positions[node]` is where the run starts, `nodes_to_n_hashes[node]` its length."""
     properties = {"nodes_to_index_positions", "nodes_to_n_hashes", "hashes", "ref_positions"}
+    _FIELDS = ("nodes_to_index_positions", "nodes_to_n_hashes", "hashes", "ref_positions")
 
     def __init__(self, nodes_to_index_positions=None, nodes_to_n_hashes=None, hashes=None, ref_positions=None):
-        self.nodes_to_index_positions = nodes_to_index_positions
-        self.nodes_to_n_hashes = nodes_to_n_hashes
-        self.hashes = hashes
-        self.ref_positions = ref_positions
+        for name, value in zip(self._FIELDS, (nodes_to_index_positions, nodes_to_n_hashes, hashes, ref_positions)):
+            setattr(self, name, value)
 
     def __str__(self):
-        description = "Nodes to index positions: %s\n" % self.nodes_to_index_positions
-        description += "Nodes to n hashes      : %s\n" % self.nodes_to_n_hashes
-        description += "Hashes:                  %s\n" % self.hashes
-        description += "Ref positions:                  %s\n" % self.ref_positions
-        return description
+        labels = ("Nodes to index positions: ", "Nodes to n hashes      : ", "Hashes:                  ", "Ref positions:                  ")
+        return "".join("%s%s\n" % (label, getattr(self, name)) for label, name in zip(labels, self._FIELDS))
+
+    def _run(self, node):
+        """[start, end) of the node's run; an unknown node raises IndexError like the reference's array lookup does."""
+        start = int(self.nodes_to_index_positions[node])
+        return start, start + int(self.nodes_to_n_hashes[node])
 
     def get_node_kmers(self, node):
-        """reverse_kmer_index.py:23-29."""
-        index_position = int(self.nodes_to_index_positions[node])
-        n_hashes = int(self.nodes_to_n_hashes[node])
-        if n_hashes == 0:
-            return []
-        return self.hashes[index_position:index_position + n_hashes]
+        """reverse_kmer_index.py:23-29 ([] for a node without k-mers)."""
+        start, end = self._run(node)
+        return [] if end == start else self.hashes[start:end]
 
     def get_node_kmers_and_ref_positions(self, node):
-        """reverse_kmer_index.py:31-42."""
+        """reverse_kmer_index.py:31-42 ([[], []] for a node without k-mers)."""
         try:
-            index_position = int(self.nodes_to_index_positions[node])
+            start, end = self._run(node)
         except IndexError:
             logging.error("Invalid node %d" % node)
             raise
-        n_hashes = int(self.nodes_to_n_hashes[node])
-        if n_hashes == 0:
+        if end == start:
             return [[], []]
-        return self.hashes[index_position:index_position + n_hashes], self.ref_positions[index_position:index_position + n_hashes]
+        return self.hashes[start:end], self.ref_positions[start:end]
 
     @classmethod
     def from_file(cls, file_name):
+        """reverse_kmer_index.py:44-51: `file_name`, else `file_name + ".npz"`."""
         try:
-            data = np.load(file_name)
+            archive = np.load(file_name)
         except FileNotFoundError:
-            data = np.load(file_name + ".npz")
-        return cls(data["nodes_to_index_positions"], data["nodes_to_n_hashes"], data["hashes"], data["ref_positions"])
+            archive = np.load(file_name + ".npz")
+        return cls(*[archive[name] for name in cls._FIELDS])
 
     def to_file(self, file_name):
-        np.savez(file_name, nodes_to_index_positions=self.nodes_to_index_positions, nodes_to_n_hashes=self.nodes_to_n_hashes,
-                 hashes=self.hashes, ref_positions=self.ref_positions)
+        """reverse_kmer_index.py:53-57 (uncompressed npz, keys = attribute names)."""
+        np.savez(file_name, **{name: getattr(self, name) for name in self._FIELDS})
 
     @classmethod
     def from_flat_kmers(cls, flat_kmers):
         """reverse_kmer_index.py:59-84.  The sort is stable (the reference's argsort is not: the order of the entries of
         one node is only defined up to a permutation there); n_kmers is uint16 like the reference's and wraps the same way."""
         nodes = np.asarray(flat_kmers._nodes)
-        max_node = int(np.max(nodes))
-        perm, first, counts = group_by_key(nodes, max_node + 1)
+        perm, first, counts = group_by_key(nodes, int(np.max(nodes)) + 1)
         return cls(first, counts.astype(np.uint16), gather(flat_kmers._hashes, perm), gather(flat_kmers._ref_offsets, perm))
