@@ -97,7 +97,7 @@ _SIGNATURES = {
     "gki_calibrate_scatter": [c_i64, c_i32, c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_copy": [c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_critical_paths": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp],
-    "gki_finder_prepare": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32,
+    "gki_finder_prepare": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32,
                            c_i32, c_i64, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), c_vp],
     "gki_finder_fill": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gki_finder_destroy": [c_vp],

@@ -33,6 +33,7 @@ struct FinderGraph {
     const uint16_t *crit_index;   // critical_graph_paths.py:11-19: offset per node, 0 for nodes that are not critical
     int64_t crit_len;
     const uint8_t *store;         // only_store_nodes as a per-node flag, or NULL
+    const uint8_t *force;         // nodes whose (already reduced) successor list is followed whatever max_variant_nodes says, or NULL
 };
 
 struct FinderParams {
@@ -228,7 +229,8 @@ __device__ void walk_chain(const FinderGraph &g, const FinderParams &p, int64_t 
                         for (int j = 0; j < nd; j++) seen |= distinct[j] == v;
                         if (!seen && nd < F_DISTINCT) { distinct[nd++] = v; n_var += !g.is_linear[v]; }
                     }
-                    if (n_var >= p.max_variant_nodes) {           // only the linear-ref continuation is allowed
+                    const bool force_follow = g.force && g.force[node];   // kf:385-388: the successors are only_follow_nodes
+                    if (!force_follow && n_var >= p.max_variant_nodes) {   // only the linear-ref continuation is allowed
                         int32_t lin = -1, n_lin = 0;
                         for (int32_t e = e0; e < e1; e++)
                             if (g.is_linear[g.edges[e]]) { lin = e; n_lin++; }
@@ -336,9 +338,9 @@ int gki_finder_destroy(gki_finder *f) {
 // Pass 1: upload the graph + starting points, count the rows.  *n_rows receives the number of output rows.
 int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int64_t *edge_offsets, const int32_t *edges,
                        const uint8_t *is_linear, const double *allele_frequencies, int64_t n_nodes, const uint16_t *crit_index,
-                       int64_t crit_len, const uint8_t *store_flags, const int32_t *start_nodes, const int32_t *start_offsets,
-                       int64_t n_starts, const int64_t *chain_first, int64_t n_chains, int32_t k, int32_t max_variant_nodes,
-                       int32_t one_node_per_kmer, int32_t early_stop, int64_t treated_slots, gki_finder **out, int64_t *n_rows,
+                       int64_t crit_len, const uint8_t *store_flags, const uint8_t *force_follow_flags, const int32_t *start_nodes,
+                       const int32_t *start_offsets, int64_t n_starts, const int64_t *chain_first, int64_t n_chains, int32_t k,
+                       int32_t max_variant_nodes, int32_t one_node_per_kmer, int32_t early_stop, int64_t treated_slots, gki_finder **out, int64_t *n_rows,
                        gki_stream_t stream) {
     cudaStream_t s = (cudaStream_t)stream;
     GKI_REQUIRE(out && n_rows && seq_offsets && edge_offsets && is_linear && allele_frequencies && n_nodes >= 1 && k >= 1 && k <= 31 &&
@@ -369,6 +371,7 @@ int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int
     GKI_TRY(upload(crit_index, (size_t)crit_len * 2, (void **)&f->g.crit_index));
     f->g.crit_len = crit_index ? crit_len : 0;
     GKI_TRY(upload(store_flags, (size_t)n_nodes, (void **)&f->g.store));
+    GKI_TRY(upload(force_follow_flags, (size_t)n_nodes, (void **)&f->g.force));
     GKI_TRY(upload(start_nodes, (size_t)n_starts * 4, (void **)&f->p.start_nodes));
     GKI_TRY(upload(start_offsets, (size_t)n_starts * 4, (void **)&f->p.start_offsets));
     GKI_TRY(upload(chain_first, (size_t)(n_chains + 1) * 8, (void **)&f->p.chain_first));

@@ -6,7 +6,9 @@ The graph argument is an obgraph.Graph-like object.  The finder needs it as flat
 methods the reference calls (kf:50,62,138,143,259,279,350,374,384; cgp:46-95).
 
 ``whitelist`` (kf:95-104, 130-132, 362-365) only decides which rows are stored, never the walk, so it is applied to the rows
-the device returns.  Not supported (raises NotImplementedError): ``only_follow_nodes`` (kf:385-388), which redirects the walk."""
+the device returns.  ``only_follow_nodes`` (kf:385-388) redirects the walk: a node with successors in the set is left with
+only those -- in the order the reference's ``set.intersection`` iterates them -- and ignores ``max_variant_nodes``; that is a
+property of the node, so it is applied to the edge lists here (`follow_only`) and the device gets a per-node flag."""
 import ctypes
 import logging
 
@@ -42,6 +44,36 @@ def graph_arrays(graph):
                 allele_frequencies=np.asarray(graph.get_node_allele_frequencies(np.arange(n)), dtype=np.float64), n_in_edges=n_in,
                 first_node=np.int64(graph.get_first_node()), node_to_ref_offset=np.asarray(graph.node_to_ref_offset),
                 chromosome_start_nodes=np.array(list(graph.chromosome_start_nodes.values()), dtype=np.int64))
+
+
+def follow_only(edge_offsets, edges, only_follow_nodes):
+    """kf:385-388 as a graph rewrite -> (edge_offsets, edges, force_follow u8[n]).  Nodes with a successor in
+    `only_follow_nodes` keep `only_follow_nodes.intersection(successors)` in that set's own iteration order (the order the
+    reference's loop at kf:406 sees) and are flagged `force_follow`."""
+    edge_offsets = np.asarray(edge_offsets, dtype=np.int64)
+    edges = np.asarray(edges, dtype=np.int32)
+    n = len(edge_offsets) - 1
+    follow = set(int(x) for x in only_follow_nodes)
+    force = np.zeros(n, dtype=np.uint8)
+    hits = np.flatnonzero(np.isin(edges, np.fromiter(follow, dtype=np.int64, count=len(follow))))
+    if len(hits) == 0:
+        return edge_offsets, edges, force
+    sources = np.unique(np.searchsorted(edge_offsets, hits, side="right") - 1)
+    keep = np.ones(len(edges), dtype=bool)
+    chosen = {}
+    for u in sources:
+        e0, e1 = int(edge_offsets[u]), int(edge_offsets[u + 1])
+        chosen[int(u)] = list(follow.intersection(int(x) for x in edges[e0:e1]))
+        keep[e0 + len(chosen[int(u)]):e1] = False
+        force[u] = 1
+    degrees = np.diff(edge_offsets)
+    degrees[sources] = [len(chosen[int(u)]) for u in sources]
+    new_offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(degrees, out=new_offsets[1:])
+    new_edges = edges[keep].copy()
+    for u, nodes in chosen.items():
+        new_edges[new_offsets[u]:new_offsets[u + 1]] = nodes
+    return new_offsets, new_edges, force
 
 
 def _c(a, dtype):
@@ -101,8 +133,7 @@ class DenseKmerFinder:
     def __init__(self, graph, k, critical_graph_paths=None, position_id=None, only_save_one_node_per_kmer=False, max_variant_nodes=4,
                  only_store_variant_nodes=False, start_at_critical_path_number=None, stop_at_critical_path_number=None, whitelist=None,
                  only_store_nodes=None, only_follow_nodes=None):
-        if only_follow_nodes is not None:
-            raise NotImplementedError("only_follow_nodes is not supported by the device finder")
+        self._only_follow_nodes = only_follow_nodes
         self._whitelist = None if whitelist is None else np.fromiter((int(x) for x in whitelist), dtype=np.int64)
         assert 1 <= k <= 31
         self._graph = graph
@@ -156,10 +187,14 @@ class DenseKmerFinder:
         slots = 1 << max(10, int(np.ceil(np.log2(max(4 * total_bases, 1024)))))
         handle = ctypes.c_void_p()
         n_rows = ctypes.c_int64()
-        keep_alive = [_c(a["seq_offsets"], np.int64), _c(a["seq"], np.uint8), _c(a["edge_offsets"], np.int64), _c(a["edges"], np.int32),
+        edge_offsets, edges, force = a["edge_offsets"], a["edges"], None
+        if self._only_follow_nodes is not None:
+            edge_offsets, edges, force = follow_only(edge_offsets, edges, self._only_follow_nodes)
+        keep_alive = [_c(a["seq_offsets"], np.int64), _c(a["seq"], np.uint8), _c(edge_offsets, np.int64), _c(edges, np.int32),
                       _c(a["is_linear"], np.uint8), _c(a["allele_frequencies"], np.float64)]
         _lib.call("gki_finder_prepare", *[_lib.ptr(x) for x in keep_alive], n, _lib.ptr(crit_index) if len(crit_index) else None,
-                  len(crit_index), _lib.ptr(store), _lib.ptr(start_nodes), _lib.ptr(start_offsets), len(starts), _lib.ptr(chain_first),
+                  len(crit_index), _lib.ptr(store), _lib.ptr(force), _lib.ptr(start_nodes), _lib.ptr(start_offsets), len(starts),
+                  _lib.ptr(chain_first),
                   len(first), k, int(self._max_variant_nodes), int(bool(self._only_save_one_node_per_kmer)), int(early_stop), slots,
                   ctypes.byref(handle), ctypes.byref(n_rows), _lib.current_stream())
         try:

@@ -244,13 +244,16 @@ int gki_critical_paths(const int64_t *seq_offsets, const int64_t *edge_offsets, 
  * (kf:54-58).  crit_index[crit_len] is CriticalGraphPaths._index (critical_graph_paths.py:11-19); start_nodes /
  * start_offsets list the starting points in processing order (kf:192-214), chain_first[n_chains+1] groups the ones a
  * single walker must handle one after the other; store_flags (optional) is only_store_nodes as a per-node byte;
+ * force_follow_flags (optional) marks, per node, `force_follow` of kf:385-388: only_follow_nodes is applied by the
+ * caller to the edge lists (a node with successors in the set keeps only those), and the successors of a flagged node
+ * are all followed even when max_variant_nodes is reached;
  * treated_slots (power of two) sizes the set behind `_positions_treated` (kf:311-319). */
 int gki_finder_prepare(const int64_t *seq_offsets, const uint8_t *seq, const int64_t *edge_offsets, const int32_t *edges,
                        const uint8_t *is_linear, const double *allele_frequencies, int64_t n_nodes, const uint16_t *crit_index,
-                       int64_t crit_len, const uint8_t *store_flags, const int32_t *start_nodes, const int32_t *start_offsets,
-                       int64_t n_starts, const int64_t *chain_first, int64_t n_chains, int32_t k, int32_t max_variant_nodes,
-                       int32_t one_node_per_kmer, int32_t early_stop, int64_t treated_slots, gki_finder_t **out, int64_t *n_rows,
-                       gki_stream_t stream);
+                       int64_t crit_len, const uint8_t *store_flags, const uint8_t *force_follow_flags, const int32_t *start_nodes,
+                       const int32_t *start_offsets, int64_t n_starts, const int64_t *chain_first, int64_t n_chains, int32_t k,
+                       int32_t max_variant_nodes, int32_t one_node_per_kmer, int32_t early_stop, int64_t treated_slots,
+                       gki_finder_t **out, int64_t *n_rows, gki_stream_t stream);
 int gki_finder_fill(gki_finder_t *finder, int64_t *kmers, int32_t *nodes, int32_t *start_nodes, int16_t *start_offsets,
                     double *allele_frequencies, gki_stream_t stream);
 int gki_finder_destroy(gki_finder_t *finder);

@@ -68,7 +68,7 @@ def _critical_index(crit_nodes, crit_offsets):
 
 
 def dense_kmer_finder(arrays, k, critical=None, max_variant_nodes=4, only_save_one_node_per_kmer=False, only_store_nodes=None,
-                      only_position=None):
+                      only_position=None, only_follow_nodes=None):
     """kmer_finder.py:37-434.  only_position=(node, offset): find_only_kmers_starting_at_position (kf:170-177).
     Returns dict(kmers int64, nodes int32, start_nodes int32, start_offsets int16, allele_frequencies float64)."""
     g = G(arrays)
@@ -177,9 +177,13 @@ def dense_kmer_finder(arrays, k, critical=None, max_variant_nodes=4, only_save_o
             children = []
             if not stopped:
                 children = g.out(node)
+                force_follow = False
+                if only_follow_nodes is not None and len(only_follow_nodes.intersection(children)) > 0:                   # kf:385-388
+                    children = list(only_follow_nodes.intersection(children))      # a set in the reference: its iteration order
+                    force_follow = True
                 if children:
                     n_var = len(set(n for n in wnode if not g.is_linear[n]))
-                    if n_var >= max_variant_nodes:
+                    if not force_follow and n_var >= max_variant_nodes:
                         children = [n for n in children if g.is_linear[n]]
                         assert len(children) == 1, "Not 1 linear ref next nodes from node %d: %s" % (node, children)
             if children:

@@ -17,7 +17,8 @@ KEYS = ("kmers", "nodes", "start_nodes", "start_offsets", "allele_frequencies")
 def run_product(arrays, opts):
     import graph_kmer_index_b200 as gki
     finder = gki.DenseKmerFinder(arrays, opts["k"], max_variant_nodes=opts["max_variant_nodes"],
-                                 only_save_one_node_per_kmer=opts["only_save_one_node_per_kmer"], only_store_nodes=opts["only_store_nodes"])
+                                 only_save_one_node_per_kmer=opts["only_save_one_node_per_kmer"], only_store_nodes=opts["only_store_nodes"],
+                                 only_follow_nodes=opts.get("only_follow_nodes"))
     if opts["only_position"] is None:
         finder.find()
     else:
@@ -38,6 +39,16 @@ def test_reference_fixtures():
             got = finder._results[key]
             assert got.dtype == ref[key].dtype or key in ("nodes", "kmers"), (i, key, got.dtype, ref[key].dtype)
             assert np.array_equal(got, ref[key]), (i, key, got[:12], ref[key][:12])
+
+
+def test_only_follow_nodes_reference_fixtures():
+    """kf:385-388: ordered equality with the unmodified reference (tests/golden/finder_follow.npz)."""
+    g = load_golden("finder_follow")
+    for i in range(int(g["n_cases"])):
+        arrays, opts, ref, _ = load_case(g, i)
+        finder = run_product(arrays, opts)
+        for key in KEYS:
+            assert np.array_equal(finder._results[key], ref[key]), (i, key, finder._results[key][:12], ref[key][:12])
 
 
 def test_reference_test_case1_order():

@@ -207,3 +207,26 @@ def test_bench_reference_arm_contract():
     assert d["steps"] == 2 and d["warmup"] == 1 and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_follow_only_rewrites_the_edge_lists():
+    """kmer_finder.follow_only (kf:385-388 as a graph rewrite): a node with successors in the set keeps exactly the set's
+    intersection with them, in the set's iteration order, and is flagged; every other node is untouched."""
+    from graph_kmer_index_b200.kmer_finder import follow_only
+    rng = np.random.default_rng(3)
+    n = 200
+    degrees = rng.integers(0, 4, n)
+    edge_offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(degrees, out=edge_offsets[1:])
+    edges = rng.integers(0, n, int(edge_offsets[-1])).astype(np.int32)      # duplicates edges included
+    for follow in (set(), {7, 8}, set(int(x) for x in rng.choice(n, 40, replace=False))):
+        new_offsets, new_edges, force = follow_only(edge_offsets, edges, follow)
+        assert new_offsets.dtype == np.int64 and new_edges.dtype == np.int32 and force.dtype == np.uint8 and len(force) == n
+        for u in range(n):
+            succ = [int(x) for x in edges[edge_offsets[u]:edge_offsets[u + 1]]]
+            got = [int(x) for x in new_edges[new_offsets[u]:new_offsets[u + 1]]]
+            want = list(follow.intersection(succ))
+            assert got == (want if want else succ) and bool(force[u]) == bool(want), u
+    # {7, 8}.intersection([7, 8]) iterates 8 first: the order of the reference's loop, not the edge order
+    o, e, f = follow_only(np.array([0, 2, 2, 2, 2, 2, 2, 2, 2, 2]), np.array([7, 8], dtype=np.int32), {7, 8})
+    assert list(e) == list({7, 8}.intersection([7, 8])) and list(f) == [1] + [0] * 8

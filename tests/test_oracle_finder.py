@@ -18,6 +18,8 @@ def load_case(g, i):
     store = g[p + "only_store_nodes"]
     opts = dict(k=int(g[p + "k"]), max_variant_nodes=int(g[p + "max_variant_nodes"]), only_save_one_node_per_kmer=bool(g[p + "one_node"]),
                 only_store_nodes=set(int(x) for x in store) if len(store) else None, only_position=tuple(int(x) for x in pos) if len(pos) else None)
+    if p + "only_follow_nodes" in g:
+        opts["only_follow_nodes"] = set(int(x) for x in g[p + "only_follow_nodes"])
     ref = {k: g[p + "ref_" + k] for k in ("kmers", "nodes", "start_nodes", "start_offsets", "allele_frequencies")}
     return arrays, opts, ref, (g[p + "crit_nodes"], g[p + "crit_offsets"])
 
@@ -36,6 +38,23 @@ def test_finder_oracle_matches_reference():
             assert np.array_equal(got[key], ref[key]), (i, key, got[key][:10], ref[key][:10])
         total += len(ref["kmers"])
     assert total > 10000
+
+
+def test_finder_oracle_only_follow_nodes_matches_reference():
+    """kf:385-388 -- fixtures of tests/golden/make_golden_finder_follow.py (the unmodified reference, used the way
+    unique_variant_kmers.py:90-96 does and through find())."""
+    g = load_golden("finder_follow")
+    n = int(g["n_cases"])
+    assert n >= 20
+    differs = 0
+    for i in range(n):
+        arrays, opts, ref, _ = load_case(g, i)
+        got = finder_oracle.dense_kmer_finder(arrays, **opts)
+        for key in ref:
+            assert np.array_equal(got[key], ref[key]), (i, key, got[key][:10], ref[key][:10])
+        plain = finder_oracle.dense_kmer_finder(arrays, **dict(opts, only_follow_nodes=None)) if opts["only_position"] is None else None
+        differs += plain is not None and not np.array_equal(plain["kmers"], ref["kmers"])
+    assert differs >= 5          # the option changes the walk in the fixtures
 
 
 def test_reference_readme_example():
