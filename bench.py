@@ -139,6 +139,55 @@ def cpu_count_rate(idx, reads, k, seconds, chunk=50_000):
     return done * nk / dt, done * nk, dt, done
 
 
+def reference_native_rate(idx, reads, k, n_nodes, seconds=6.0, chunk=2000):
+    """The reference's own compiled code where it exists: cython_kmer_index.pyx built as-is into oracle/_ref (pyx:47-109, two-pass probe
+    -> hit list; gates as shipped) + np.bincount over the hit nodes, fed by the np.convolve hashing of read_kmers.py:67-70 read by read
+    (oracle/numpy_oracle.read_kmer_hashes), on one thread like the reference.  Time-boxed prefix of the step's reads.  None when the
+    extension was not built (no reference tree at build time)."""
+    import contextlib
+    import glob
+    import importlib.util
+    import io
+    from oracle import numpy_oracle as no
+    so = glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "cython_kmer_index*.so"))
+    if not so:
+        return None
+    spec = importlib.util.spec_from_file_location("cython_kmer_index", so[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class View:   # pyx:33-41 reads these attributes; hashes_to_index must be long[:]
+        pass
+    view = View()
+    for key in ("_n_kmers", "_nodes", "_ref_offsets", "_kmers", "_frequencies", "_allele_frequencies", "_modulo"):
+        setattr(view, key, idx[key])
+    view._hashes_to_index = idx["_hashes_to_index"].astype(np.int64)
+    with contextlib.redirect_stdout(io.StringIO()):
+        cy = mod.CythonKmerIndex(view)
+    counts = np.zeros(n_nodes, dtype=np.float64)
+    done, t_hash, t_probe, t0 = 0, 0.0, 0.0, time.perf_counter()
+    while done < len(reads) and time.perf_counter() - t0 < seconds:
+        t1 = time.perf_counter()
+        hashes = []
+        for row in reads[done:done + chunk]:
+            hashes.append(no.read_kmer_hashes(row, k))
+            hashes.append(no.read_kmer_hashes(no.reverse_complement_ascii(row), k))
+        hashes = np.concatenate(hashes)
+        t2 = time.perf_counter()
+        with contextlib.redirect_stdout(io.StringIO()):
+            hits = cy.get(hashes)
+        counts += np.bincount(hits[0].astype(np.int64), minlength=n_nodes)[:n_nodes]
+        t_hash += t2 - t1
+        t_probe += time.perf_counter() - t2
+        done += min(chunk, len(reads) - done)
+    dt = time.perf_counter() - t0
+    nk = (reads.shape[1] - k + 1) * 2
+    return {"value": done * nk / dt, "unit": "kmers/s", "cores": 1, "kind": "reference",
+            "hash_kmers_per_s": done * nk / max(t_hash, 1e-9), "probe_kmers_per_s": done * nk / max(t_probe, 1e-9),
+            "sample": "first %d reads of the step in %.1f s: np.convolve hashing per read (read_kmers.py:67-70) + the reference's compiled "
+                      "CythonKmerIndex.get (oracle/_ref, built from cython_kmer_index.pyx as-is) + np.bincount, single thread" % (done, dt)}
+
+
 def run_reference(args, cfg, rank):
     """--impl reference: the reference's CPU path for the metric (oracle port; the reference itself is pure Python
     whose counting step lives in an absent third-party package) on the host cores, bounded sample per step."""
@@ -175,6 +224,9 @@ def run_reference(args, cfg, rank):
             "cpu_baseline": {"value": value, "unit": "kmers/s", "cores": threads, "kind": "port",
                              "sample": "%d of %d reads per step, oracle/gki_oracle.c with OpenMP over %d host threads" % (sample_reads, cfg["reads"], threads)},
             "e2e": {"value": value, "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if not args.no_cpu_baseline:
+        # reported next to the port: the port (all host threads, C) is the faster, i.e. the conservative, baseline and stays `value`
+        line["reference_native"] = reference_native_rate(idx, reads, k, cfg["nodes"])
     print(json.dumps(line), flush=True)
 
 

@@ -207,6 +207,8 @@ def test_bench_reference_arm_contract():
     assert d["steps"] == 2 and d["warmup"] == 1 and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "kmers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    native = d["reference_native"]        # the reference's compiled probe (oracle/_ref), when it was built
+    assert native is None or (native["kind"] == "reference" and native["cores"] == 1 and 0 < native["value"] < d["value"] * 50)
 
 
 def test_follow_only_rewrites_the_edge_lists():
