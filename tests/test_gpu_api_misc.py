@@ -81,3 +81,41 @@ def test_convert_kmers_to_complement(gki, index):
                           skip_frequencies=True)
     for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_allele_frequencies", "_frequencies"):
         assert np.array_equal(getattr(comp, key), want[key]), key
+
+
+def test_bionumpy_hash_and_structural_variant_kmers(gki):
+    """Row a10 (bionumpy_wrapper.py:4-10) and its caller, as the reference's tests/test_structural_variants.py:10-49 pins them: the hashes
+    equal sequence_to_kmer_hash of every window, and the sampled k-mers index the nodes the reference expects."""
+    from graph_kmer_index_b200.bionumpy_wrapper import bionumpy_hash
+    from graph_kmer_index_b200.structural_variants import sample_kmers_from_structural_variants
+    seq = "GGGGAAAACCCCAAAA"
+    got = bionumpy_hash(gki.letter_sequence_to_numeric(seq), 5)
+    assert got.dtype == np.uint64 and got.tolist() == [no.sequence_to_kmer_hash(seq[i:i + 5]) for i in range(len(seq) - 4)]
+    rng = np.random.default_rng(1)
+    codes = rng.integers(0, 4, 5000)
+    want = np.convolve(codes.astype(np.uint64), no.power_array(31), mode="valid").astype(np.uint64)       # read_kmers.py:67-70
+    assert np.array_equal(bionumpy_hash(codes, 31), want)
+    assert len(bionumpy_hash(codes[:4], 5)) == 0
+
+    class DummyGraph:
+        def __init__(self, node_sequences):
+            self.node_sequences = node_sequences
+
+        def get_numeric_node_sequence(self, node):
+            return gki.letter_sequence_to_numeric(self.node_sequences[node])
+
+        def get_node_size(self, node):
+            return len(self.node_sequences[node])
+
+    class DummyKmerIndex:
+        def get_frequency(self, kmer):
+            return 1
+
+    graph = DummyGraph({1: "AAAAAAAAAAA", 2: "ACTG", 3: "GGGGAAAACCCCAAAA", 4: "AGGGG"})
+    kmers = sample_kmers_from_structural_variants(graph, zip(np.array([1, 3]), np.array([2, 4])), DummyKmerIndex(), k=5)
+    assert kmers._hashes.dtype == np.uint64 and kmers._nodes.dtype == np.uint32
+    assert kmers._nodes.tolist() == [1, 1, 3, 3, 3]              # windows 0, 5 of node 1 and 0, 5, 10 of node 3
+    index = gki.KmerIndex.from_flat_kmers(kmers)
+    assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("AAAAA")) == [1])
+    assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("GGGGA")) == [3])
+    assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("AAACC")) == [3])
