@@ -7,7 +7,7 @@ touch CUDA; the first call that needs the library loads it and fails loudly if i
 from .kmer_hashing import (letter_sequence_to_numeric, numeric_to_letter_sequence, kmer_to_hash_fast,  # noqa: F401
                            sequence_to_kmer_hash, kmer_hash_to_sequence)
 from .flat_kmers import FlatKmers, FlatKmers2  # noqa: F401
-from .collision_free_kmer_index import CollisionFreeKmerIndex, CounterKmerIndex, MinimalKmerIndex, DeviceIndex  # noqa: F401
+from .collision_free_kmer_index import CollisionFreeKmerIndex, CounterKmerIndex, MinimalKmerIndex, DeviceIndex, KmerIndex2  # noqa: F401
 from .collision_free_kmer_index import CollisionFreeKmerIndex as KmerIndex  # noqa: F401
 from .cython_kmer_index import CythonKmerIndex  # noqa: F401
 from .read_kmers import ReadKmers  # noqa: F401

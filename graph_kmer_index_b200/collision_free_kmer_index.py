@@ -329,6 +329,78 @@ class MinimalKmerIndex:
         return cls(h2i, nk, nodes, kmers, modulo)
 
 
+class _KeyedCounts:
+    """What `HashTable(unique_kmers, counts)` is to KmerIndex2 (cfki:148-158): counts[kmer] for a scalar or an array of known keys."""
+
+    def __init__(self, keys, counts):
+        self._keys, self._values = keys, counts
+
+    def __getitem__(self, keys):
+        keys = np.asarray(keys).astype(self._keys.dtype)
+        at = np.searchsorted(self._keys, keys)
+        if np.any(at >= len(self._keys)) or np.any(self._keys[np.minimum(at, len(self._keys) - 1)] != keys):
+            raise IndexError("key not in the table")
+        return self._values[at]
+
+
+class KmerIndex2:
+    """cfki:110-158: like CollisionFreeKmerIndex, with start node / start offset instead of ref_offset -- the index of
+    DenseKmerFinder.get_flat_kmers(v="2").  Built on the device through MultiValueHashTable."""
+
+    def __init__(self, data, frequencies=None):
+        self._data = data
+        self._frequencies = frequencies
+
+    def get_start_nodes(self, kmer):
+        return self._data[kmer]["start_nodes"]
+
+    def get_start_offsets(self, kmer):
+        return self._data[kmer]["start_offsets"]
+
+    def get_nodes(self, kmer):
+        return self._data[kmer]["nodes"]
+
+    def get_all_kmers(self):
+        return self._data.get_all_keys()
+
+    def get_kmer_frequency(self, kmer):
+        assert self._frequencies is not None, "Frequencies not set"
+        return self._frequencies[kmer]
+
+    @classmethod
+    def from_flat_kmers(cls, flat_kmers, modulo=None, skip_frequencies=False):
+        from .multi_value_hashtable import MultiValueHashTable
+        hash_table = MultiValueHashTable.from_keys_and_values(
+            flat_kmers._hashes, {"nodes": flat_kmers._nodes, "start_nodes": flat_kmers._start_nodes,
+                                 "start_offsets": flat_kmers._start_offsets, "allele_frequencies": flat_kmers._allele_frequencies},
+            mod=modulo)
+        index = cls(hash_table)
+        if not skip_frequencies:
+            index.count_unique_kmer_occurences()
+        return index
+
+    def count_unique_kmer_occurences(self):
+        """cfki:148-158: per distinct k-mer the number of distinct (start node, start offset) pairs.  That is set_frequencies
+        (cfki:267-293) with the pair as the ref offset, so it runs in the same device pass (uint16 there: k-mers of a bucket with
+        65536 or more entries are recounted here)."""
+        table = self._data._hash_table
+        rows = table._nodes
+        start = (np.asarray(self._data._values["start_nodes"]).astype(np.int64) << 16) | \
+            (np.asarray(self._data._values["start_offsets"]).astype(np.int64) & 0xffff)
+        start = start[rows]                                              # in the table's entry order
+        # the entries are already in bucket order and the sort is stable: frequencies come back aligned with them
+        frequencies = build_index_arrays(table._kmers, None, np.ascontiguousarray(start).view(np.uint64), None, table._modulo, False)[6]
+        unique_kmers, first = np.unique(table._kmers, return_index=True)
+        counts = np.zeros_like(unique_kmers)
+        counts[:] = frequencies[first]
+        for bucket in np.flatnonzero(table._n_kmers >= 65536):
+            lo = int(table._hashes_to_index[bucket])
+            kmers, pairs = table._kmers[lo:lo + int(table._n_kmers[bucket])], start[lo:lo + int(table._n_kmers[bucket])]
+            for kmer in np.unique(kmers):
+                counts[np.searchsorted(unique_kmers, kmer)] = len(np.unique(pairs[kmers == kmer]))
+        self._frequencies = _KeyedCounts(unique_kmers, counts)
+
+
 class CollisionFreeKmerIndex:
     """collision_free_kmer_index.py:163-490."""
 

@@ -142,3 +142,49 @@ def test_chunked_runs_match_the_reference():
         whole = distributed.find_kmers_sharded(arrays, k, critical_graph_paths=gki.CriticalGraphPaths(cn, co), n_chunks=n_chunks, rank=0, world_size=1,
                                                max_variant_nodes=mvn)
         assert len(whole._hashes) == sum(len(f._hashes) for _, f in parts)
+
+
+def test_kmer_index2_after_the_reference_tests():
+    """KmerIndex2 / MultiValueHashTable (cfki:110-158, multi_value_hashtable.py) as the reference's own tests pin them:
+    tests/test_indexes2.py:6-22 and the KmerIndex2 assertions of tests/test_kmer_finder.py:10-80."""
+    import graph_kmer_index_b200 as gki
+    flat = gki.FlatKmers2(np.array([1, 1, 1, 2, 3, 10, 11, 2]), np.array([1, 1, 2, 2, 3, 1, 10, 5]), np.array([0, 0, 1, 2, 3, 4, 5, 6]),
+                          np.array([1, 2, 3, 4, 5, 6, 7, 8]), np.array([0.4, 0.1, 0.3, 0.4, 0.1, 0.1, 0.1, 0.1]))
+    index = gki.KmerIndex2.from_flat_kmers(flat)
+    assert index.get_kmer_frequency(1) == 2
+    assert np.all(index.get_start_nodes(1) == [1, 1, 2])
+    assert np.all(index.get_nodes(3) == [5])
+    assert np.all(index.get_nodes(2) == [4, 8]) and np.all(index.get_start_offsets(2) == [2, 6]) and index.get_kmer_frequency(2) == 2
+    assert np.all(index._data[1]["allele_frequencies"] == [0.4, 0.1, 0.3])
+    assert len(index.get_nodes(7)) == 0 and sorted(index.get_all_kmers()) == sorted(flat._hashes)
+
+    h = gki.sequence_to_kmer_hash
+    graph = Graph.from_dicts({0: "AAA", 1: "C", 2: "T", 3: "AAA"}, {0: [1, 2], 2: [3], 1: [3]}, [0, 1, 3])
+    finder = gki.DenseKmerFinder(graph, k=3)
+    finder.find()
+    index = gki.KmerIndex2.from_flat_kmers(finder.get_flat_kmers(), modulo=15)
+    assert np.all(index.get_nodes(h("ATA")) == [0, 2, 3])
+    assert np.all(index.get_start_nodes(h("ATA")) == [3, 3, 3])
+    assert np.all(index.get_start_offsets(h("ATA")) == [0, 0, 0])
+    assert set(index.get_nodes(h("ACA"))) == {0, 1, 3} and set(index.get_nodes(h("AAA"))) == {0, 3}
+    assert len(index.get_all_kmers()) == 16
+
+    graph = Graph.from_dicts({0: "ACTGACTG", 1: "A", 2: "T", 3: "AAAAA", 4: "C", 5: "T", 6: "TGGGGG"},
+                             {0: [1, 2], 2: [3], 1: [3], 3: [4, 5], 4: [6], 5: [6]}, [0, 1, 3, 4, 6])
+    finder = gki.DenseKmerFinder(graph, k=3)
+    finder.find()
+    index = gki.KmerIndex2.from_flat_kmers(finder.get_flat_kmers())
+    assert set(index.get_nodes(h("ACT"))) == {0, 3, 4, 6}
+    assert set(index.get_start_nodes(h("AAC"))) == {4} and set(index.get_start_offsets(h("AAC"))) == {0}
+
+    graph = Graph.from_dicts({1: "ATC", 2: "AAAAAAAA", 3: "T", 4: "CTA"}, {1: [2, 3], 2: [4], 3: [4]}, [1, 2, 4])
+    finder = gki.DenseKmerFinder(graph, k=3)
+    finder.find()
+    flat = finder.get_flat_kmers()
+    index = gki.KmerIndex2.from_flat_kmers(flat)
+    assert len(index.get_nodes(h("AAA"))) == 6 and len(index.get_nodes(h("AAC"))) == 2
+    # frequencies against a direct count over the finder's rows
+    for kmer in np.unique(flat._hashes):
+        rows = flat._hashes == kmer
+        assert index.get_kmer_frequency(kmer) == len(set(zip(flat._start_nodes[rows].tolist(), flat._start_offsets[rows].tolist())))
+        assert np.array_equal(index.get_nodes(kmer), flat._nodes[rows])            # rows of a key come back in input order
