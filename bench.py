@@ -468,6 +468,27 @@ def main():
                         "and the counter sector written back (+ one line per position when the filter does not fit L2); "
                         "traffic = ncu dram bytes of one launch (false-positive and chain probes are the excess)"}
 
+    # ---------------- index build end to end: the reference-facing call on host numpy arrays (cfki:422-467) ----------------
+    build_e2e = None
+    if world == 1 and not args.no_e2e:
+        from graph_kmer_index_b200 import CollisionFreeKmerIndex, FlatKmers
+        d_h, d_n = torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, dtype=torch.int32, device=dev)
+        d_r, d_a = torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, dtype=torch.float32, device=dev)
+        _lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(d_h), _lib.ptr(d_n), _lib.ptr(d_r), _lib.ptr(d_a), stream)
+        flat = FlatKmers(d_h.cpu().numpy().view(np.uint64), d_n.cpu().numpy().view(np.uint32), d_r.cpu().numpy().view(np.uint64), d_a.cpu().numpy())
+        del d_h, d_n, d_r, d_a
+        secs = []
+        for _ in range(2):
+            t0 = time.perf_counter()
+            built = CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo, skip_frequencies=True)
+            secs.append(time.perf_counter() - t0)
+        assert np.array_equal(built._hashes_to_index, h2i.cpu().numpy()) and np.array_equal(built._kmers, s_kmers.cpu().numpy().view(np.uint64))
+        bytes_in, bytes_out = 24 * n, 26 * n + 8 * modulo
+        build_e2e = {"entries_per_s": n / min(secs), "ms": 1e3 * min(secs), "first_call_ms": 1e3 * secs[0], "h2d_bytes": bytes_in, "d2h_bytes": bytes_out,
+                     "note": "CollisionFreeKmerIndex.from_flat_kmers(FlatKmers of host numpy arrays: k-mers, nodes, ref offsets, allele frequencies; "
+                             "skip_frequencies) -> the reference's eight host arrays, pageable memory both ways; best of two calls"}
+        del flat, built
+
     # ---------------- CPU baseline (oracle port on the host cores, bounded sample) ----------------
     cpu = None
     if not args.no_cpu_baseline:
@@ -488,7 +509,7 @@ def main():
             "index_build": {"entries_per_s": n / (build_ms / 1e3), "ms": build_ms, "entries": n,
                             "compulsory_gbs": (50.0 * n + 8.0 * modulo) / (build_ms / 1e3) / 1e9,
                             "note": "gki_index_build (skip_frequencies, kmers+nodes), device-resident, second of two runs; binned path (one scatter + per-bin ordering, csrc/build.cu)"},
-            "index_build_partitioned": part_build,
+            "index_build_e2e": build_e2e, "index_build_partitioned": part_build,
             "index": {"device_bytes": info["device_bytes"], "has_filter": info["has_filter"], "nonempty_buckets": info["nonempty_buckets"]}}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -88,7 +88,7 @@ struct DevOut {
     void *host = nullptr;
     size_t bytes = 0;
     int prepare(void *p, size_t nbytes, cudaStream_t s);       // p may be NULL -> dptr NULL
-    int finish(cudaStream_t s);                                // async D2H; caller syncs the stream
+    int finish(cudaStream_t s);                                // D2H (async, or complete on return for large pageable arrays); caller syncs the stream
     template <typename T> T *as() { return (T *)dptr; }
 };
 

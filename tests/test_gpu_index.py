@@ -454,3 +454,35 @@ def test_build_into_unaligned_table_views(gki):
             assert np.array_equal(a, b)
     want = c_oracle.build_index(hashes, nodes, np.zeros(n, np.uint64), np.ones(n, np.float32), modulo, skip_frequencies=True)
     assert np.array_equal(outs[0][0], want["_hashes_to_index"]) and np.array_equal(outs[0][1].view(np.uint32), want["_n_kmers"])
+
+
+@pytest.mark.parametrize("threads,chunk", [(3, 4096), (8, 65536), (1, 1 << 20)])
+def test_large_pageable_arrays_take_the_parallel_copy(gki, monkeypatch, threads, chunk):
+    """runtime.cu parallel_host_copy (pageable host arrays above GKI_HOST_COPY_MIN_BYTES move through pinned double buffers on
+    several host threads): forced on for small arrays with odd sizes, results equal to the plain path's, byte for byte."""
+    from graph_kmer_index_b200 import synthetic
+    from graph_kmer_index_b200.read_kmers import hash_read_matrix
+    n, modulo = 300_007, 1_000_003
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 5000, 31)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    reads = synthetic.reads(3001, 150, n, 31, 300, n_permille=5)
+    monkeypatch.setenv("GKI_HOST_COPY_THREADS", "0")
+    plain = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo)
+    plain_hashes = hash_read_matrix(reads, 31)
+    monkeypatch.setenv("GKI_HOST_COPY_THREADS", str(threads))
+    monkeypatch.setenv("GKI_HOST_COPY_MIN_BYTES", "1000")
+    monkeypatch.setenv("GKI_HOST_COPY_CHUNK_BYTES", str(chunk))
+    for _ in range(2):
+        index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo)
+        for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_allele_frequencies", "_frequencies"):
+            assert np.array_equal(getattr(index, key), getattr(plain, key)), key
+        fwd, rc = hash_read_matrix(reads, 31)
+        assert np.array_equal(fwd, plain_hashes[0]) and np.array_equal(rc, plain_hashes[1])
+    counter = gki.CounterKmerIndex.from_kmer_index(index)
+    counter.count_kmers(fwd.ravel())
+    counter.count_kmers(rc.ravel())
+    want = gki.CounterKmerIndex.from_kmer_index(plain)
+    monkeypatch.setenv("GKI_HOST_COPY_THREADS", "0")
+    want.count_kmers(plain_hashes[0].ravel())
+    want.count_kmers(plain_hashes[1].ravel())
+    assert np.array_equal(counter.get_node_counts(5000), want.get_node_counts(5000)) and counter.get_node_counts(5000).sum() > 0
