@@ -26,7 +26,10 @@ def _c(a, dtype=None):
 
 
 def _queries(kmers):
-    return _c(np.atleast_1d(np.asarray(kmers)), np.uint64)
+    kmers = np.atleast_1d(np.asarray(kmers))
+    if kmers.dtype == np.int64 and kmers.flags.c_contiguous:
+        return kmers.view(np.uint64)          # same bits as astype(uint64), without the copy
+    return _c(kmers, np.uint64)
 
 
 class DeviceIndex:
@@ -279,7 +282,10 @@ class CounterKmerIndex:
         """cfki:33-37."""
         if not update_counter:
             self.reset()
-        self.counter.count(kmers if not isinstance(kmers, np.ndarray) else kmers.astype(np.int64).view(np.uint64))
+        if isinstance(kmers, np.ndarray):
+            # `kmers.astype(np.int64)` of the reference keeps the bits of a 64-bit integer array: no copy is needed for those
+            kmers = kmers.view(np.uint64) if kmers.dtype in (np.uint64, np.int64) and kmers.flags.c_contiguous else kmers.astype(np.int64).view(np.uint64)
+        self.counter.count(kmers)
 
     def count_reads(self, reads, k, both_strands=True, update_counter=True):
         """Fused read hashing + counting (read_kmers.py:14-26 feeding cfki:33-37) without materialising hashes."""

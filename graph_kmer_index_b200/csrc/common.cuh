@@ -62,6 +62,10 @@ const DeviceInfo &device_info();
 // ------------------------------------------------------------------ host<->device staging
 // Where does a caller pointer live?
 bool is_device_ptr(const void *p);
+// large pageable host arrays (runtime.cu): true when `host` should go through parallel_host_copy, which moves it through pinned double
+// buffers on several host threads (waits for the work queued on `s`, returns when the copy is complete)
+bool wants_parallel_copy(const void *host, size_t bytes);
+int parallel_host_copy(void *dev, void *host, size_t bytes, bool to_device, cudaStream_t s);
 
 // RAII device scratch from the stream-ordered pool.
 struct Scratch {

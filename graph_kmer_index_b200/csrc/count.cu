@@ -1209,14 +1209,17 @@ int gki_count_kmers(gki_index_t *ix, const uint64_t *queries, int64_t nq, gki_st
     GKI_TRY(ensure_table(ix, 0, s));
     if (is_device_ptr(queries)) return launch_count_kmers(ix, queries, nq, s);
     // host queries: chunked, double-buffered H2D overlapped with the probe kernel
-    const int64_t chunk = 4 << 20;   // 4 Mi queries = 32 MiB
+    // (pageable arrays: every chunk crosses through the threaded pinned-buffer copy of runtime.cu, in larger chunks)
+    const bool threaded = wants_parallel_copy(queries, (size_t)nq * 8);
+    const int64_t chunk = threaded ? (16 << 20) : (4 << 20);   // 4 Mi queries = 32 MiB
     GKI_TRY(ensure_staging(ix, (size_t)chunk * 8));
     int c = 0;
     for (int64_t off = 0; off < nq; off += chunk, ++c) {
         int bsel = c & 1;
         int64_t cnt = nq - off < chunk ? nq - off : chunk;
         if (c >= 2) GKI_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->done[bsel], 0));
-        GKI_CUDA(cudaMemcpyAsync(ix->stage[bsel], queries + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, ix->copy_stream));
+        if (threaded) GKI_TRY(parallel_host_copy(ix->stage[bsel], const_cast<uint64_t *>(queries + off), (size_t)cnt * 8, true, ix->copy_stream));
+        else GKI_CUDA(cudaMemcpyAsync(ix->stage[bsel], queries + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, ix->copy_stream));
         GKI_CUDA(cudaEventRecord(ix->ready[bsel], ix->copy_stream));
         GKI_CUDA(cudaStreamWaitEvent(s, ix->ready[bsel], 0));
         GKI_TRY(launch_count_kmers(ix, (const uint64_t *)ix->stage[bsel], cnt, s));
