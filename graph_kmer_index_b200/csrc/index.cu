@@ -140,7 +140,10 @@ template <typename T> static int dev_alloc_copy(T **dst, const T *src, size_t co
     if (!src || count == 0) return GKI_OK;
     GKI_CUDA(cudaMalloc((void **)dst, count * sizeof(T)));
     total += count * sizeof(T);
-    GKI_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDefault, s));
+    if (!is_device_ptr(src) && wants_parallel_copy(src, count * sizeof(T)))   // multi-GB tables of an index held in numpy arrays
+        GKI_TRY(parallel_host_copy(*dst, const_cast<T *>(src), count * sizeof(T), true, s));
+    else
+        GKI_CUDA(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyDefault, s));
     return GKI_OK;
 }
 
