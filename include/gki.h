@@ -13,7 +13,9 @@
  *   - Every array argument is a plain pointer that may live in DEVICE memory or in HOST memory
  *     (pageable or pinned); the library detects which (cudaPointerGetAttributes).  Host inputs are
  *     staged to the device (chunked and double-buffered for the streaming read batches), host
- *     outputs are copied back before the call returns.  Calls whose arguments are all device
+ *     outputs are copied back before the call returns; pageable host arrays of 32 MB or more
+ *     cross the bus through pinned double buffers filled / drained by several host threads
+ *     (GKI_HOST_COPY_THREADS, csrc/runtime.cu).  Calls whose arguments are all device
  *     pointers are asynchronous on `stream` unless stated otherwise.
  *   - Buffers are caller-owned and never freed or resized by the library; inputs are not modified.
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
