@@ -76,6 +76,25 @@ def follow_only(edge_offsets, edges, only_follow_nodes):
     return new_offsets, new_edges, force
 
 
+def starting_points_in_order(crit_nodes, crit_offsets, first_node, start_at, stop_at):
+    """The starting points of DenseKmerFinder.find in processing order, as arrays.  The reference pops them off the end of the
+    reversed list of critical paths (kf:192, 223-226): they come in the order of the critical paths, minus the first `start_at`,
+    up to the first one on the node of path number `stop_at`; the beginning of the graph (`first_node`, when its node is too short to
+    be critical, kf:212-214) comes first."""
+    nodes = np.asarray(crit_nodes).astype(np.int64)
+    offsets = np.asarray(crit_offsets).astype(np.int64)
+    stop_at_node = int(nodes[stop_at]) if stop_at is not None and stop_at < len(nodes) else None
+    if start_at is not None and start_at > 0:
+        nodes, offsets = nodes[start_at:], offsets[start_at:]
+    if first_node is not None:
+        nodes, offsets = np.append(first_node, nodes), np.append(0, offsets)
+    if stop_at_node is not None:
+        at_stop = np.flatnonzero(nodes == stop_at_node)
+        if len(at_stop):
+            nodes, offsets = nodes[:at_stop[0]], offsets[:at_stop[0]]
+    return nodes, offsets
+
+
 def _c(a, dtype):
     return np.ascontiguousarray(np.asarray(a), dtype=dtype)
 
@@ -167,16 +186,19 @@ class DenseKmerFinder:
         return FlatKmers2(r["kmers"], r["start_nodes"], r["start_offsets"], r["nodes"], r["allele_frequencies"])
 
     # ---- searches ----
-    def _run(self, starts, crit_index, early_stop):
+    def _run(self, start_nodes, start_offsets, crit_index, early_stop):
         a = self._arrays
         n = len(a["seq_offsets"]) - 1
         k = self._k
-        start_nodes = _c([s[0] for s in starts], np.int32)
-        start_offsets = _c([s[1] for s in starts], np.int32)
+        start_nodes = _c(start_nodes, np.int32)
+        start_offsets = _c(start_offsets, np.int32)
+        n_starts = len(start_nodes)
         # a start at offset 0 is overrun by the search before it (kf:333 only tests offset + 1), so it shares the
         # walker -- and the `_positions_treated` history -- of that search
-        first = [i for i in range(len(starts)) if i == 0 or starts[i][1] != 0]
-        chain_first = _c(first + [len(starts)], np.int64)
+        is_first = start_offsets != 0
+        is_first[:1] = True
+        first = np.flatnonzero(is_first)
+        chain_first = _c(np.append(first, n_starts), np.int64)
         store = None
         if self._only_store_nodes is not None:
             store = np.zeros(n, dtype=np.uint8)
@@ -193,9 +215,8 @@ class DenseKmerFinder:
         keep_alive = [_c(a["seq_offsets"], np.int64), _c(a["seq"], np.uint8), _c(edge_offsets, np.int64), _c(edges, np.int32),
                       _c(a["is_linear"], np.uint8), _c(a["allele_frequencies"], np.float64)]
         _lib.call("gki_finder_prepare", *[_lib.ptr(x) for x in keep_alive], n, _lib.ptr(crit_index) if len(crit_index) else None,
-                  len(crit_index), _lib.ptr(store), _lib.ptr(force), _lib.ptr(start_nodes), _lib.ptr(start_offsets), len(starts),
-                  _lib.ptr(chain_first),
-                  len(first), k, int(self._max_variant_nodes), int(bool(self._only_save_one_node_per_kmer)), int(early_stop), slots,
+                  len(crit_index), _lib.ptr(store), _lib.ptr(force), _lib.ptr(start_nodes), _lib.ptr(start_offsets), n_starts,
+                  _lib.ptr(chain_first), len(first), k, int(self._max_variant_nodes), int(bool(self._only_save_one_node_per_kmer)), int(early_stop), slots,
                   ctypes.byref(handle), ctypes.byref(n_rows), _lib.current_stream())
         try:
             m = n_rows.value
@@ -210,11 +231,11 @@ class DenseKmerFinder:
             keep = np.isin(out["kmers"], self._whitelist)
             out = {key: v[keep] for key, v in out.items()}
         # results accumulate over calls like the reference's NpLists do
-        self._results = {key: np.concatenate([self._results[key], out[key]]) for key in out}
+        self._results = out if len(self._results["kmers"]) == 0 else {key: np.concatenate([self._results[key], out[key]]) for key in out}
 
     def find_only_kmers_starting_at_position(self, node, offset):
         """kf:170-177."""
-        self._run([(int(node), int(offset))], np.zeros(0, dtype=np.uint16), early_stop=True)
+        self._run([int(node)], [int(offset)], np.zeros(0, dtype=np.uint16), early_stop=True)
 
     def find(self):
         """kf:179-244."""
@@ -222,23 +243,13 @@ class DenseKmerFinder:
         if self._critical_graph_paths is None:
             self._critical_graph_paths = CriticalGraphPaths.from_graph(self._arrays, k)
         crit = self._critical_graph_paths
-        starting_points = [(int(nd), int(off)) for nd, off in crit][::-1]
-        stop_at_node = None
-        if self._stop_at_critical_path_number is not None and self._stop_at_critical_path_number < len(starting_points):
-            stop_at_node = starting_points[-self._stop_at_critical_path_number - 1][0]
-        if self._start_at_critical_path_number is not None and self._start_at_critical_path_number > 0:
-            starting_points = starting_points[:-self._start_at_critical_path_number]
         a = self._arrays
+        first_node = None
         if self._start_at_critical_path_number is None or self._start_at_critical_path_number == 0:
-            first_node = int(a["first_node"])
-            if int(a["seq_offsets"][first_node + 1] - a["seq_offsets"][first_node]) <= k:
-                starting_points.append((first_node, 0))
-        order = []
-        while starting_points:                       # pop() from the end, stop at the chunk boundary (kf:223-226)
-            nd, off = starting_points.pop()
-            if stop_at_node is not None and stop_at_node == nd:
-                break
-            order.append((nd, off))
+            if int(a["seq_offsets"][int(a["first_node"]) + 1] - a["seq_offsets"][int(a["first_node"])]) <= k:      # kf:212-214
+                first_node = int(a["first_node"])
+        nodes, offsets = starting_points_in_order(crit.nodes, crit.offsets, first_node, self._start_at_critical_path_number,
+                                                  self._stop_at_critical_path_number)
         if crit._index is None:
             crit._make_index()
-        self._run(order, np.asarray(crit._index), early_stop=False)
+        self._run(nodes, offsets, np.asarray(crit._index), early_stop=False)

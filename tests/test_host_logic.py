@@ -232,3 +232,35 @@ def test_follow_only_rewrites_the_edge_lists():
     # {7, 8}.intersection([7, 8]) iterates 8 first: the order of the reference's loop, not the edge order
     o, e, f = follow_only(np.array([0, 2, 2, 2, 2, 2, 2, 2, 2, 2]), np.array([7, 8], dtype=np.int32), {7, 8})
     assert list(e) == list({7, 8}.intersection([7, 8])) and list(f) == [1] + [0] * 8
+
+
+def test_finder_starting_points_in_order():
+    """kmer_finder.starting_points_in_order against the reference's list handling restated literally (kf:192-226: reverse, slice,
+    append, pop from the end, stop at the chunk boundary)."""
+    from graph_kmer_index_b200.kmer_finder import starting_points_in_order
+    rng = np.random.default_rng(4)
+    for trial in range(300):
+        n = int(rng.integers(0, 12))
+        crit_nodes = np.sort(rng.choice(40, n, replace=False)).astype(np.uint32)
+        if n and trial % 3 == 0:
+            crit_nodes[rng.integers(0, n)] = crit_nodes[0]                 # several critical positions on one node
+        crit_offsets = rng.integers(1, 50, n).astype(np.uint16)
+        start_at = [None, 0, int(rng.integers(0, 14))][trial % 3]
+        stop_at = [None, int(rng.integers(0, 14))][trial % 2]
+        first = 0 if (start_at is None or start_at == 0) and trial % 5 else None
+        starting_points = [(int(a), int(b)) for a, b in zip(crit_nodes, crit_offsets)][::-1]
+        stop_at_node = None
+        if stop_at is not None and stop_at < len(starting_points):
+            stop_at_node = starting_points[-stop_at - 1][0]
+        if start_at is not None and start_at > 0:
+            starting_points = starting_points[:-start_at]
+        if first is not None:
+            starting_points.append((first, 0))
+        want = []
+        while len(starting_points) > 0:
+            node, offset = starting_points.pop()
+            if stop_at_node is not None and stop_at_node == node:
+                break
+            want.append((node, offset))
+        nodes, offsets = starting_points_in_order(crit_nodes, crit_offsets, first, start_at, stop_at)
+        assert list(zip(nodes.tolist(), offsets.tolist())) == want, (trial, crit_nodes, start_at, stop_at, first)
