@@ -489,7 +489,10 @@ class CollisionFreeKmerIndex:
         """cfki:252-265, batched: one device lookup for the positions of every distinct k-mer."""
         unique = np.unique(self._kmers)
         entries, qidx = self.device_index().lookup_entries(unique)
-        values = np.array([max(min_frequency, other.get_frequency(int(kmer)) * multiplier) for kmer in unique])
+        if hasattr(other, "get_frequencies"):
+            values = np.maximum(min_frequency, other.get_frequencies(unique) * multiplier)
+        else:
+            values = np.array([max(min_frequency, other.get_frequency(int(kmer)) * multiplier) for kmer in unique])
         self._frequencies[entries] = values[qidx]
 
     def set_frequencies(self, skip=False):
@@ -538,6 +541,22 @@ class CollisionFreeKmerIndex:
             if nodes is not None:
                 f += int(frequencies[0])
         return f
+
+    def get_frequencies(self, kmers, include_reverse_complement=True, k=31):
+        """`get_frequency` (cfki:336-352) of every k-mer of an array in two device lookups -> int64 array."""
+        def first_hit_frequency(queries):
+            entries, qidx = self.device_index().lookup_entries(queries)
+            found = np.zeros(len(queries), dtype=np.int64)
+            if len(entries):
+                first_of_query = np.ones(len(qidx), dtype=bool)
+                first_of_query[1:] = qidx[1:] != qidx[:-1]
+                found[qidx[first_of_query]] = self._frequencies[entries[first_of_query]]     # frequencies[0] of the hits
+            return found
+        queries = _queries(kmers)
+        frequencies = first_hit_frequency(queries)
+        if include_reverse_complement:
+            frequencies += first_hit_frequency(kmer_hashes_to_reverse_complement_hash(queries, k))
+        return frequencies
 
     def _multi_get(self, kmers, max_hits):
         """Batched form of the per-k-mer loops at cfki:354-391 incl. the frequency gate of `get` (cfki:312)."""

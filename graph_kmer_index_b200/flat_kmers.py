@@ -73,9 +73,13 @@ class FlatKmers:
         return FlatKmers(hashes, nodes, ref_offsets, af)
 
     def sum_of_kmer_frequencies(self, kmer_index_with_frequencies):
+        if hasattr(kmer_index_with_frequencies, "get_frequencies"):       # one batched lookup instead of one per k-mer
+            return int(np.maximum(1, kmer_index_with_frequencies.get_frequencies(self._hashes)).sum()) if len(self._hashes) else 0
         return sum([0] + [max(1, kmer_index_with_frequencies.get_frequency(int(kmer))) for kmer in self._hashes])
 
     def maximum_kmer_frequency(self, kmer_index_with_frequencies):
+        if hasattr(kmer_index_with_frequencies, "get_frequencies"):
+            return int(kmer_index_with_frequencies.get_frequencies(self._hashes).max()) if len(self._hashes) else 0
         return max([0] + [kmer_index_with_frequencies.get_frequency(int(kmer)) for kmer in self._hashes])
 
     def get_new_without_singletons(self):
