@@ -267,7 +267,8 @@ class CounterKmerIndex:
     def from_kmer_index(cls, kmer_index, k=None):
         """cfki:20-28.  The counters live on the device in a table over the distinct index k-mers (csrc/count.cu).
         `k` (extension, optional): the k-mer length, which lets both strands of a read position share one probe."""
-        kmers = kmer_index._kmers.astype(np.int64)
+        kmers = kmer_index._kmers      # cfki:22 takes an int64 copy; 64-bit integers keep their bits, so a view serves
+        kmers = kmers.view(np.int64) if isinstance(kmers, np.ndarray) and kmers.dtype == np.uint64 else np.asarray(kmers).astype(np.int64)
         nodes = kmer_index._nodes
         device = kmer_index.device_index()
         if k is not None:

@@ -64,7 +64,7 @@ class FlatKmers:
     def from_multiple_flat_kmers(cls, flat_kmers_list):
         """flat_kmers.py:71-90 (dtypes forced to uint64 / uint32 / uint64 / float32)."""
         flat_kmers_list = list(flat_kmers_list)
-        cat = lambda arrays, dt: np.concatenate([np.asarray(a) for a in arrays]).astype(dt) if arrays else np.array([], dtype=dt)
+        cat = lambda arrays, dt: np.concatenate([np.asarray(a) for a in arrays]).astype(dt, copy=False) if arrays else np.array([], dtype=dt)
         hashes = cat([f._hashes for f in flat_kmers_list], np.uint64)
         nodes = cat([f._nodes for f in flat_kmers_list], np.uint32)
         refs = [f._ref_offsets for f in flat_kmers_list if f._ref_offsets is not None]
