@@ -264,3 +264,57 @@ def test_finder_starting_points_in_order():
             want.append((node, offset))
         nodes, offsets = starting_points_in_order(crit_nodes, crit_offsets, first, start_at, stop_at)
         assert list(zip(nodes.tolist(), offsets.tolist())) == want, (trial, crit_nodes, start_at, stop_at, first)
+
+
+def test_fastx_line_index_edge_files(tmp_path):
+    """fastx_open on small odd files, with the AVX-512 newline scan (in this process, if the CPU has it) and with the memchr
+    path (GKI_PACK_SCALAR=1 in a child process): empty lines, CRLF, no final newline, only newlines, one line, a file of
+    several MB without any newline, lines around the 64-byte steps of the scan."""
+    from graph_kmer_index_b200.read_kmers import FastxFile
+    cases = {
+        "one.fa": b"ACGT", "one_nl.fa": b"ACGT\n", "only_newlines.fa": b"\n\n\n", "header_only.fa": b">x\n", "crlf.fa": b">a\r\nAC GT \r\n\r\n>b\r\nTT",
+        "blank_lines.fa": b">a\n\nACGT\n\n\n>b\nGG\n\n", "q1.fq": b"@r\nACGT\n+\n!!!!", "q2.fq": b"@r\nACGT\n+\n!!!!\n@s\n\n+\n\n@t\nGGA\n+\n@@@\n",
+        "steps.fa": b"".join(b">" + b"h" * n + b"\n" + b"A" * (127 - n) + b"\n" for n in range(0, 127)),
+        "long_no_newline.fa": b"ACGT" * (1 << 20),
+        "long_lines.fa": b">h\n" + b"\n".join(b"C" * n for n in [1 << 20, 63, 64, 65, 1 << 21, 0, 1]),
+    }
+    expected = {}
+    for name, content in cases.items():
+        (tmp_path / name).write_bytes(content)
+        lines = content.decode().split("\n")
+        if content.endswith(b"\n"):
+            lines = lines[:-1]                       # nothing follows the last newline
+        if name.endswith(".fq"):
+            expected[name] = [l.strip() for l in lines[1::4]]
+        else:
+            expected[name] = [l.strip() for l in lines if not l.startswith(">")]
+        # the reference's own filter (read_kmers.py:16-18) on the same file
+        if not name.endswith(".fq"):
+            assert expected[name] == [l.strip() for l in open(tmp_path / name, newline="\n").readlines() if not l.startswith(">")], name
+
+    def check():
+        for name, content in cases.items():
+            with FastxFile(tmp_path / name) as f:
+                offsets, lengths = f.lines()
+                got = [content[o:o + n].decode() for o, n in zip(offsets, lengths)]
+            assert got == expected[name], (name, got[:5], expected[name][:5])
+    check()
+    script = tmp_path / "scalar.py"
+    script.write_text(textwrap.dedent("""
+        import sys
+        sys.path.insert(0, %r)
+        from graph_kmer_index_b200.read_kmers import FastxFile
+        import ast
+        cases = ast.literal_eval(open(%r).read())
+        for path, want in cases.items():
+            content = open(path, "rb").read()
+            with FastxFile(path) as f:
+                offsets, lengths = f.lines()
+            got = [content[o:o + n].decode() for o, n in zip(offsets, lengths)]
+            assert got == want, (path, got[:5], want[:5])
+        print("ok")
+    """ % (ROOT, str(tmp_path / "expected.txt"))))
+    (tmp_path / "expected.txt").write_text(repr({str(tmp_path / name): want for name, want in expected.items()}))
+    out = subprocess.run([sys.executable, str(script)], env=dict(os.environ, GKI_PACK_SCALAR="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
