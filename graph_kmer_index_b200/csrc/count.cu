@@ -1357,7 +1357,7 @@ int gki_count_fastx(gki_index_t *ix, const gki_fastx_t *fx, int32_t k, int32_t b
     int64_t total = 0;
     // lines grouped by length: the fused kernel walks equal-length rows; sequencing runs have one or a handful of lengths
     std::vector<int32_t> order_len;
-    std::vector<std::vector<int64_t>> groups;
+    std::vector<OffsetVector> groups;
     const bool uniform = !f.offsets.empty() && f.min_len == f.max_len;   // the usual case: the file's own offset array is the group
     if (uniform) {
         if (f.max_len >= k) order_len.push_back(f.max_len);
@@ -1378,7 +1378,7 @@ int gki_count_fastx(gki_index_t *ix, const gki_fastx_t *fx, int32_t k, int32_t b
     const int n_lanes = default_pack_threads();
     for (size_t g = 0; g < order_len.size(); g++) {
         const int32_t len = order_len[g];
-        const std::vector<int64_t> &rows = uniform ? f.offsets : groups[g];
+        const OffsetVector &rows = uniform ? f.offsets : groups[g];
         total += (int64_t)rows.size() * (len - k + 1) * (both_strands ? 2 : 1);
         if (n_lanes > 0 && (int64_t)rows.size() >= 4 * UNIT_READS) {
             GKI_TRY(count_reads_host_pipeline(ix, f.data, rows.data(), (int64_t)rows.size(), len, 0, k, both_strands, s, n_lanes));

@@ -2,7 +2,9 @@
 // Plain C++ (compiled by the host compiler, no CUDA), shared by count.cu's host-input pipeline and gki_pack_reads.
 #pragma once
 #include <cstdint>
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace gki {
@@ -19,6 +21,18 @@ int64_t pack_rows(const uint8_t *reads, int64_t row_stride, const int64_t *row_o
 // "avx512" or "scalar": which implementation pack_rows dispatches to on this CPU
 const char *pack_rows_isa();
 
+// std::vector whose resize() leaves new elements uninitialised: the line arrays of a large file are filled by all threads at once,
+// and a zero-fill by the resizing thread would touch (and page-fault) every page first
+template <typename T> struct DefaultInitAllocator : std::allocator<T> {
+    template <typename U> struct rebind { using other = DefaultInitAllocator<U>; };
+    template <typename U, typename... Args> void construct(U *p, Args &&...args) {
+        if constexpr (sizeof...(Args) == 0) ::new ((void *)p) U;
+        else ::new ((void *)p) U(std::forward<Args>(args)...);
+    }
+};
+using OffsetVector = std::vector<int64_t, DefaultInitAllocator<int64_t>>;
+using LengthVector = std::vector<int32_t, DefaultInitAllocator<int32_t>>;
+
 // A FASTA / FASTQ file mapped into memory with the positions of its sequence lines: FASTA -- every line that does not start
 // with '>' (what read_kmers.py:16-18 treats as a read), FASTQ (first byte '@') -- the second line of every four.  Lines are
 // stripped of surrounding blanks like the reference's line.strip().
@@ -27,8 +41,8 @@ struct FastxFile {
     const uint8_t *data = nullptr;
     size_t bytes = 0;
     int format = 0;                 // 0 FASTA, 1 FASTQ
-    std::vector<int64_t> offsets;   // start of every sequence line
-    std::vector<int32_t> lengths;   // its length after stripping
+    OffsetVector offsets;           // start of every sequence line
+    LengthVector lengths;           // its length after stripping
     int32_t max_len = 0, min_len = 0;
 };
 // NULL on failure (message in err)
