@@ -167,3 +167,12 @@ def test_kmer_counter_from_kmers(gki):
     sub = KmerCounter.from_flat_kmersv2(flat, 19999999, subsample_ratio=3)
     u3, c3 = np.unique(kmers[::3], return_counts=True)
     assert np.array_equal(sub.counter[u3], c3)
+
+
+def test_multi_value_hashtable_reference_test(gki):
+    """The reference's tests/test_multi_value_hashtable.py:5-8, verbatim expectations."""
+    from graph_kmer_index_b200.multi_value_hashtable import MultiValueHashTable
+    h = MultiValueHashTable.from_keys_and_values([1, 2, 3, 1], {"nodes": np.array([1, 2, 3, 10]), "offsets": np.array([5, 3, 2, 100])}, mod=11)
+    assert np.all(h[1]["nodes"] == [1, 10])
+    assert np.all(h[2]["offsets"] == [3])
+    assert sorted(h.get_all_keys().tolist()) == [1, 1, 2, 3] and h.get_unique_keys().tolist() == [1, 2, 3]
