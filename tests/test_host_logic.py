@@ -318,3 +318,51 @@ def test_fastx_line_index_edge_files(tmp_path):
     out = subprocess.run([sys.executable, str(script)], env=dict(os.environ, GKI_PACK_SCALAR="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                          text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == "ok", out.stderr[-2000:]
+
+
+def test_kmer_index2_host_logic_with_the_device_calls_emulated(monkeypatch):
+    """KmerIndex2 / MultiValueHashTable host logic (row numbers as the node column, frequencies from the set_frequencies pass, input
+    order per key) with the two device calls underneath replaced by the numpy oracle -- the GPU tests run the real ones."""
+    import graph_kmer_index_b200 as gki
+    import graph_kmer_index_b200.collision_free_kmer_index as cfki
+    from graph_kmer_index_b200.multi_value_hashtable import MultiValueHashTable
+
+    def build(kmers, nodes, ref, af, modulo, skip):
+        kmers, n = np.asarray(kmers), len(kmers)
+        idx = no.build_index(kmers.astype(np.uint64), nodes if nodes is not None else np.zeros(n, np.uint32),
+                             ref if ref is not None else np.zeros(n, np.uint64), af if af is not None else np.zeros(n, np.float32), modulo, skip)
+        return (idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"].view(kmers.dtype), idx["_nodes"], idx["_ref_offsets"],
+                idx["_allele_frequencies"], idx["_frequencies"])
+
+    class Device:
+        def __init__(self, index):
+            self.index = index
+
+        def lookup_entries(self, kmers):
+            entries, qidx = [], []
+            for j, kmer in enumerate(cfki._queries(kmers)):
+                bucket = int(kmer) % self.index._modulo
+                lo = int(self.index._hashes_to_index[bucket])
+                for p in range(lo, lo + int(self.index._n_kmers[bucket])):
+                    if int(self.index._kmers.view(np.uint64)[p]) == int(kmer):
+                        entries.append(p)
+                        qidx.append(j)
+            return np.array(entries, dtype=np.int64), np.array(qidx, dtype=np.int64)
+
+    monkeypatch.setattr(cfki, "build_index_arrays", build)
+    monkeypatch.setattr(cfki.CollisionFreeKmerIndex, "device_index", lambda self: Device(self))
+    h = MultiValueHashTable.from_keys_and_values([1, 2, 3, 1], {"nodes": np.array([1, 2, 3, 10]), "offsets": np.array([5, 3, 2, 100])}, mod=11)
+    assert np.all(h[1]["nodes"] == [1, 10]) and np.all(h[2]["offsets"] == [3])                 # the reference's tests/test_multi_value_hashtable.py
+    flat = gki.FlatKmers2(np.array([1, 1, 1, 2, 3, 10, 11, 2]), np.array([1, 1, 2, 2, 3, 1, 10, 5]), np.array([0, 0, 1, 2, 3, 4, 5, 6]),
+                          np.array([1, 2, 3, 4, 5, 6, 7, 8]), np.array([0.4, 0.1, 0.3, 0.4, 0.1, 0.1, 0.1, 0.1]))
+    index = gki.KmerIndex2.from_flat_kmers(flat)                                                # the reference's tests/test_indexes2.py
+    assert index.get_kmer_frequency(1) == 2 and np.all(index.get_start_nodes(1) == [1, 1, 2]) and np.all(index.get_nodes(3) == [5])
+    rng = np.random.default_rng(8)
+    n = 3000
+    flat = gki.FlatKmers2(rng.integers(0, 200, n), rng.integers(0, 30, n).astype(np.int32), rng.integers(0, 4, n).astype(np.int16),
+                          rng.integers(0, 1000, n).astype(np.int32), rng.random(n))
+    index = gki.KmerIndex2.from_flat_kmers(flat, modulo=97)
+    for kmer in np.unique(flat._hashes)[::7]:
+        rows = flat._hashes == kmer
+        assert np.array_equal(index.get_nodes(kmer), flat._nodes[rows]) and np.array_equal(index._data[kmer]["allele_frequencies"], flat._allele_frequencies[rows])
+        assert index.get_kmer_frequency(kmer) == len(set(zip(flat._start_nodes[rows].tolist(), flat._start_offsets[rows].tolist())))
