@@ -1,5 +1,5 @@
 // ingest.cpp -- CPU 2-bit packing of read rows (see ingest.h).  The wide path handles 64 bases per step with AVX-512BW
-// (two multiply-adds fold four 2-bit codes into a byte, vpmovdb gathers the 16 bytes); the scalar path is a 256-entry
+// (one byte shuffle maps letters to codes, two multiply-adds fold four 2-bit codes into a byte, vpmovdb gathers the 16 bytes); the scalar path is a 256-entry
 // table.  Which one runs is decided once from cpuid; both produce identical words.
 #include "ingest.h"
 
@@ -55,20 +55,21 @@ bool pack_row_scalar(const uint8_t *row, int32_t read_len, int words, uint64_t *
 
 #if GKI_X86
 __attribute__((target("avx512f,avx512bw"))) inline bool pack_row_avx512(const uint8_t *row, int32_t read_len, int words, uint64_t *out) {
-    const __m512i lower = _mm512_set1_epi8(0x20), three = _mm512_set1_epi8(3);
-    const __m512i letters = _mm512_broadcast_i32x4(_mm_setr_epi8('a', 'c', 'g', 't', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0));
+    // The low nibble tells the four letters apart in either case (A 1, C 3, G 7, T 4): one byte shuffle gives the code, a second one
+    // the lower-case letter that nibble stands for -- a byte is valid iff it, lower-cased, is that letter (bytes >= 128 shuffle to 0).
+    const __m512i lower = _mm512_set1_epi8(0x20);
+    const __m512i code_of = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 0, 0, 1, 3, 0, 0, 2, 0, 0, 0, 0, 0, 0, 0, 0));
+    const __m512i letter_of = _mm512_broadcast_i32x4(_mm_setr_epi8(0, 'a', 0, 'c', 't', 0, 0, 'g', 0, 0, 0, 0, 0, 0, 0, 0));
     const __m512i w8 = _mm512_set1_epi16(0x0401);        // bytes (1, 4): code pairs -> 4 bits per 16-bit lane
     const __m512i w16 = _mm512_set1_epi32(0x00100001);   // words (1, 16): -> 8 bits (4 bases) per 32-bit lane
     __mmask64 bad = 0;
     for (int c = 0; c < read_len; c += 64) {
         const int n = read_len - c < 64 ? read_len - c : 64;
         const __mmask64 in = n == 64 ? ~0ull : ((1ull << n) - 1ull);
-        const __m512i lc = _mm512_or_si512(n == 64 ? _mm512_loadu_si512(row + c) : _mm512_maskz_loadu_epi8(in, row + c), lower);
-        // (bit1 ^ bit2, bit2 ^ bit3) of the lower-case letter is a0 c1 g2 t3; the 16-bit shifts only leak into bits that are masked off
-        const __m512i code = _mm512_and_si512(_mm512_xor_si512(_mm512_srli_epi16(lc, 1), _mm512_srli_epi16(lc, 2)), three);
-        bad |= _mm512_cmpneq_epi8_mask(lc, _mm512_shuffle_epi8(letters, code)) & in;
-        const __m512i clean = _mm512_maskz_mov_epi8(in, code);                       // bytes past the read pack to zero
-        const __m128i bits = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(clean, w8), w16));   // 64 bases -> 128 bits
+        const __m512i raw = n == 64 ? _mm512_loadu_si512(row + c) : _mm512_maskz_loadu_epi8(in, row + c);
+        bad |= _mm512_cmpneq_epi8_mask(_mm512_or_si512(raw, lower), _mm512_shuffle_epi8(letter_of, raw)) & in;
+        const __m512i code = _mm512_shuffle_epi8(code_of, raw);                      // bytes past the read are 0 and pack to zero
+        const __m128i bits = _mm512_cvtepi32_epi8(_mm512_madd_epi16(_mm512_maddubs_epi16(code, w8), w16));   // 64 bases -> 128 bits
         const int w = c >> 5;
         if (w + 1 < words) _mm_storeu_si128((__m128i *)(out + w), bits);
         else _mm_storel_epi64((__m128i *)(out + w), bits);

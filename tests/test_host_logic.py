@@ -366,3 +366,23 @@ def test_kmer_index2_host_logic_with_the_device_calls_emulated(monkeypatch):
         rows = flat._hashes == kmer
         assert np.array_equal(index.get_nodes(kmer), flat._nodes[rows]) and np.array_equal(index._data[kmer]["allele_frequencies"], flat._allele_frequencies[rows])
         assert index.get_kmer_frequency(kmer) == len(set(zip(flat._start_nodes[rows].tolist(), flat._start_offsets[rows].tolist())))
+
+
+def test_pack_reads_every_byte_value():
+    """The AVX-512 packer (nibble-table shuffle) and the table-driven scalar packer classify every byte value alike: a row is clean
+    iff all its bytes are in ACGTacgt, at every position of a 64-byte step and in the masked tail."""
+    from graph_kmer_index_b200.read_kmers import pack_reads
+    L = 150
+    base = np.frombuffer(b"ACGTacgt", dtype=np.uint8)[np.random.default_rng(2).integers(0, 8, L)]
+    rows = []
+    for value in range(256):
+        for position in (0, 1, 63, 64, 127, 128, 149):
+            row = base.copy()
+            row[position] = value
+            rows.append(row)
+    reads = np.array(rows, dtype=np.uint8)
+    wide_packed, wide_dirty = pack_reads(reads, n_threads=1)
+    scalar_packed, scalar_dirty = pack_reads(reads, n_threads=1, force_scalar=True)
+    assert np.array_equal(wide_dirty, scalar_dirty) and np.array_equal(wide_packed, scalar_packed)
+    want_dirty = np.flatnonzero(~np.isin(reads, np.frombuffer(b"ACGTacgt", dtype=np.uint8)).all(axis=1))
+    assert np.array_equal(np.sort(wide_dirty), want_dirty) and len(want_dirty) == (256 - 8) * 7
