@@ -39,13 +39,17 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + _sources()
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()      # linked beside the target and renamed: a reader never sees a half-written library
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
     try:
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     except FileNotFoundError as e:
         raise GkiError("nvcc not found; libgki.so must be prebuilt in-tree (%s)" % e)
     if out.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise GkiError("nvcc failed:\n" + out.stdout)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(out.stdout)
     return LIB_PATH
@@ -95,6 +99,7 @@ _SIGNATURES = {
     "gki_synth_reads": [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp],
     "gki_calibrate_random_gather": [c_i64, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_scatter": [c_i64, c_i32, c_i64, ctypes.POINTER(ctypes.c_float)],
+    "gki_calibrate_store_groups": [c_i64, c_i32, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_copy": [c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_critical_paths": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i32, c_i32, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), c_vp],
     "gki_finder_prepare": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_i32, c_i32,

@@ -7,6 +7,7 @@ A device-resident copy of the index (``DeviceIndex``) is created lazily the firs
 import ctypes
 import gc
 import logging
+import weakref
 
 import numpy as np
 
@@ -270,10 +271,26 @@ class CounterKmerIndex:
         kmers = kmer_index._kmers      # cfki:22 takes an int64 copy; 64-bit integers keep their bits, so a view serves
         kmers = kmers.view(np.int64) if isinstance(kmers, np.ndarray) and kmers.dtype == np.uint64 else np.asarray(kmers).astype(np.int64)
         nodes = kmer_index._nodes
+        # cfki:27 gives every CounterKmerIndex a fresh zeroed Counter.  The counters live inside the device index's count table, so
+        # the first counter made from an index uses the index's cached device copy and every further one that is alive at the same
+        # time gets a device copy (and count table) of its own.
         device = kmer_index.device_index()
+        owner = getattr(kmer_index, "_counter_owner", None)
+        if owner is not None and owner() is not None and owner().counter._device is device:
+            device = DeviceIndex.from_index(kmer_index)
+            shared = False
+        else:
+            shared = True
         if k is not None:
             device.prepare_counting(k)
-        return cls(kmers, nodes, DeviceCounter(device))
+        device.reset_counts()
+        obj = cls(kmers, nodes, DeviceCounter(device))
+        if shared:
+            try:
+                kmer_index._counter_owner = weakref.ref(obj)
+            except AttributeError:        # an index-like object with __slots__: nothing to share, nothing to guard
+                pass
+        return obj
 
     def reset(self):
         """cfki:30-31 (the reference rebinds the Counter to np.zeros_like(counter); the intent -- zero every count -- is kept)."""
@@ -392,8 +409,8 @@ class KmerIndex2:
         65536 or more entries are recounted here)."""
         table = self._data._hash_table
         rows = table._nodes
-        start = (np.asarray(self._data._values["start_nodes"]).astype(np.int64) << 16) | \
-            (np.asarray(self._data._values["start_offsets"]).astype(np.int64) & 0xffff)
+        start = (np.asarray(self._data._values["start_nodes"]).astype(np.int64) << 32) | \
+            (np.asarray(self._data._values["start_offsets"]).astype(np.int64) & 0xffffffff)      # nodes < 2^31, offsets of any integer width
         start = start[rows]                                              # in the table's entry order
         # the entries are already in bucket order and the sort is stable: frequencies come back aligned with them
         frequencies = build_index_arrays(table._kmers, None, np.ascontiguousarray(start).view(np.uint64), None, table._modulo, False)[6]
@@ -426,14 +443,22 @@ class CollisionFreeKmerIndex:
         self._allele_frequencies = _allele_frequencies
         self._device = None
         self._device_key = None
+        self._device_version = 0
+        self._counter_owner = None
 
     # ---- device residency ----
+    _DEVICE_COLUMNS = ("_hashes_to_index", "_n_kmers", "_nodes", "_kmers", "_frequencies", "_ref_offsets", "_allele_frequencies")
+
+    def invalidate_device(self):
+        """Call after editing any of the host arrays in place (``index._frequencies[...] = x``): the next lookup uploads the index
+        again.  Every method of this class that changes an array does it itself.  A device copy that a CounterKmerIndex or a
+        CythonKmerIndex still holds stays alive (and keeps its counts) until they let go of it."""
+        self._device_version += 1
+
     def device_index(self):
-        key = tuple(id(getattr(self, a)) for a in ("_hashes_to_index", "_n_kmers", "_nodes", "_kmers", "_frequencies"))
+        key = (self._device_version, int(self._modulo)) + tuple(id(getattr(self, a)) for a in self._DEVICE_COLUMNS)
         if self._device is None or self._device_key != key:
-            if self._device is not None:
-                self._device.close()
-            self._device = DeviceIndex.from_index(self)
+            self._device = DeviceIndex.from_index(self)      # the previous copy is released when its last holder drops it
             self._device_key = key
         return self._device
 
@@ -443,9 +468,8 @@ class CollisionFreeKmerIndex:
         self._nodes = None
         self._kmers = None
         self._modulo = None
-        if self._device is not None:
-            self._device.close()
-            self._device = None
+        self._device = None              # closed by DeviceIndex.__del__ once no counter holds it any more
+        self._device_key = None
         gc.collect()
 
     def copy(self):
@@ -479,12 +503,15 @@ class CollisionFreeKmerIndex:
         self._nodes = self._nodes.astype(np.int32)
         self._n_kmers = self._n_kmers.astype(np.int32)
         self._modulo = np.uint64(self._modulo)
+        self.invalidate_device()
 
     def remove_ref_offsets(self):
         self._ref_offsets = np.array([0])
+        self.invalidate_device()
 
     def remove_frequencies(self):
         self._frequencies = np.array([0])
+        self.invalidate_device()
 
     def set_frequencies_using_other_index(self, other, multiplier=1, min_frequency=1):
         """cfki:252-265, batched: one device lookup for the positions of every distinct k-mer."""
@@ -495,6 +522,7 @@ class CollisionFreeKmerIndex:
         else:
             values = np.array([max(min_frequency, other.get_frequency(int(kmer)) * multiplier) for kmer in unique])
         self._frequencies[entries] = values[qidx]
+        self.invalidate_device()
 
     def set_frequencies(self, skip=False):
         """cfki:267-293 on the device (gki_index_build computes the same quantity during construction)."""
@@ -504,6 +532,7 @@ class CollisionFreeKmerIndex:
         # rebuild frequencies only: the entries are already in bucket order, a stable sort keeps them in place
         _, _, _, _, _, _, freq = build_index_arrays(self._kmers, None, self._ref_offsets, None, self._modulo, False)
         self._frequencies = freq
+        self.invalidate_device()
 
     def __contains__(self, item):
         return self.get(int(item), 100000000000)[0] is not None

@@ -16,6 +16,8 @@
 // Frequencies (cfki:267-293) are bucket-local scans over the sorted columns on both paths.
 //
 // Roofline: HBM streaming, compulsory traffic 50*N + 8*modulo bytes.
+#include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace gki {
@@ -539,6 +541,226 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
     }
 }
 
+// ---- slab build: one append-scatter into L2-friendly slabs, then every slab is ordered in shared memory -------------------
+// The 16-entry bins above make the scatter a random 32-byte store per entry (8 M open bins: every store is its own partial line
+// in L2 and in DRAM) and leave ~300 warp instructions of ordering per bin.  Here a bin is a range of `nb` consecutive buckets
+// expected to hold ~3/4 of SLAB_CAP entries, and owns a fixed-capacity slab of SLAB_CAP records:
+//   (1) scatter: bucket -> bin (multiply-high division), returning atomic on the bin's counter = slot in its slab, ONE 256-bit
+//       store.  There is no histogram pass (the capacity is fixed), and with tens of thousands of bins instead of millions the
+//       line every counter currently appends to stays in L2 until its four records have arrived: DRAM sees whole lines.
+//   (2) exclusive scan of the bin counters -> output position of every bin.
+//   (3) finish: a CTA takes a bin: ONE bulk copy (cp.async.bulk, mbarrier) brings its slab into shared memory; per-bucket counts
+//       by shared-memory atomics on packed 16-bit counters (the value returned is the record's arrival rank in its bucket);
+//       in-place exclusive scan; records of a bucket shared by several entries are ranked by input index (the stable order,
+//       whatever order the atomics produced); then the payload columns leave in output order with coalesced stores, and BOTH
+//       dense tables are written for every bucket of the bin, empty ones included (no memset, no table scatter).
+// A bin that receives more than SLAB_CAP records (tiny modulo, one k-mer repeated thousands of times) raises a flag and the build
+// falls back to the 16-entry-bin path above, then to the radix path.
+constexpr int SLAB_CAP = 2048;        // records per slab (64 KB of shared memory)
+constexpr int SLAB_THREADS = 512;
+constexpr int SLAB_NB_MAX = 16384;    // buckets per bin (packed 16-bit counters in shared memory)
+struct SlabParams {
+    FastMod fm;
+    uint64_t nb_magic;      // ceil(2^64 / nb): bucket / nb = umulhi64(bucket, nb_magic), exact for bucket < 2^32, nb <= 2^16
+    uint64_t table_len;
+    uint32_t bucket_lo, nb, n_bins, chunk;   // chunk: counters per thread in the scan (even, chunk / 2 odd: conflict-free word stride)
+    int32_t position_offset;
+};
+__device__ __forceinline__ uint32_t slab_bin_of(uint32_t bucket, const SlabParams &p) { return (uint32_t)__umul64hi((uint64_t)bucket, p.nb_magic); }
+
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+slab_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
+                    const float *__restrict__ af, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
+                    uint32_t *__restrict__ overflow) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
+        unsigned long long km[UNROLL];
+        uint32_t bin[UNROLL], bl[UNROLL], pos[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            km[u] = i < n ? __ldg(kmers + i) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            const uint32_t b = fastmod(km[u], p.fm) - p.bucket_lo;
+            bin[u] = slab_bin_of(b, p);
+            bl[u] = b - bin[u] * p.nb;
+            pos[u] = SLAB_CAP;
+            if (i < n && bin[u] < p.n_bins) pos[u] = atomicAdd(count + bin[u], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            if (i >= n) continue;
+            if (pos[u] >= (uint32_t)SLAB_CAP) {
+                *overflow = 1u;
+                continue;
+            }
+            const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
+            const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slab + (size_t)bin[u] * SLAB_CAP + pos[u]), "l"(km[u]),
+                         "l"((unsigned long long)(ref ? __ldg(ref + i) : 0ull)), "l"(nd | (a << 32)),
+                         "l"((unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32))
+                         : "memory");
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SLAB_THREADS, 2)
+slab_finish_kernel(SlabParams p, const uint32_t *__restrict__ count, const uint32_t *__restrict__ bin_start, const BinRecord *__restrict__ slab,
+                   int32_t *__restrict__ h2i, uint32_t *__restrict__ nk, uint64_t *__restrict__ kmers_o, uint32_t *__restrict__ nodes_o,
+                   uint64_t *__restrict__ ref_o, float *__restrict__ af_o, uint32_t *__restrict__ perm_o) {
+    constexpr int T = SLAB_THREADS, R = SLAB_CAP / SLAB_THREADS;
+    extern __shared__ __align__(128) unsigned char slab_smem[];
+    BinRecord *rec = (BinRecord *)slab_smem;                                  // SLAB_CAP records, filled by the bulk copy
+    uint32_t *sidx = (uint32_t *)(slab_smem + (size_t)SLAB_CAP * 32);         // input index of the record placed at a slot
+    uint16_t *order = (uint16_t *)(sidx + SLAB_CAP);                          // order[output rank] = record
+    uint32_t *cnt32 = (uint32_t *)(order + SLAB_CAP);                         // T * chunk packed 16-bit bucket counters -> offsets
+    const uint16_t *start16 = (const uint16_t *)cnt32;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t warp_tot[T / 32 + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t words = p.chunk / 2;                                       // counter words per thread
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    const bool tables_vec = (p.nb % 4 == 0) && ((((uintptr_t)h2i | (uintptr_t)nk) & 15) == 0);
+    for (uint32_t bin = blockIdx.x; bin < p.n_bins; bin += gridDim.x) {
+        const uint32_t c = min(__ldg(count + bin), (uint32_t)SLAB_CAP), gstart = __ldg(bin_start + bin);
+        if (tid == 0 && c) {
+            fence_proxy_async();
+            mbar_expect_tx(&bar, c * 32u);
+            bulk_g2s(rec, slab + (size_t)bin * SLAB_CAP, c * 32u, &bar);
+        }
+        for (uint32_t w = tid; w < words * T; w += T) cnt32[w] = 0u;
+        __syncthreads();
+        uint32_t bl[R], arr[R], idx[R];
+        if (c) {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t j = tid + r * T;
+            bl[r] = 0; arr[r] = 0; idx[r] = 0;
+            if (j < c) {
+                const unsigned long long w = rec[j].index;
+                idx[r] = (uint32_t)w;
+                bl[r] = (uint32_t)(w >> 32);
+                const uint32_t sh = (bl[r] & 1u) << 4;
+                arr[r] = (atomicAdd(cnt32 + (bl[r] >> 1), 1u << sh) >> sh) & 0xffffu;
+            }
+        }
+        __syncthreads();
+        // in-place exclusive scan of the packed counters: a thread owns `chunk` consecutive buckets
+        uint32_t sum = 0;
+        for (uint32_t w = 0; w < words; w++) {
+            const uint32_t v = cnt32[tid * words + w];
+            sum += (v & 0xffffu) + (v >> 16);
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t wv = lane < T / 32 ? warp_tot[lane] : 0u;
+            uint32_t winc = wv;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
+                if (lane >= d) winc += t;
+            }
+            if (lane < T / 32) warp_tot[lane] = winc - wv;
+        }
+        __syncthreads();
+        uint32_t run = warp_tot[warp] + inc - sum;
+        for (uint32_t w = 0; w < words; w++) {
+            const uint32_t v = cnt32[tid * words + w];
+            const uint32_t lo = run, hi = run + (v & 0xffffu);
+            run = hi + (v >> 16);
+            cnt32[tid * words + w] = lo | (hi << 16);
+        }
+        __syncthreads();
+        // slot of every record inside the bin: grouped by bucket, arrival order inside a bucket
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t j = tid + r * T;
+            if (j < c) {
+                arr[r] += start16[bl[r]];
+                sidx[arr[r]] = idx[r];
+            }
+        }
+        // both tables, every bucket of the bin (cfki:444-457): position of the run head, run length; 0 / 0 when empty
+        const uint64_t g0 = (uint64_t)bin * p.nb;
+        const uint32_t nb_here = (uint32_t)min((uint64_t)p.nb, p.table_len - g0);
+        const int32_t head0 = (int32_t)gstart + p.position_offset;
+        if (tables_vec) {
+            for (uint32_t b = tid * 4; b < nb_here; b += T * 4) {
+                const uint2 sw = *(const uint2 *)(start16 + b);
+                const uint32_t s0 = sw.x & 0xffffu, s1 = sw.x >> 16, s2 = sw.y & 0xffffu, s3 = sw.y >> 16, s4 = start16[b + 4];
+                const uint4 len = make_uint4(s1 - s0, s2 - s1, s3 - s2, s4 - s3);
+                const uint4 head = make_uint4(len.x ? head0 + s0 : 0, len.y ? head0 + s1 : 0, len.z ? head0 + s2 : 0, len.w ? head0 + s3 : 0);
+                if (b + 4 <= nb_here) {
+                    *(uint4 *)(nk + g0 + b) = len;
+                    *(uint4 *)(h2i + g0 + b) = head;
+                } else {
+                    nk[g0 + b] = len.x;
+                    h2i[g0 + b] = (int32_t)head.x;
+                    if (b + 1 < nb_here) {
+                        nk[g0 + b + 1] = len.y;
+                        h2i[g0 + b + 1] = (int32_t)head.y;
+                    }
+                    if (b + 2 < nb_here) {
+                        nk[g0 + b + 2] = len.z;
+                        h2i[g0 + b + 2] = (int32_t)head.z;
+                    }
+                }
+            }
+        } else {
+            for (uint32_t b = tid; b < nb_here; b += T) {
+                const uint32_t s0 = start16[b], len = start16[b + 1] - s0;
+                nk[g0 + b] = len;
+                h2i[g0 + b] = len ? head0 + (int32_t)s0 : 0;
+            }
+        }
+        __syncthreads();
+        // stable order inside a bucket: rank by input index among the records sharing the bucket
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t j = tid + r * T;
+            if (j < c) {
+                const uint32_t lo = start16[bl[r]], hi = start16[bl[r] + 1];
+                uint32_t rank = lo;
+                if (hi - lo > 1)
+                    for (uint32_t q = lo; q < hi; q++) rank += sidx[q] < idx[r];
+                order[rank] = (uint16_t)j;
+            }
+        }
+        __syncthreads();
+        for (uint32_t q = tid; q < c; q += T) {
+            const uint4 *src = (const uint4 *)(rec + order[q]);
+            const uint4 a = src[0], b = src[1];
+            const size_t dst = (size_t)gstart + q;
+            if (kmers_o) kmers_o[dst] = ((uint64_t)a.y << 32) | a.x;
+            if (ref_o) ref_o[dst] = ((uint64_t)a.w << 32) | a.z;
+            if (nodes_o) nodes_o[dst] = b.x;
+            if (af_o) af_o[dst] = __uint_as_float(b.y);
+            if (perm_o) perm_o[dst] = b.z;
+        }
+        __syncthreads();   // the next bin's bulk copy and counter reset overwrite what was just read
+    }
+}
+
 // set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
 // (k-mer, ref_offset) pair
 // (the bucket of entry e is the key of its sort element, or, after the binned build, kmers[e] % modulo - bucket_lo)
@@ -726,11 +948,69 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     }
     const FastMod fm = make_fastmod(modulo);
 
-    // ---- binned path (see bin_finish_kernel): applies when every bin of 2^shift buckets holds at most BIN_CAP entries ----
     bool binned = false;
     SortBuffers bufs;
     const unsigned long long *sorted = nullptr;
-    if (n >= (1 << 15) && !getenv("GKI_BUILD_RADIX")) {
+    const char *force_path = getenv("GKI_BUILD_PATH");   // tests force a path: "slab" (default first choice), "binned", "radix"
+    const bool allow_slab = !force_path || !strcmp(force_path, "slab");
+    const bool allow_binned = (!force_path || !strcmp(force_path, "binned") || !strcmp(force_path, "slab"));
+    // ---- slab path (see slab_finish_kernel): bins of nb buckets expected to hold ~3/4 of a slab ----
+    bool fold_offset = false;
+    if (n >= (1 << 15) && allow_slab) {
+        SlabParams sp;
+        sp.fm = fm;
+        sp.bucket_lo = (uint32_t)bucket_lo;
+        sp.table_len = table_len;
+        const char *mean_env = getenv("GKI_SLAB_MEAN");
+        const double mean = mean_env ? atof(mean_env) : 0.75 * SLAB_CAP;
+        double nb_f = mean * (double)table_len / (double)n;
+        uint32_t nb = nb_f >= (double)SLAB_NB_MAX ? (uint32_t)SLAB_NB_MAX : (uint32_t)nb_f;
+        nb &= ~3u;
+        if (nb < 4) nb = 4;
+        sp.nb = nb;
+        sp.nb_magic = (~0ull) / nb + 1ull;
+        const uint64_t n_bins = (table_len + nb - 1) / nb;
+        uint32_t chunk = (nb + 1 + SLAB_THREADS - 1) / SLAB_THREADS;
+        chunk += chunk & 1u;
+        if (((chunk / 2) & 1u) == 0) chunk += 2;
+        sp.chunk = chunk;
+        sp.n_bins = (uint32_t)n_bins;
+        fold_offset = !want_freq;   // the frequency pass below reads hashes_to_index as local positions
+        sp.position_offset = fold_offset ? (int32_t)position_offset : 0;
+        const size_t smem = (size_t)SLAB_CAP * 38 + (size_t)SLAB_THREADS * chunk * 2;
+        Scratch counts, starts, slab, flag;
+        if (n_bins < (1ull << 31) / SLAB_CAP * 64 && smem <= device_info().smem_optin && slab.try_alloc((size_t)n_bins * SLAB_CAP * sizeof(BinRecord), s)) {
+            GKI_TRY(counts.alloc((size_t)(n_bins + 1) * 4, s));
+            GKI_TRY(starts.alloc((size_t)(n_bins + 1) * 4, s));
+            GKI_TRY(flag.alloc(4, s));
+            GKI_CUDA(cudaMemsetAsync(counts.ptr, 0, (size_t)(n_bins + 1) * 4, s));
+            GKI_CUDA(cudaMemsetAsync(flag.ptr, 0, 4, s));
+            slab_scatter_kernel<4><<<grid_for(n, 256 * 4, device_info().sms * 8), 256, 0, s>>>(
+                n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(),
+                slab.as<BinRecord>(), flag.as<uint32_t>());
+            GKI_CHECK_LAUNCH();
+            uint32_t overflow = 0;
+            GKI_CUDA(cudaMemcpyAsync(&overflow, flag.ptr, 4, cudaMemcpyDeviceToHost, s));
+            GKI_TRY(exclusive_scan_u32(counts.as<uint32_t>(), starts.as<uint32_t>(), (int64_t)n_bins + 1, nullptr, s));
+            GKI_CUDA(cudaStreamSynchronize(s));
+            if (!overflow) {
+                GKI_CUDA(cudaFuncSetAttribute(slab_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int grid = (int)std::min<uint64_t>(n_bins, (uint64_t)device_info().sms * 2);
+                slab_finish_kernel<<<grid, SLAB_THREADS, smem, s>>>(sp, counts.as<uint32_t>(), starts.as<uint32_t>(), slab.as<BinRecord>(), o_h2i.as<int32_t>(),
+                                                                    o_nk.as<uint32_t>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(),
+                                                                    o_perm.as<uint32_t>());
+                GKI_CHECK_LAUNCH();
+                binned = true;
+            } else {
+                fold_offset = false;
+            }
+        } else {
+            fold_offset = false;
+        }
+    }
+
+    // ---- binned path (see bin_finish_kernel): applies when every bin of 2^shift buckets holds at most BIN_CAP entries ----
+    if (!binned && n >= (1 << 15) && allow_binned) {
         BinParams bp;
         bp.fm = fm;
         bp.bucket_lo = (uint32_t)bucket_lo;
@@ -832,7 +1112,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
             GKI_CHECK_LAUNCH();
         }
     }
-    if (position_offset) {
+    if (position_offset && !fold_offset) {
         add_offset_nonempty_kernel<<<grid_for((int64_t)table_len, 256 * 4, device_info().sms * 16), 256, 0, s>>>(
             o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), (int64_t)table_len, (int32_t)position_offset);
         GKI_CHECK_LAUNCH();

@@ -73,6 +73,7 @@ struct Scratch {
     cudaStream_t stream = nullptr;
     ~Scratch() { release(); }
     int alloc(size_t bytes, cudaStream_t s);
+    bool try_alloc(size_t bytes, cudaStream_t s);   // false (and no error recorded) when the pool cannot supply the bytes
     void release();
     template <typename T> T *as() { return (T *)ptr; }
 };

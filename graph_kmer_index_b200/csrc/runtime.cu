@@ -72,6 +72,17 @@ int Scratch::alloc(size_t bytes, cudaStream_t s) {
     GKI_CUDA(cudaMallocAsync(&ptr, bytes, s));
     return GKI_OK;
 }
+bool Scratch::try_alloc(size_t bytes, cudaStream_t s) {
+    release();
+    stream = s;
+    device_info();
+    if (cudaMallocAsync(&ptr, bytes ? bytes : 16, s) != cudaSuccess) {
+        ptr = nullptr;
+        cudaGetLastError();
+        return false;
+    }
+    return true;
+}
 void Scratch::release() {
     if (ptr) {
         cudaFreeAsync(ptr, stream);

@@ -135,6 +135,35 @@ __global__ void atomic_scatter_kernel(uint32_t *__restrict__ bins, uint32_t n_bi
     }
 }
 
+// scattered 32-byte stores, `group` consecutive lanes writing `group` consecutive records (group = 4: one whole 128-byte line per
+// request); launched with one 1024-thread CTA per SM on `ctas` SMs (dynamic shared memory keeps a second CTA off the SM)
+__global__ void __launch_bounds__(1024) scatter_group_kernel(uint4 *__restrict__ dst, uint32_t n_slots, int64_t n, int group) {
+    extern __shared__ unsigned char pad_smem[];
+    if (n < 0) pad_smem[threadIdx.x] = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t g = (uint32_t)(i / group), r = (uint32_t)(i % group);
+        const size_t s = (size_t)gather_slot(g, n_slots / group) * group + r;
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * s), "l"((unsigned long long)i), "l"((unsigned long long)g),
+                     "l"((unsigned long long)r), "l"(1ull)
+                     : "memory");
+    }
+}
+
+// append to n_bins cursors: streamed 8-byte key load -> returning atomic on the bin's cursor -> ONE 256-bit store at the cursor.
+// With few enough bins the open lines of all cursors stay in L2 and leave it as whole lines (the slab scatter of build.cu).
+__global__ void atomic_append256_kernel(const uint64_t *__restrict__ keys, uint32_t *__restrict__ bins, uint32_t n_bins, uint32_t per_bin,
+                                        uint4 *__restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long key = __ldg(keys + i);
+        const uint32_t b = (uint32_t)(((key >> 32) * (unsigned long long)n_bins) >> 32);
+        const uint32_t r = atomicAdd(bins + b, 1u);
+        const size_t s = (size_t)b * per_bin + (r < per_bin ? r : per_bin - 1);
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * s), "l"(key), "l"((unsigned long long)i), "l"((unsigned long long)b),
+                     "l"((unsigned long long)r)
+                     : "memory");
+    }
+}
+
 __global__ void fill_kernel(uint64_t *__restrict__ t, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) t[i] = splitmix64(i);
 }
@@ -235,15 +264,21 @@ int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t 
 }
 
 int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms) {
-    GKI_REQUIRE(n >= 1 && n < (1ll << 31) && ms && mode >= 0 && mode <= 6 && n_bins >= 0 && n_bins < (1ll << 31), GKI_ERR_INVALID,
+    GKI_REQUIRE(n >= 1 && n < (1ll << 31) && ms && mode >= 0 && mode <= 7 && n_bins >= 0 && n_bins < (1ll << 31), GKI_ERR_INVALID,
                 "gki_calibrate_scatter: bad arguments");
     GKI_REQUIRE(mode < 3 || mode == 6 || n_bins >= 1, GKI_ERR_INVALID, "gki_calibrate_scatter: the atomic modes need n_bins");
     uint4 *dst = nullptr;
     uint32_t *bins = nullptr, *sink = nullptr;
-    const uint32_t per_bin = mode == 5 ? (uint32_t)(n / n_bins) + 1 : 0;
-    const size_t dst_bytes = mode == 5 ? (size_t)n_bins * per_bin * 32 : (size_t)n * 32;
+    uint64_t *keys = nullptr;
+    const uint32_t per_bin = mode == 5 ? (uint32_t)(n / n_bins) + 1 : mode == 7 ? (uint32_t)(((n / n_bins) * 5) / 4 + 64) : 0;
+    const size_t dst_bytes = (mode == 5 || mode == 7) ? (size_t)n_bins * per_bin * 32 : (size_t)n * 32;
     if (mode <= 2 || mode >= 5) GKI_CUDA(cudaMalloc((void **)&dst, dst_bytes));
-    if (mode >= 3 && mode <= 5) {
+    if (mode == 7) {
+        GKI_CUDA(cudaMalloc((void **)&keys, (size_t)n * 8));
+        fill_kernel<<<device_info().sms * 8, 256>>>(keys, (uint64_t)n);
+        GKI_CHECK_LAUNCH();
+    }
+    if ((mode >= 3 && mode <= 5) || mode == 7) {
         GKI_CUDA(cudaMalloc((void **)&bins, (size_t)n_bins * 4));
         GKI_CUDA(cudaMemset(bins, 0, (size_t)n_bins * 4));
     }
@@ -256,7 +291,10 @@ int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms) {
         else if (mode == 2) scatter_store_kernel<<<grid, 256>>>(dst, (uint32_t)n, n, 8);
         else if (mode == 3) atomic_rank_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, n, 1, sink);
         else if (mode == 4) atomic_rank_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, n, 0, sink);
-        else atomic_scatter_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, per_bin, dst, n);
+        else if (mode == 7) {
+            cudaMemsetAsync(bins, 0, (size_t)n_bins * 4);
+            atomic_append256_kernel<<<grid, 256>>>(keys, bins, (uint32_t)n_bins, per_bin, dst, n);
+        } else atomic_scatter_kernel<<<grid, 256>>>(bins, (uint32_t)n_bins, per_bin, dst, n);
     };
     cudaEvent_t a, b;
     GKI_CUDA(cudaEventCreate(&a));
@@ -274,6 +312,33 @@ int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms) {
     cudaFree(dst);
     cudaFree(bins);
     cudaFree(sink);
+    cudaFree(keys);
+    return GKI_OK;
+}
+
+// mode bits: group (1, 2, 4, 8 lanes per run of records); n_slots: number of 32-byte slots of the destination (small = L2-resident);
+// ctas: SMs used (one 1024-thread CTA each)
+int gki_calibrate_store_groups(int64_t n, int32_t group, int64_t n_slots, int32_t ctas, float *ms) {
+    GKI_REQUIRE(n >= 1 && ms && group >= 1 && group <= 32 && n_slots >= group && n_slots < (1ll << 32) && ctas >= 1, GKI_ERR_INVALID,
+                "gki_calibrate_store_groups: bad arguments");
+    uint4 *dst = nullptr;
+    GKI_CUDA(cudaMalloc((void **)&dst, (size_t)n_slots * 32));
+    const size_t smem = 120 * 1024;
+    GKI_CUDA(cudaFuncSetAttribute(scatter_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t a, b;
+    GKI_CUDA(cudaEventCreate(&a));
+    GKI_CUDA(cudaEventCreate(&b));
+    scatter_group_kernel<<<ctas, 1024, smem>>>(dst, (uint32_t)n_slots, n, group);
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(a));
+    scatter_group_kernel<<<ctas, 1024, smem>>>(dst, (uint32_t)n_slots, n, group);
+    GKI_CHECK_LAUNCH();
+    GKI_CUDA(cudaEventRecord(b));
+    GKI_CUDA(cudaEventSynchronize(b));
+    GKI_CUDA(cudaEventElapsedTime(ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(dst);
     return GKI_OK;
 }
 

@@ -277,6 +277,8 @@ int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t 
  * atomicAdd picks a slot inside the counter's own bin of a (n_bins x n/n_bins) array and a 32-byte record is stored there;
  * 6: 32-byte records to random slots with one 256-bit store each. */
 int gki_calibrate_scatter(int64_t n, int32_t mode, int64_t n_bins, float *ms);
+/* scattered 32-byte stores where `group` consecutive lanes write consecutive records, into n_slots slots, from `ctas` SMs */
+int gki_calibrate_store_groups(int64_t n, int32_t group, int64_t n_slots, int32_t ctas, float *ms);
 int gki_calibrate_copy(int64_t bytes, float *ms);
 
 #ifdef __cplusplus

@@ -43,6 +43,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """torchrun exports OMP_NUM_THREADS=1; the bench's reference arm asks for the cores it may use instead"""
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
 def hash_reads(reads_u8, k, rc=True):
     reads_u8 = np.ascontiguousarray(reads_u8, dtype=np.uint8)
     n, L = reads_u8.shape
@@ -86,6 +91,20 @@ def build_index(kmers, nodes, ref_offsets, af, modulo, skip_frequencies=False):
     return out
 
 
+def build_index_kmers_nodes(kmers, nodes, modulo):
+    """k-mer / node columns and both tables of build_index (same order), on all host threads (bench CPU arm at 1 B entries)"""
+    kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
+    nodes = np.ascontiguousarray(nodes, dtype=np.uint32)
+    n = len(kmers)
+    out = dict(_hashes_to_index=np.empty(modulo, np.int32), _n_kmers=np.empty(modulo, np.uint32),
+               _kmers=np.empty(n, np.uint64), _nodes=np.empty(n, np.uint32), _modulo=int(modulo))
+    rc = lib().orc_build_kmers_nodes(_p(kmers, _u64p), _p(nodes, _u32p), ctypes.c_int64(n), ctypes.c_uint64(modulo),
+                                     _p(out["_hashes_to_index"], _i32p), _p(out["_n_kmers"], _u32p), _p(out["_kmers"], _u64p),
+                                     _p(out["_nodes"], _u32p))
+    assert rc == 0
+    return out
+
+
 def _index_args(index):
     h2i = np.ascontiguousarray(index["_hashes_to_index"], dtype=np.int32)
     nk = np.ascontiguousarray(index["_n_kmers"], dtype=np.uint32)
@@ -115,11 +134,13 @@ def count_reads(index, reads_u8, k, both_strands=True, entry_counts=None, prepar
     return entry_counts
 
 
-def node_counts_from_entry_counts(index, entry_counts, min_nodes=0):
+def node_counts_from_entry_counts(index, entry_counts, min_nodes=0, parallel=False, size=None):
     nodes = np.ascontiguousarray(index["_nodes"], dtype=np.uint32)
-    size = max(int(min_nodes), int(nodes.max()) + 1 if len(nodes) else 0)
+    if size is None:
+        size = max(int(min_nodes), int(nodes.max()) + 1 if len(nodes) else 0)
     out = np.zeros(size, dtype=np.float64)
-    lib().orc_node_counts(_p(nodes, _u32p), _p(entry_counts, _u32p), ctypes.c_int64(len(nodes)), _p(out, _f64p))
+    fn = lib().orc_node_counts_parallel if parallel else lib().orc_node_counts
+    fn(_p(nodes, _u32p), _p(entry_counts, _u32p), ctypes.c_int64(len(nodes)), _p(out, _f64p))
     return out
 
 

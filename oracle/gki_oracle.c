@@ -33,6 +33,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the bench's reference arm asks for the cores it may use instead */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n >= 1) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* flat_kmers.py:134-145 */
 void orc_encode(const uint8_t *seq, int64_t n, uint64_t *out) {
     for (int64_t i = 0; i < n; i++) { int v; out[i] = (uint64_t)base_code(seq[i], &v); }
@@ -138,6 +147,57 @@ int orc_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_
     return 0;
 }
 
+/* The k-mer and node columns and both tables of orc_build (same stable order, same values), built by all host threads: thread t
+ * owns a contiguous range of buckets, scans the bucket ids of every entry and places those of its range in input order.  Used by
+ * the bench's CPU arm for the human-scale index (1 B entries), where the serial counting sort above takes minutes; checked
+ * against orc_build in tests/test_oracle_golden.py. */
+int orc_build_kmers_nodes(const uint64_t *kmers, const uint32_t *nodes, int64_t n, uint64_t modulo,
+                          int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_o, uint32_t *nodes_o) {
+    uint32_t *bucket = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n > 0 ? n : 1));
+    if (!bucket) return -1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; i++) bucket[i] = (uint32_t)(kmers[i] % modulo);
+    int T = orc_num_threads();
+    int64_t *range_total = (int64_t *)calloc((size_t)T + 1, sizeof(int64_t));
+    if (!range_total) { free(bucket); return -1; }
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        int t = 0, nt = 1;
+#endif
+        uint64_t lo = modulo * (uint64_t)t / (uint64_t)nt, hi = modulo * (uint64_t)(t + 1) / (uint64_t)nt;
+        memset(n_kmers + lo, 0, sizeof(uint32_t) * (hi - lo));
+        int64_t mine = 0;
+        for (int64_t i = 0; i < n; i++) {
+            uint32_t b = bucket[i];
+            if (b >= lo && b < hi) { n_kmers[b]++; mine++; }
+        }
+        range_total[t + 1] = mine;
+#pragma omp barrier
+#pragma omp single
+        for (int q = 0; q < nt; q++) range_total[q + 1] += range_total[q];
+        int64_t run = range_total[t];
+        for (uint64_t b = lo; b < hi; b++) {          /* hashes_to_index doubles as the bucket cursor while placing */
+            hashes_to_index[b] = (int32_t)run;
+            run += n_kmers[b];
+        }
+        for (int64_t i = 0; i < n; i++) {
+            uint32_t b = bucket[i];
+            if (b >= lo && b < hi) {
+                int64_t p = hashes_to_index[b]++;
+                kmers_o[p] = kmers[i];
+                nodes_o[p] = nodes[i];
+            }
+        }
+        for (uint64_t b = lo; b < hi; b++) hashes_to_index[b] = n_kmers[b] ? hashes_to_index[b] - (int32_t)n_kmers[b] : 0;
+    }
+    free(range_total);
+    free(bucket);
+    return 0;
+}
+
 /* Probe of one query, cython_kmer_index.pyx:57-72 / collision_free_kmer_index.py:303-309, without
  * the .pyx's three gates: every entry of the bucket whose k-mer equals the query gets +1.
  * Afterwards counts[e] == counter[kmers[e]] of CounterKmerIndex (cfki:33-40). */
@@ -185,6 +245,16 @@ void orc_count_reads(const int32_t *h2i, const uint32_t *nk, const uint64_t *ikm
 /* cfki:39-40: np.bincount(nodes, weights=counter[kmers], minlength) */
 void orc_node_counts(const uint32_t *nodes, const uint32_t *entry_counts, int64_t n, double *out) {
     for (int64_t e = 0; e < n; e++) out[nodes[e]] += (double)entry_counts[e];
+}
+/* the same on all host threads (integer-valued additions below 2^53 are exact in any order) */
+void orc_node_counts_parallel(const uint32_t *nodes, const uint32_t *entry_counts, int64_t n, double *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < n; e++) {
+        if (!entry_counts[e]) continue;
+        double w = (double)entry_counts[e];
+#pragma omp atomic
+        out[nodes[e]] += w;
+    }
 }
 
 /* cython_kmer_index.pyx:47-109, two passes, gates optional. out may be NULL (count only).

@@ -119,3 +119,65 @@ def test_bionumpy_hash_and_structural_variant_kmers(gki):
     assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("AAAAA")) == [1])
     assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("GGGGA")) == [3])
     assert np.all(index.get_nodes(gki.sequence_to_kmer_hash("AAACC")) == [3])
+
+
+def test_every_counter_has_its_own_zeroed_counts(gki, index):
+    """cfki:27: each CounterKmerIndex.from_kmer_index gets a fresh Counter -- two samples counted against one index do not mix"""
+    idx, flat, k = index
+    first = gki.CounterKmerIndex.from_kmer_index(idx)
+    first.count_kmers(idx._kmers[:50])
+    a = first.get_node_counts()
+    assert a.sum() > 0
+    second = gki.CounterKmerIndex.from_kmer_index(idx)              # while `first` is alive: starts from zero, counts separately
+    assert second.get_node_counts().sum() == 0
+    second.count_kmers(idx._kmers[50:60])
+    b = second.get_node_counts()
+    assert np.array_equal(first.get_node_counts(), a)
+    third = gki.CounterKmerIndex.from_kmer_index(idx)
+    third.count_kmers(idx._kmers[:50])
+    third.count_kmers(idx._kmers[50:60])
+    assert np.array_equal(third.get_node_counts(), a + b)
+    del first, second, third
+    again = gki.CounterKmerIndex.from_kmer_index(idx)               # nobody holds the cached device copy any more: reused, but reset
+    assert again.get_node_counts().sum() == 0
+
+
+def test_device_copy_follows_edits_of_the_host_arrays(gki):
+    """in-place edits + invalidate_device(), and the methods that rebind or edit arrays themselves"""
+    g = load_golden("index_small")
+    flat = gki.FlatKmers(g["in_hashes"], g["in_nodes"], g["in_ref_offsets"], g["in_allele_frequencies"])
+    idx = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=int(g["stable_modulo"]))
+    cy = gki.CythonKmerIndex(idx) if hasattr(gki, "CythonKmerIndex") else None
+    q = idx._kmers[:200].copy()
+    before = idx.device_index().lookup_hits(q, skip_bucket0=False, max_bucket=None, max_frequency=20)
+    assert before.shape[1] > 0
+    idx._frequencies[:] = 1000                                      # in-place edit: every hit is gated out after invalidation
+    idx.invalidate_device()
+    after = idx.device_index().lookup_hits(q, skip_bucket0=False, max_bucket=None, max_frequency=20)
+    assert after.shape[1] == 0
+    idx.set_frequencies()                                           # rebinds and invalidates itself
+    again = idx.device_index().lookup_hits(q, skip_bucket0=False, max_bucket=None, max_frequency=20)
+    assert np.array_equal(again, before)
+    counter = gki.CounterKmerIndex.from_kmer_index(idx)
+    counter.count_kmers(q)
+    want = counter.get_node_counts()
+    idx.remove_frequencies()                                        # a new device copy for the index; the counter keeps its own, with its counts
+    assert idx.device_index() is not counter.counter._device
+    assert np.array_equal(counter.get_node_counts(), want)
+    del cy
+
+
+def test_kmer_index2_frequencies_with_wide_offsets(gki):
+    """start offsets wider than 16 bits stay distinct in count_unique_kmer_occurences (cfki:148-158)"""
+    from graph_kmer_index_b200.collision_free_kmer_index import KmerIndex2
+
+    class Flat2:
+        pass
+    f = Flat2()
+    f._hashes = np.array([5, 5, 5, 9, 9], dtype=np.uint64)
+    f._nodes = np.array([1, 2, 3, 4, 5], dtype=np.uint32)
+    f._start_nodes = np.array([7, 7, 7, 8, 8], dtype=np.int32)
+    f._start_offsets = np.array([3, 3 + 65536, 3, 10, 10], dtype=np.int32)
+    f._allele_frequencies = np.ones(5, dtype=np.float32)
+    idx = KmerIndex2.from_flat_kmers(f, modulo=101)
+    assert idx.get_kmer_frequency(5) == 2 and idx.get_kmer_frequency(9) == 1

@@ -386,3 +386,28 @@ def test_pack_reads_every_byte_value():
     assert np.array_equal(wide_dirty, scalar_dirty) and np.array_equal(wide_packed, scalar_packed)
     want_dirty = np.flatnonzero(~np.isin(reads, np.frombuffer(b"ACGTacgt", dtype=np.uint8)).all(axis=1))
     assert np.array_equal(np.sort(wide_dirty), want_dirty) and len(want_dirty) == (256 - 8) * 7
+
+
+def test_reference_module_paths_and_nplist():
+    """graph_kmer_index/__init__.py:1-12 and the modules KAGE imports from: snp_kmer_finder, critical_graph_paths, nplist"""
+    import importlib
+    for module, names in (("snp_kmer_finder", ("kmer_to_hash_fast", "sequence_to_kmer_hash", "kmer_hash_to_sequence")),
+                          ("critical_graph_paths", ("CriticalGraphPaths",)), ("nplist", ("NpList",)),
+                          ("flat_kmers", ("FlatKmers", "letter_sequence_to_numeric", "numeric_to_letter_sequence"))):
+        mod = importlib.import_module("graph_kmer_index_b200." + module)
+        for name in names:
+            assert hasattr(mod, name), (module, name)
+    from graph_kmer_index_b200.nplist import NpList
+    a = NpList(dtype=np.int64)
+    for i in range(250):
+        a.append(i)
+    a.extend(np.array([7, 8, 9]))
+    assert len(a) == 253 and a[-1] == 9 and a[100] == 100 and a.get_nparray().dtype == np.int64
+    b = a.copy()
+    assert b == a and len(b) == 253
+    a.set_n_elements(10)
+    assert len(a) == 10 and a.get_nparray().tolist() == list(range(10))
+    c = NpList()
+    c.append(5)
+    c.append(7)
+    assert c.get_nparray().tolist() == [5, 7]

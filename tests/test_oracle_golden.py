@@ -169,3 +169,22 @@ def test_side_indexes_golden():
         want = g["seq_k%d_kmers" % k]
         assert np.array_equal(no.read_kmer_hashes(seq, k).astype(want.dtype), want)
         assert np.array_equal(g["seq_k%d_index" % k], np.arange(len(seq), dtype=np.uint32))
+
+
+@pytest.mark.parametrize("n,modulo", [(1, 1), (1000, 7), (50_000, 65_521), (400_000, 1_000_003)])
+def test_parallel_bench_helpers_equal_the_serial_oracle(n, modulo):
+    """the all-threads builder / node-count pass the bench's CPU arm uses at 1 B entries are the serial oracle's results"""
+    from graph_kmer_index_b200 import synthetic
+    h, nd, ref, af = synthetic.flat_kmers(n, max(n // 10, 1), 31)
+    h = h.copy()
+    h[::7] = h[0]
+    want = c_oracle.build_index(h, nd, ref, af, modulo, skip_frequencies=True)
+    got = c_oracle.build_index_kmers_nodes(h, nd, modulo)
+    for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes"):
+        assert np.array_equal(want[key], got[key]), key
+    ec = np.random.default_rng(n).integers(0, 3, n).astype(np.uint32)
+    assert np.array_equal(c_oracle.node_counts_from_entry_counts(want, ec), c_oracle.node_counts_from_entry_counts(want, ec, parallel=True))
+    before = c_oracle.num_threads()
+    c_oracle.set_num_threads(2)
+    assert c_oracle.num_threads() == 2
+    c_oracle.set_num_threads(before)
