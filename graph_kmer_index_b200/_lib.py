@@ -13,9 +13,9 @@ import numpy as np
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.path.join(_PKG, "libgki.so")
-SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "count.cu", "build.cu", "synth.cu", "finder.cu", "ingest.cpp"]
+SOURCES = ["runtime.cu", "scan.cu", "hash.cu", "index.cu", "count.cu", "build.cu", "synth.cu", "finder.cu", "comm.cu", "ingest.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared", "-lpthread"]
+              "-Xcompiler", "-fPIC", "-shared", "-lpthread", "-ldl"]
 
 
 class GkiError(RuntimeError):
@@ -80,6 +80,7 @@ _SIGNATURES = {
     "gki_prepare_counting": [c_vp, c_i32, c_vp],
     "gki_pack_reads": [c_vp, c_i64, c_i32, c_i64, c_vp, c_vp, c_i64, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_i32, c_i32],
     "gki_count_packed_reads": [c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_vp],
+    "gki_host_read_bandwidth": [c_vp, c_i64, c_i32, ctypes.POINTER(ctypes.c_double)],
     "gki_fastx_open": [ctypes.c_char_p, ctypes.POINTER(c_vp), ctypes.POINTER(c_i64), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)],
     "gki_fastx_lines": [c_vp, c_vp, c_vp],
     "gki_count_fastx": [c_vp, c_vp, c_i32, c_i32, ctypes.POINTER(c_i64), c_vp],
@@ -98,6 +99,11 @@ _SIGNATURES = {
     "gki_synth_flat_kmers": [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gki_synth_reads": [c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_i32, c_vp, c_vp],
     "gki_calibrate_random_gather": [c_i64, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
+    "gki_nccl_unique_id": [c_vp],
+    "gki_nccl_comm_create": [c_vp, c_i32, c_i32, ctypes.POINTER(c_vp)],
+    "gki_nccl_comm_destroy": [c_vp],
+    "gki_allreduce_counts": [c_vp, c_vp, c_i64, c_i32, c_vp],
+    "gki_release_scratch": [],
     "gki_calibrate_scatter": [c_i64, c_i32, c_i64, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_store_groups": [c_i64, c_i32, c_i64, c_i32, ctypes.POINTER(ctypes.c_float)],
     "gki_calibrate_copy": [c_i64, ctypes.POINTER(ctypes.c_float)],
@@ -112,6 +118,7 @@ EXPORTED = [n for n in _SIGNATURES] + ["gki_last_error", "gki_version", "gki_lau
 GKI_BUILD_SKIP_FREQUENCIES = 1
 GKI_COUNTS_WRAP_UINT16 = 1
 GKI_PROBE_SKIP_BUCKET0 = 1
+GKI_COUNTS_FLOAT64, GKI_COUNTS_UINT64 = 0, 1
 
 _lib = None
 

@@ -568,19 +568,30 @@ struct SlabParams {
 };
 __device__ __forceinline__ uint32_t slab_bin_of(uint32_t bucket, const SlabParams &p) { return (uint32_t)__umul64hi((uint64_t)bucket, p.nb_magic); }
 
-template <int UNROLL>
+// HINT (experiment, GKI_SLAB_HINT): L2 eviction priority of the slab stores (1: evict_last, 3: evict_normal stated explicitly,
+// 4: evict_first) and, with bit 3 (8) added, evict_first on the streamed input loads
+template <int UNROLL, int HINT>
 __global__ void __launch_bounds__(256)
 slab_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
                     const float *__restrict__ af, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
                     uint32_t *__restrict__ overflow) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    unsigned long long pol_st = 0, pol_ld = 0;
+    if ((HINT & 7) == 1) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_st));
+    if ((HINT & 7) == 3) asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_st));
+    if ((HINT & 7) == 4) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
+    if (HINT & 8) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ld));
     for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
         unsigned long long km[UNROLL];
         uint32_t bin[UNROLL], bl[UNROLL], pos[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
-            km[u] = i < n ? __ldg(kmers + i) : 0ull;
+            km[u] = 0ull;
+            if (i < n) {
+                if (HINT & 8) asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(km[u]) : "l"(kmers + i), "l"(pol_ld));
+                else km[u] = __ldg(kmers + i);
+            }
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
@@ -601,10 +612,15 @@ slab_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_
             }
             const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
             const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
-            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slab + (size_t)bin[u] * SLAB_CAP + pos[u]), "l"(km[u]),
-                         "l"((unsigned long long)(ref ? __ldg(ref + i) : 0ull)), "l"(nd | (a << 32)),
-                         "l"((unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32))
-                         : "memory");
+            const unsigned long long r = ref ? __ldg(ref + i) : 0ull;
+            const unsigned long long tag = (unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32);
+            BinRecord *dst = slab + (size_t)bin[u] * SLAB_CAP + pos[u];
+            if (HINT & 7)
+                asm volatile("st.global.L2::cache_hint.v4.u64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "l"(km[u]), "l"(r), "l"(nd | (a << 32)), "l"(tag),
+                             "l"(pol_st)
+                             : "memory");
+            else
+                asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(km[u]), "l"(r), "l"(nd | (a << 32)), "l"(tag) : "memory");
         }
     }
 }
@@ -985,9 +1001,20 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
             GKI_TRY(flag.alloc(4, s));
             GKI_CUDA(cudaMemsetAsync(counts.ptr, 0, (size_t)(n_bins + 1) * 4, s));
             GKI_CUDA(cudaMemsetAsync(flag.ptr, 0, 4, s));
-            slab_scatter_kernel<4><<<grid_for(n, 256 * 4, device_info().sms * 8), 256, 0, s>>>(
-                n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(),
-                slab.as<BinRecord>(), flag.as<uint32_t>());
+            const int hint = getenv("GKI_SLAB_HINT") ? atoi(getenv("GKI_SLAB_HINT")) : 0;
+            const int sgrid = grid_for(n, 256 * 4, device_info().sms * 8);
+#define GKI_SLAB_SCATTER(H)                                                                                                              \
+    slab_scatter_kernel<4, H><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), \
+                                                    sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>())
+            switch (hint) {
+                case 1: GKI_SLAB_SCATTER(1); break;
+                case 3: GKI_SLAB_SCATTER(3); break;
+                case 4: GKI_SLAB_SCATTER(4); break;
+                case 9: GKI_SLAB_SCATTER(9); break;
+                case 8: GKI_SLAB_SCATTER(8); break;
+                default: GKI_SLAB_SCATTER(0); break;
+            }
+#undef GKI_SLAB_SCATTER
             GKI_CHECK_LAUNCH();
             uint32_t overflow = 0;
             GKI_CUDA(cudaMemcpyAsync(&overflow, flag.ptr, 4, cudaMemcpyDeviceToHost, s));

@@ -15,9 +15,10 @@
 //   * bucketised open-addressing table over the distinct k-mers: bucket = key[4] | cnt[4][2] = 64 bytes, two buckets
 //     per 128-byte line (a full bucket overflows into its line mate first); a probe reads the four keys with ONE
 //     256-bit load, a hit adds one RED on the other half of the bucket.
-//   * canonical keys: key = min(x, revcomp_k(x)), cnt[o] with o = (x != key).  The forward and reverse-complement
+//   * canonical keys: key = min(x, revcomp_k(x)), one count per orientation o = (x != key).  The forward and reverse-complement
 //     hashes of a read position share the key, so a position (2 queries) costs one filter access, at most one
-//     table access and one 64-bit RED (+1 on both orientations).
+//     table access and one 32-bit RED (cnt[0] counts orientation 0, cnt[1] holds the DIFFERENCE of the two orientations,
+//     so "+1 on both" touches cnt[0] alone and no carry can run between the two counts; see add_both_orientations).
 //   * multiply-fold hash + multiply-high range reduction: no 64-bit modulo in the hot loop.
 //
 // The fused kernel is warp-autonomous: every warp streams its own tiles of reads into shared memory with TMA
@@ -218,18 +219,35 @@ __device__ __forceinline__ unsigned long long slot_id(const TableView &t, const 
 __device__ __forceinline__ uint32_t *slot_counters(const TableView &t, unsigned long long slot) {
     return t.buckets[slot >> 2].cnt[slot & 3];
 }
+// Counter pair of a slot: cnt[0] = count of orientation 0, cnt[1] = count of orientation 1 MINUS count of orientation 0, both
+// modulo 2^32.  A read position counted on both strands adds one to each orientation, i.e. +1 on cnt[0] alone: one 32-bit RED,
+// and no carry can run from one orientation's count into the other's (a single 64-bit add of {1, 1} on two plain counters did
+// exactly that after 2^32 hits).  Every orientation's count is exact modulo 2^32 (the reference's Counter wraps at 2^16, cfki:27).
+__device__ __forceinline__ void add_both_orientations(uint32_t *cnt, uint32_t n) { atomicAdd(cnt, n); }
+__device__ __forceinline__ void add_one_orientation(const TableView &t, uint32_t *cnt, uint32_t o) {
+    if (o) {
+        atomicAdd(cnt + 1, 1u);
+    } else {
+        atomicAdd(cnt, 1u);
+        if (t.k) atomicAdd(cnt + 1, 0xffffffffu);   // raw keys (k == 0) have orientation 0 only: the difference is never read
+    }
+}
+__device__ __forceinline__ uint32_t read_orientation(const uint32_t *cnt, uint32_t o) {
+    const uint32_t a = *(const volatile uint32_t *)cnt;
+    return o ? a + *(const volatile uint32_t *)(cnt + 1) : a;
+}
 
 // one independent query
 __device__ __forceinline__ void count_one(const TableView &t, uint64_t q) {
     Key key = make_key(q, t.k);
     if (!key.ok) return;
     Hash h = hash_key(key.c);
-    if (t.filter) {
+    if (t.filter && key.c != SLOT_EMPTY) {   // the value that collides with the empty marker has its own bucket and no filter bits
         uint32_t m = filter_mask(t, h);
         if ((__ldg(t.filter + filter_word_of(t, h, key.c)) & m) != m) return;
     }
     uint32_t *cnt = find_slot(t, key.c, h);
-    if (cnt) atomicAdd(cnt + key.o, 1u);
+    if (cnt) add_one_orientation(t, cnt, key.o);
 }
 
 // ------------------------------------------------------------------ table construction
@@ -309,7 +327,7 @@ __global__ void __launch_bounds__(COUNT_THREADS) count_kmers_kernel(TableView t,
             const uint32_t idx = (qhead + lane) & (CK_QCAP - 1);
             const uint32_t meta = qmeta[idx];
             uint32_t *cnt = find_slot_from(t, qkey[idx], meta & 0x7fffffffu);
-            if (cnt) atomicAdd(cnt + (meta >> 31), 1u);
+            if (cnt) add_one_orientation(t, cnt, meta >> 31);
         }
         qhead += n;
         __syncwarp();
@@ -419,10 +437,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             const unsigned long long key = qkey[idx];
             const uint32_t meta = qmeta[idx];
             uint32_t *cnt = find_slot_from<(HINTS & 2) ? 1 : ((HINTS & 64) ? 2 : 0)>(t, key, meta & 0x7fffffffu, pol_first);
-            if (cnt) {
-                if (!KODD && (meta >> 31)) atomicAdd(cnt, 2u);                                   // palindrome (even k)
-                else atomicAdd((unsigned long long *)cnt, 0x0000000100000001ull);                // +1 on both orientations
-            }
+            if (cnt) add_both_orientations(cnt, (!KODD && (meta >> 31)) ? 2u : 1u);   // palindrome (even k): both strands are orientation 0
         }
         qhead += n;
         __syncwarp();
@@ -636,7 +651,7 @@ __device__ __forceinline__ uint32_t kmer_count(const TableView &t, uint64_t km, 
     uint32_t w = 0;
     if (key.ok) {
         uint32_t *cnt = find_slot(t, key.c, hash_key(key.c));
-        if (cnt) w = *(volatile uint32_t *)(cnt + key.o);
+        if (cnt) w = read_orientation(cnt, key.o);
     }
     return wrap16 ? (w & 0xFFFFu) : w;
 }
@@ -673,7 +688,7 @@ __global__ void node_counts_csr_kernel(TableView t, const uint32_t *__restrict__
                                        double *__restrict__ out, int64_t n_out, bool wrap16) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t nd = __ldg(cs_node + i);
-        uint32_t w = *(volatile uint32_t *)(slot_counters(t, __ldg(cs_slot + i)) + (nd >> 31));
+        uint32_t w = read_orientation(slot_counters(t, __ldg(cs_slot + i)), nd >> 31);
         if (wrap16) w &= 0xFFFFu;
         const uint32_t node = nd & 0x7fffffffu;
         if (w && (int64_t)node < n_out) atomicAdd(out + node, (double)w);
@@ -725,63 +740,81 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     GKI_REQUIRE(buckets < (1ull << 31), GKI_ERR_UNSUPPORTED, "count table: too many distinct k-mers");
     t.n_buckets = (uint32_t)buckets;
     const size_t n_slots = ((size_t)buckets + 1) * SLOTS_PER_BUCKET;
-    GKI_CUDA(cudaMalloc((void **)&t.buckets, ((size_t)buckets + 1) * sizeof(Bucket)));
-    ix->table_bytes = ((size_t)buckets + 1) * sizeof(Bucket);
-    table_init_kernel<<<grid_for((int64_t)(buckets + 1) * 8, 256 * 4, device_info().sms * 16), 256, 0, s>>>(t.buckets, (size_t)buckets + 1);
-    GKI_CHECK_LAUNCH();
-
-    // Bloom filter: as many bits per key as fit the L2 budget (<= 16); below 1.5 bits per key it filters nothing
-    size_t budget = (size_t)32 << 20;   // measured optimum at c2 (profiles/r1/tune_filter_v4.jsonl): flat from 32 to 40 MB, worse
-                                        // below (false positives) and above (the filter starts missing L2)
-    if (const char *e = getenv("GKI_FILTER_MAX_MB")) budget = (size_t)atoi(e) << 20;
-    size_t want = (size_t)distinct * 2;                  // 16 bits per key
-    // Indexes too large for an L2-resident filter still profit from an HBM-resident one at 8 bits per key (measured at
-    // 500 M distinct k-mers: kernel 297 ms without, 164 ms with a 512 MB filter): a filter miss costs one small fetch
-    // from a compact region instead of a bucket line from the 32x larger table.
-    if (!getenv("GKI_FILTER_MAX_MB") && (size_t)distinct > budget) budget = (size_t)distinct;
-    size_t fbytes = want < budget ? want : budget;
-    fbytes = (fbytes + 31) & ~(size_t)31;   // whole 32-byte sectors
-    if (fbytes < 64) fbytes = 64;
-    double bits_per_key = distinct ? (double)fbytes * 8.0 / (double)distinct : 16.0;
-    uint32_t *filter = nullptr;
-    if (budget > 0 && bits_per_key >= 1.5) {
-        GKI_CUDA(cudaMalloc((void **)&filter, fbytes));
-        GKI_CUDA(cudaMemsetAsync(filter, 0, fbytes, s));
-        t.filter = filter;
-        t.filter_words = (uint32_t)(fbytes / 4);
-        // a filter that cannot stay in L2 is addressed by minimizer (odd k in 27..31: 17 m-mers of m = k - 16 <= 15 bases)
-        const bool mz_possible = k >= 27 && k <= 31 && (k & 1);
-        bool mz = mz_possible && fbytes > ((size_t)48 << 20);
-        if (const char *e = getenv("GKI_FILTER_MZ")) mz = mz_possible && atoi(e) != 0;
-        t.filter_m = mz ? k - 16 : 0;
-        t.filter_k = bits_per_key >= 5.0 ? 3 : (bits_per_key >= 3.0 ? 2 : 1);
-        if (const char *e = getenv("GKI_FILTER_K")) t.filter_k = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
-        ix->filter_bytes = fbytes;
-    }
-    table_insert_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, filter, (unsigned int *)counters.ptr + 2);
-    GKI_CHECK_LAUNCH();
+    // Everything is built into locals: the table, the slot-ordered entry list and the byte counts are published together once
+    // every step has succeeded, so a failed build (an allocation, an insertion) leaves no half-made table for the next call to find.
+    uint32_t *cs_slot = nullptr, *cs_node = nullptr, *filter = nullptr;
+    size_t table_bytes = ((size_t)buckets + 1) * sizeof(Bucket), filter_bytes = 0;
     unsigned int failed = 0;
-    GKI_CUDA(cudaMemcpyAsync(&failed, (unsigned int *)counters.ptr + 2, 4, cudaMemcpyDeviceToHost, s));
-    GKI_CUDA(cudaStreamSynchronize(s));
-    ix->table = t;
-    GKI_REQUIRE(failed == 0, GKI_ERR_CUDA, "count table: %u insertions failed", failed);
-    // regroup the entries by slot (one-time sort) so that get_node_counts reads the counters in table order
-    if (n_slots < (1ull << 32) && ix->max_node < (1ll << 31) && !getenv("GKI_NO_CSR")) {
-        Scratch a, b, hist;
-        GKI_TRY(a.alloc((size_t)ix->n * 8, s));
-        entry_slots_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, a.as<unsigned long long>());
+    auto build_rest = [&]() -> int {
+        GKI_CUDA(cudaMalloc((void **)&t.buckets, ((size_t)buckets + 1) * sizeof(Bucket)));
+        table_init_kernel<<<grid_for((int64_t)(buckets + 1) * 8, 256 * 4, device_info().sms * 16), 256, 0, s>>>(t.buckets, (size_t)buckets + 1);
         GKI_CHECK_LAUNCH();
-        int bits = 1;
-        while ((1ull << bits) < n_slots) bits++;
-        const unsigned long long *sorted = nullptr;
-        GKI_TRY(radix_sort_packed(a, b, hist, ix->n, bits, &sorted, s));
-        GKI_CUDA(cudaMalloc((void **)&ix->cs_slot, (size_t)ix->n * 4));
-        GKI_CUDA(cudaMalloc((void **)&ix->cs_node, (size_t)ix->n * 4));
-        csr_fill_kernel<<<grid_n, 256, 0, s>>>(t, sorted, ix->kmers, ix->nodes, ix->n, ix->cs_slot, ix->cs_node);
+
+        // Bloom filter: as many bits per key as fit the L2 budget (<= 16); below 1.5 bits per key it filters nothing
+        size_t budget = (size_t)32 << 20;   // measured optimum at c2 (profiles/r1/tune_filter_v4.jsonl): flat from 32 to 40 MB, worse
+                                            // below (false positives) and above (the filter starts missing L2)
+        if (const char *e = getenv("GKI_FILTER_MAX_MB")) budget = (size_t)atoi(e) << 20;
+        size_t want = (size_t)distinct * 2;                  // 16 bits per key
+        // Indexes too large for an L2-resident filter still profit from an HBM-resident one at 8 bits per key (measured at
+        // 500 M distinct k-mers: kernel 297 ms without, 164 ms with a 512 MB filter): a filter miss costs one small fetch
+        // from a compact region instead of a bucket line from the 32x larger table.
+        if (!getenv("GKI_FILTER_MAX_MB") && (size_t)distinct > budget) budget = (size_t)distinct;
+        size_t fbytes = want < budget ? want : budget;
+        fbytes = (fbytes + 31) & ~(size_t)31;   // whole 32-byte sectors
+        if (fbytes < 64) fbytes = 64;
+        double bits_per_key = distinct ? (double)fbytes * 8.0 / (double)distinct : 16.0;
+        if (budget > 0 && bits_per_key >= 1.5) {
+            GKI_CUDA(cudaMalloc((void **)&filter, fbytes));
+            GKI_CUDA(cudaMemsetAsync(filter, 0, fbytes, s));
+            t.filter = filter;
+            t.filter_words = (uint32_t)(fbytes / 4);
+            // a filter that cannot stay in L2 is addressed by minimizer (odd k in 27..31: 17 m-mers of m = k - 16 <= 15 bases)
+            const bool mz_possible = k >= 27 && k <= 31 && (k & 1);
+            bool mz = mz_possible && fbytes > ((size_t)48 << 20);
+            if (const char *e = getenv("GKI_FILTER_MZ")) mz = mz_possible && atoi(e) != 0;
+            t.filter_m = mz ? k - 16 : 0;
+            t.filter_k = bits_per_key >= 5.0 ? 3 : (bits_per_key >= 3.0 ? 2 : 1);
+            if (const char *e = getenv("GKI_FILTER_K")) t.filter_k = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
+            filter_bytes = fbytes;
+        }
+        table_insert_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, filter, (unsigned int *)counters.ptr + 2);
         GKI_CHECK_LAUNCH();
+        GKI_CUDA(cudaMemcpyAsync(&failed, (unsigned int *)counters.ptr + 2, 4, cudaMemcpyDeviceToHost, s));
         GKI_CUDA(cudaStreamSynchronize(s));
-        ix->table_bytes += (size_t)ix->n * 8;
+        GKI_REQUIRE(failed == 0, GKI_ERR_CUDA, "count table: %u insertions failed", failed);
+        // regroup the entries by slot (one-time sort) so that get_node_counts reads the counters in table order
+        if (n_slots < (1ull << 32) && ix->max_node < (1ll << 31) && !getenv("GKI_NO_CSR")) {
+            Scratch a, b, hist;
+            GKI_TRY(a.alloc((size_t)ix->n * 8, s));
+            entry_slots_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, a.as<unsigned long long>());
+            GKI_CHECK_LAUNCH();
+            int bits = 1;
+            while ((1ull << bits) < n_slots) bits++;
+            const unsigned long long *sorted = nullptr;
+            GKI_TRY(radix_sort_packed(a, b, hist, ix->n, bits, &sorted, s));
+            GKI_CUDA(cudaMalloc((void **)&cs_slot, (size_t)ix->n * 4));
+            GKI_CUDA(cudaMalloc((void **)&cs_node, (size_t)ix->n * 4));
+            csr_fill_kernel<<<grid_n, 256, 0, s>>>(t, sorted, ix->kmers, ix->nodes, ix->n, cs_slot, cs_node);
+            GKI_CHECK_LAUNCH();
+            GKI_CUDA(cudaStreamSynchronize(s));
+            table_bytes += (size_t)ix->n * 8;
+        }
+        return GKI_OK;
+    };
+    const int rc = build_rest();
+    if (rc != GKI_OK) {
+        cudaStreamSynchronize(s);
+        cudaFree(t.buckets);
+        cudaFree(filter);
+        cudaFree(cs_slot);
+        cudaFree(cs_node);
+        return rc;
     }
+    ix->table = t;
+    ix->filter_bytes = filter_bytes;
+    ix->cs_slot = cs_slot;
+    ix->cs_node = cs_node;
+    ix->table_bytes = table_bytes;
     return GKI_OK;
 }
 
@@ -1263,6 +1296,41 @@ int gki_count_reads(gki_index_t *ix, const uint8_t *reads, int64_t n_reads, int3
         GKI_CUDA(cudaEventRecord(ix->done[bsel], s));
     }
     GKI_CUDA(cudaStreamSynchronize(s));
+    return GKI_OK;
+}
+
+// Host DRAM read bandwidth seen by n_threads threads sweeping `bytes` bytes of host memory with 64-bit loads (a plain sum): the
+// ceiling the packing lanes of gki_count_reads run against, measured on the caller's own buffer (bench.py reports e2e.host_frac).
+int gki_host_read_bandwidth(const void *host, int64_t bytes, int32_t n_threads, double *gb_per_s) {
+    GKI_REQUIRE(host && bytes >= 4096 && gb_per_s && !is_device_ptr(host), GKI_ERR_INVALID, "gki_host_read_bandwidth: need a host buffer of >= 4096 bytes");
+    int T = n_threads > 0 ? n_threads : default_pack_threads() + 1;
+    if (T > 256) T = 256;
+    const uint64_t *words = (const uint64_t *)(((uintptr_t)host + 7) & ~(uintptr_t)7);
+    const int64_t n_words = (bytes - 8) / 8;
+    std::vector<uint64_t> sums((size_t)T * 8, 0);
+    auto body = [&](int t) {
+        const int64_t w0 = n_words * t / T, w1 = n_words * (t + 1) / T;
+        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int64_t i = w0;
+        for (; i + 8 <= w1; i += 8) {
+            a0 += words[i] + words[i + 4];
+            a1 += words[i + 1] + words[i + 5];
+            a2 += words[i + 2] + words[i + 6];
+            a3 += words[i + 3] + words[i + 7];
+        }
+        for (; i < w1; i++) a0 += words[i];
+        sums[(size_t)t * 8] = a0 + a1 + a2 + a3;
+    };
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> threads;
+    for (int t = 1; t < T; t++) threads.emplace_back(body, t);
+    body(0);
+    for (auto &th : threads) th.join();
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    uint64_t total = 0;
+    for (int t = 0; t < T; t++) total += sums[(size_t)t * 8];
+    if (total == 0x9e3779b97f4a7c15ull) fprintf(stderr, " ");   // keep the sum alive
+    *gb_per_s = (double)n_words * 8.0 / secs / 1e9;
     return GKI_OK;
 }
 

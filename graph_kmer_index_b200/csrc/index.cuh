@@ -16,9 +16,10 @@ struct IndexView {
 // Counting structure (count.cu): a bucketised open-addressing table over the DISTINCT index k-mers.
 //   bucket = 64 bytes = key[4] (one 32-byte sector, read by a probe with ONE 256-bit load) | cnt[4][2] (the other sector);
 //   key    = canonical form min(x, revcomp_k(x)) when the k-mer length k is known (k > 0), else x itself;
-//   cnt[o] = number of counted queries q with canonical(q) == key and orientation o = (q != key).
+//   cnt[0] = number of counted queries q with canonical(q) == key and orientation o = (q != key) equal to 0;
+//   cnt[1] = (the same for orientation 1) - cnt[0]; both modulo 2^32 (count.cu: add_both_orientations / read_orientation).
 // Both strands of a read position share one canonical key, so a position costs ONE filter access and at most
-// ONE table access, and a hit is ONE 64-bit RED on the line that was just fetched.
+// ONE table access, and a hit is ONE 32-bit RED on the line that was just fetched.
 //   filter = register-blocked Bloom filter (32-bit words, filter_k bits per key) sized to stay resident in L2.
 struct Bucket {
     unsigned long long key[4];

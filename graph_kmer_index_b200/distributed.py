@@ -31,12 +31,63 @@ def init_process_group(backend=None):
     return dist.get_rank(), dist.get_world_size()
 
 
+class CountsComm:
+    """The communicator of the path's one collective, made and used through the C ABI (include/gki.h: gki_nccl_unique_id,
+    gki_nccl_comm_create, gki_allreduce_counts) -- what a non-Python host does too.  The 128-byte NCCL id travels from rank 0 over the
+    torch.distributed group that torchrun set up; creation is collective (every rank constructs one)."""
+
+    def __init__(self):
+        import ctypes
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0:
+            _lib.call("gki_nccl_unique_id", ident.data_ptr())
+        on_device = dist.get_backend() == "nccl"
+        moved = ident.cuda() if on_device else ident
+        dist.broadcast(moved, src=0)
+        ident = moved.cpu().contiguous()
+        self.handle = ctypes.c_void_p()
+        _lib.call("gki_nccl_comm_create", ident.data_ptr(), self.rank, self.world, ctypes.byref(self.handle))
+
+    def allreduce(self, counts):
+        """in-place sum of a float64 device tensor over the ranks, on torch's current stream"""
+        import torch
+        from . import _lib
+        assert counts.is_cuda and counts.is_contiguous() and counts.dtype == torch.float64
+        _lib.call("gki_allreduce_counts", self.handle, counts.data_ptr(), counts.numel(), _lib.GKI_COUNTS_FLOAT64, _lib.current_stream())
+        return counts
+
+    def close(self):
+        from . import _lib
+        if getattr(self, "handle", None) is not None and self.handle.value:
+            _lib.call("gki_nccl_comm_destroy", self.handle)
+            self.handle = None
+
+
+_counts_comm = None
+
+
+def counts_comm():
+    """the process's CountsComm, created on first use (collective: every rank must reach its first all-reduce)"""
+    global _counts_comm
+    if _counts_comm is None:
+        _counts_comm = CountsComm()
+    return _counts_comm
+
+
 def allreduce_node_counts(counts):
-    """Sum per-rank node counts in place.  `counts`: torch float64 tensor (device tensor for NCCL).  float64 sums of
-    integer counts are exact below 2^53, so the result equals the single-GPU count bit for bit."""
+    """Sum per-rank node counts in place.  `counts`: torch float64 tensor.  float64 sums of integer counts are exact below 2^53, so
+    the result equals the single-GPU count bit for bit.  Device tensors under the NCCL backend go through the C ABI
+    (gki_allreduce_counts on a communicator made by gki_nccl_comm_create); host tensors (gloo, the CPU tests) through torch."""
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+        if counts.is_cuda and dist.get_backend() == "nccl" and os.environ.get("GKI_TORCH_ALLREDUCE", "0") != "1":
+            counts_comm().allreduce(counts)
+        else:
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     return counts
 
 

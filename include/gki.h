@@ -181,6 +181,9 @@ int gki_pack_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int6
                    int64_t *dirty_index, int64_t dirty_cap, int64_t *n_clean, int64_t *n_dirty, int32_t n_threads, int32_t flags);
 int gki_count_packed_reads(gki_index_t *index, const uint64_t *packed, int64_t n_reads, int32_t read_len, int32_t k,
                            int32_t both_strands, gki_stream_t stream);
+/* host DRAM read bandwidth (GB/s) of n_threads threads (<= 0: as many as the packing lanes) summing `bytes` bytes of a host
+ * buffer: the ceiling of the host side of gki_count_reads, measured on the caller's own read batch */
+int gki_host_read_bandwidth(const void *host, int64_t bytes, int32_t n_threads, double *gb_per_s);
 
 /* FASTA / FASTQ in front of the packer.  gki_fastx_open maps the file and finds its sequence lines with all host threads:
  * FASTA -- every line that does not start with '>' (exactly what ReadKmers.from_fasta_file treats as a read,
@@ -272,6 +275,22 @@ int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t fir
  * one; bit 1: loads ask for a 64-byte L2 fill (ld.global.nc.L2::64B) instead of the default whole line.
  * *ms receives the kernel time. Synchronous. */
 int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms);
+/* ---- multi-GPU: reads shard over the ranks, the index is replicated, the ranks' node-count vectors are summed by ONE
+ * NCCL all-reduce.  Reference analogue: the parent summing / concatenating its workers' results (shared_mem.py:164-171, cfki:222-232).
+ * gki_allreduce_counts takes the host application's ncclComm_t (as void*: this header does not include nccl.h) and sums `counts`
+ * (device memory, n elements of float64 -- exact below 2^53, the dtype of get_node_counts, cfki:39-40 -- or uint64) in place over its
+ * ranks, on `stream`.  NCCL is bound at run time (libnccl.so.2 of the process, or GKI_NCCL_LIBRARY).  A host without a communicator
+ * of its own gets one from gki_nccl_unique_id (rank 0; send the 128 bytes to every rank by any means) + gki_nccl_comm_create. */
+#define GKI_COUNTS_FLOAT64 0
+#define GKI_COUNTS_UINT64 1
+int gki_nccl_unique_id(void *id128);
+int gki_nccl_comm_create(const void *id128, int32_t rank, int32_t world_size, void **nccl_comm_out);
+int gki_nccl_comm_destroy(void *nccl_comm);
+int gki_allreduce_counts(void *nccl_comm, void *counts, int64_t n, int32_t dtype, gki_stream_t stream);
+
+/* return the library's cached device scratch (stream-ordered pool) to the driver; synchronises the device */
+int gki_release_scratch(void);
+
 /* n random stores or atomics (the measurements the index-build design rests on).  mode 0/1/2: 32/16/8-byte stores to random
  * slots of an n-slot array; 3: returning atomicAdd on n_bins random counters; 4: the same without a return value; 5: returning
  * atomicAdd picks a slot inside the counter's own bin of a (n_bins x n/n_bins) array and a 32-byte record is stored there;

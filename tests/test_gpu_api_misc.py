@@ -181,3 +181,32 @@ def test_kmer_index2_frequencies_with_wide_offsets(gki):
     f._allele_frequencies = np.ones(5, dtype=np.float32)
     idx = KmerIndex2.from_flat_kmers(f, modulo=101)
     assert idx.get_kmer_frequency(5) == 2 and idx.get_kmer_frequency(9) == 1
+
+
+def test_counts_allreduce_through_the_c_abi_single_rank(gki):
+    """gki_nccl_unique_id / gki_nccl_comm_create / gki_allreduce_counts (include/gki.h) with a one-rank communicator: the sum over one
+    rank is the vector itself, for both dtypes; bad arguments are refused.  (Two ranks: tests/test_gpu_multi.py.)"""
+    import ctypes
+    import torch
+    from graph_kmer_index_b200 import _lib
+    ident = np.zeros(128, dtype=np.uint8)
+    _lib.call("gki_nccl_unique_id", ident.ctypes.data)
+    assert ident.any()
+    comm = ctypes.c_void_p()
+    _lib.call("gki_nccl_comm_create", ident.ctypes.data, 0, 1, ctypes.byref(comm))
+    assert comm.value
+    stream = torch.cuda.current_stream().cuda_stream
+    f = torch.arange(100_000, dtype=torch.float64, device="cuda") * 3
+    _lib.call("gki_allreduce_counts", comm, f.data_ptr(), f.numel(), _lib.GKI_COUNTS_FLOAT64, stream)
+    u = torch.arange(100_000, dtype=torch.int64, device="cuda") + (1 << 40)
+    _lib.call("gki_allreduce_counts", comm, u.data_ptr(), u.numel(), _lib.GKI_COUNTS_UINT64, stream)
+    torch.cuda.synchronize()
+    assert torch.equal(f.cpu(), torch.arange(100_000, dtype=torch.float64) * 3)
+    assert torch.equal(u.cpu(), torch.arange(100_000, dtype=torch.int64) + (1 << 40))
+    with pytest.raises(_lib.GkiError):
+        _lib.call("gki_allreduce_counts", comm, f.data_ptr(), f.numel(), 7, stream)
+    host = np.zeros(8)
+    with pytest.raises(_lib.GkiError):
+        _lib.call("gki_allreduce_counts", comm, host.ctypes.data, 8, _lib.GKI_COUNTS_FLOAT64, stream)
+    _lib.call("gki_nccl_comm_destroy", comm)
+    _lib.call("gki_release_scratch")

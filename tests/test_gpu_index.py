@@ -133,6 +133,233 @@ def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
     assert np.array_equal(k_o, hashes[perm]) and np.array_equal(n_o, nodes[perm]) and np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
 
 
+def test_build_dtypes_and_defaults(gki):
+    """payload columns keep whatever dtype the caller had (cfki:436-440 are plain fancy-indexing)"""
+    rng = np.random.default_rng(2)
+    n, modulo = 3000, 1009
+    hashes = rng.integers(0, 4 ** 31, n, dtype=np.uint64)
+    hashes[::3] = hashes[1]
+    nodes = rng.integers(0, 50, n)                      # int64 nodes
+    flat = gki.FlatKmers(hashes, nodes)                 # default ref_offsets float64 zeros, af float32 ones
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo)
+    want = no.build_index(hashes, nodes, np.zeros(n), np.ones(n, dtype=np.float32), modulo)
+    assert_index_equal(index, want)
+    for rdt, ndt in ((np.int32, np.uint16), (np.float32, np.int8), (np.uint8, np.uint32)):
+        ref = rng.integers(0, 100, n).astype(rdt)
+        nd = rng.integers(0, 100, n).astype(ndt)
+        af = rng.random(n)                              # float64 allele frequencies
+        index = gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(hashes, nd, ref, af), modulo=modulo)
+        assert_index_equal(index, no.build_index(hashes, nd, ref, af, modulo))
+    with pytest.raises(IndexError):
+        gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(np.zeros(0, np.uint64), np.zeros(0, np.uint32)), modulo=7)
+    m = gki.MinimalKmerIndex.from_flat_kmers(gki.FlatKmers(hashes, nodes.astype(np.uint32)), modulo=modulo)
+    assert m._hashes_to_index.dtype == np.int64 and np.array_equal(m._hashes_to_index, want["_hashes_to_index"])
+    assert np.array_equal(m._kmers, want["_kmers"]) and np.array_equal(m._nodes, want["_nodes"])
+
+
+def test_singletons_and_set_frequencies(gki):
+    rng = np.random.default_rng(4)
+    hashes = rng.integers(0, 500, 4000).astype(np.uint64)
+    nodes = np.arange(4000, dtype=np.uint32)
+    ref = rng.integers(0, 5, 4000).astype(np.uint64)
+    af = np.ones(4000, dtype=np.float32)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    kept = flat.get_new_without_singletons()
+    want = no.without_singletons(hashes, nodes, ref, af)
+    for a, b in zip((kept._hashes, kept._nodes, kept._ref_offsets, kept._allele_frequencies), want):
+        assert np.array_equal(a, b)
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=101, skip_singletons=True)
+    w = no.build_index(*want, 101)
+    assert np.array_equal(index._frequencies, w["_frequencies"] + 1) and np.array_equal(index._kmers, w["_kmers"])
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=101, skip_frequencies=True)
+    assert not index._frequencies.any()
+    index.set_frequencies()
+    assert np.array_equal(index._frequencies, no.build_index(hashes, nodes, ref, af, 101)["_frequencies"])
+    rc = flat.get_reverse_complement_flat_kmers(31)
+    assert np.array_equal(rc._hashes, no.revcomp_hashes(hashes, 31))
+    both = gki.FlatKmers.from_multiple_flat_kmers([flat, rc])
+    assert len(both._hashes) == 8000 and both._nodes.dtype == np.uint32 and both._ref_offsets.dtype == np.uint64
+
+
+@pytest.mark.parametrize("name", ["index_small", "index_sparse"])
+def test_lookup_and_counts_golden(gki, name):
+    g = load_golden(name)
+    idx = golden_index(g)
+    index = product_index(gki, idx)
+    q = g["queries"]
+    nodes, offs, ns = [], [], []
+    for kmer in q[:200]:
+        r = index.get(kmer, max_hits=10 ** 9)
+        ns.append(0 if r[0] is None else len(r[0]))
+        if r[0] is not None:
+            nodes.extend(r[0]); offs.extend(r[1])
+    assert ns == list(g["get_n"]) and nodes == list(g["get_nodes"]) and offs == list(g["get_ref_offsets"])
+    counter = gki.CounterKmerIndex.from_kmer_index(index)
+    counter.count_kmers(q)
+    counter.count_kmers(q[:100])
+    got = counter.get_node_counts()
+    assert got.dtype == np.float64 and np.array_equal(got, g["node_counts_min0"])
+    assert np.array_equal(counter.get_node_counts(int(g["n_nodes"]) + 17), g["node_counts_min_big"])
+    assert np.array_equal(counter.counter[counter.kmers], c_oracle.count_kmers(idx, np.concatenate([q, q[:100]])))
+    counter.count_kmers(q[:100], update_counter=False)                       # cfki:34-35: reset first
+    assert np.array_equal(counter.get_node_counts(), no.node_counts(idx, q[:100]))
+    if "cython_get" in g.files:
+        assert np.array_equal(gki.CythonKmerIndex(index).get(q), g["cython_get"])
+    assert np.array_equal(index.device_index().lookup_hits(q, False, None, None), no.lookup_hits(idx, q, False, None, None))
+    assert np.array_equal(index.has_kmers(q), no.has_kmers(idx, q))
+    n_nodes = int(g["n_nodes"])
+    assert np.array_equal(index.map_kmers(q, n_nodes), no.map_kmers(idx, q, n_nodes))
+    # reads -> node counts, fused
+    counter.reset()
+    counter.count_reads(g["reads"], int(g["k"]))
+    assert np.array_equal(counter.get_node_counts(n_nodes), g["read_node_counts"])
+
+
+@pytest.mark.parametrize("mode", ["canonical", "raw", "nofilter", "tinyfilter", "k_mismatch", "minimizer", "minimizer_k_mismatch"])
+@pytest.mark.parametrize("n,modulo,n_reads,L,k", [(40000, 200003, 3000, 150, 31), (40000, 4099, 1500, 150, 31), (5000, 7, 300, 100, 15),
+                                                   (40000, 200003, 777, 64, 31), (3000, 1009, 400, 90, 16)])
+def test_count_reads_vs_oracle(gki, monkeypatch, mode, n, modulo, n_reads, L, k):
+    """every layout of the counting structure gives the oracle's node counts: canonical keys (both strands share a
+    probe), raw keys, no Bloom filter, a saturated filter, and a table prepared for another k"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 997, k)
+    if k % 2 == 0:                                     # even k: palindromic k-mers exist; make sure some are indexed and read
+        pal = np.array([no.sequence_to_kmer_hash("ACGT" * (k // 4))], dtype=np.uint64)
+        assert no.revcomp_hashes(pal, k)[0] == pal[0]
+        hashes = hashes.copy()
+        hashes[:3] = pal[0]
+    idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    reads = synthetic.reads(n_reads, L, n, k, p_hit_permille=400, n_permille=10)
+    if k % 2 == 0:
+        reads[:5, :k] = np.frombuffer(("ACGT" * (k // 4)).encode(), dtype=np.uint8)
+    if mode == "raw":
+        monkeypatch.setenv("GKI_TABLE_RAW", "1")
+    elif mode == "nofilter":
+        monkeypatch.setenv("GKI_FILTER_MAX_MB", "0")
+    elif mode == "tinyfilter":
+        monkeypatch.setenv("GKI_FILTER_K", "1")
+    elif mode.startswith("minimizer"):                 # filter words addressed by minimizer (odd k in 27..31, else it stays off)
+        monkeypatch.setenv("GKI_FILTER_MZ", "1")
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], modulo)
+    dev.prepare_counting((k + 1 if k < 31 else k - 1) if mode == "k_mismatch" else (29 if mode == "minimizer_k_mismatch" else (0 if mode == "raw" else k)))
+    assert dev.info()["has_filter"] == (mode != "nofilter")
+    want = c_oracle.read_node_counts(idx, reads, k, 1000)
+    assert want.sum() > 0
+    dev.count_reads(reads, k)                                   # host buffer: chunked H2D inside the call
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dreads = torch.from_numpy(reads).cuda()
+    dev.count_reads(dreads, k)                                  # device-resident
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    dev.count_reads(dreads, k, both_strands=False)
+    assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads, k, 1000, both_strands=False))
+    # unfused: hashes -> count_kmers equals the fused path; linearity over two halves
+    from graph_kmer_index_b200.read_kmers import hash_read_matrix
+    fwd, rc = hash_read_matrix(reads, k)
+    dev.reset_counts()
+    half = n_reads // 2
+    dev.count_kmers(np.concatenate([fwd[:half].ravel(), rc[:half].ravel()]))
+    first = dev.node_counts(1000)
+    dev.count_kmers(torch.from_numpy(np.concatenate([fwd[half:].ravel(), rc[half:].ravel()]).view(np.int64)).cuda())
+    assert np.array_equal(dev.node_counts(1000), want)
+    assert np.array_equal(want - first, c_oracle.read_node_counts(idx, reads[half:], k, 1000))
+    # strided host rows
+    padded = np.full((n_reads, L + 10), ord("A"), dtype=np.uint8)
+    padded[:, :L] = reads
+    dev.reset_counts()
+    dev.count_reads(padded[:, :L], k)
+    assert np.array_equal(dev.node_counts(1000), want)
+    assert np.array_equal(dev.entry_counts(), c_oracle.count_reads(idx, reads, k))
+    dev.close()
+
+
+def test_uint16_wrap_flag_and_hot_kmer(gki):
+    """a k-mer hit > 65535 times: exact by default, modulo 2^16 with the reference-Counter compat flag (cfki:27)"""
+    kmers = np.array([5, 5, 9], dtype=np.uint64)
+    nodes = np.array([1, 2, 3], dtype=np.uint32)
+    idx = no.build_index(kmers, nodes, np.zeros(3, np.uint64), np.ones(3, np.float32), 11, skip_frequencies=True)
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], 11)
+    dev.count_kmers(np.full(70000, 5, dtype=np.uint64))
+    dev.count_kmers(np.array([9, 9, 4, 16], dtype=np.uint64))
+    assert list(dev.node_counts()) == [0, 70000, 70000, 2]
+    assert list(dev.node_counts(wrap_uint16=True)) == [0, 70000 - 65536, 70000 - 65536, 2]
+    assert list(dev.node_counts(6)) == [0, 70000, 70000, 2, 0, 0]
+
+
+def test_counter_past_2_pow_32_does_not_leak_into_the_other_orientation(gki):
+    """Counters are 32 bits per k-mer orientation and wrap (the reference's Counter wraps at 2^16, cfki:27).  Poly-A reads counted on
+    both strands push the counter of AAA..A (orientation 0 of the canonical key) and of TTT..T (orientation 1) past 2^32: each must
+    come back modulo 2^32 on its own -- a packed 64-bit add of {1, 1} carried the overflow of one into the other."""
+    import torch
+    k, L = 31, 150
+    poly_a, poly_t = 0, 4 ** k - 1
+    kmers = np.array([poly_a, poly_t, 12345], dtype=np.uint64)
+    nodes = np.array([1, 2, 3], dtype=np.uint32)
+    idx = no.build_index(kmers, nodes, np.zeros(3, np.uint64), np.ones(3, np.float32), 101, skip_frequencies=True)
+    dev = gki.DeviceIndex(idx["_hashes_to_index"], idx["_n_kmers"], idx["_kmers"], idx["_nodes"], 101)
+    dev.prepare_counting(k)
+    n_reads, calls = 1_200_000, 30
+    reads = torch.full((n_reads, L), ord("A"), dtype=torch.uint8, device="cuda")
+    for _ in range(calls):
+        dev.count_reads(reads, k, True)
+    positions = n_reads * (L - k + 1) * calls
+    assert positions > 2 ** 32
+    dev.count_kmers(np.full(3, poly_a, dtype=np.uint64))          # orientation 0 alone
+    dev.count_kmers(np.full(5, poly_t, dtype=np.uint64))          # orientation 1 alone
+    got = dev.node_counts()
+    assert got[1] == (positions + 3) % 2 ** 32 and got[2] == (positions + 5) % 2 ** 32 and got[3] == 0
+    assert list(dev.query_counts(np.array([poly_a, poly_t, 12345, 7], dtype=np.uint64))) == [(positions + 3) % 2 ** 32, (positions + 5) % 2 ** 32, 0, 0]
+    dev.close()
+
+
+def test_device_resident_build_and_count_full_config1(gki):
+    """BASELINE config 1 (1M entries, 100k nodes, 100k x 150bp reads) entirely on the device; the oracle checks it."""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    n, n_nodes, modulo, k, n_reads, L = 1_000_000, 100_000, 19_999_999, 31, 100_000, 150
+    glen = synthetic.genome_length(n, k)
+    dev = torch.device("cuda")
+    genome = torch.empty(glen, dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_genome", _lib.ptr(genome), glen, None)
+    hashes = torch.empty(n, dtype=torch.int64, device=dev)
+    nodes = torch.empty(n, dtype=torch.int32, device=dev)
+    ref = torch.empty(n, dtype=torch.int64, device=dev)
+    af = torch.empty(n, dtype=torch.float32, device=dev)
+    _lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n_nodes, k, _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), None)
+    reads = torch.empty((n_reads, L), dtype=torch.uint8, device=dev)
+    _lib.call("gki_synth_reads", _lib.ptr(genome), glen, 0, n_reads, L, 100, 0, _lib.ptr(reads), None)
+    torch.cuda.synchronize()
+    # device generators == host mirror
+    h_hashes, h_nodes, h_ref, h_af = synthetic.flat_kmers(n, n_nodes, k)
+    assert np.array_equal(hashes.cpu().numpy().view(np.uint64), h_hashes) and np.array_equal(nodes.cpu().numpy().view(np.uint32), h_nodes)
+    assert np.array_equal(ref.cpu().numpy().view(np.uint64), h_ref) and np.array_equal(af.cpu().numpy(), h_af)
+    h_reads = synthetic.reads(n_reads, L, n, k, 100)
+    assert np.array_equal(reads.cpu().numpy(), h_reads)
+    # build on the device
+    h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
+    nk = torch.empty(modulo, dtype=torch.int32, device=dev)
+    o_k, o_r = torch.empty_like(hashes), torch.empty_like(ref)
+    o_n, o_a = torch.empty_like(nodes), torch.empty_like(af)
+    o_f = torch.empty(n, dtype=torch.int16, device=dev)
+    _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), n, modulo, 0, _lib.ptr(h2i), _lib.ptr(nk),
+              _lib.ptr(o_k), _lib.ptr(o_n), _lib.ptr(o_r), _lib.ptr(o_a), _lib.ptr(o_f), None, None)
+    torch.cuda.synchronize()
+    want = c_oracle.build_index(h_hashes, h_nodes, h_ref, h_af, modulo)
+    assert np.array_equal(h2i.cpu().numpy(), want["_hashes_to_index"]) and np.array_equal(nk.cpu().numpy().view(np.uint32), want["_n_kmers"])
+    assert np.array_equal(o_k.cpu().numpy().view(np.uint64), want["_kmers"]) and np.array_equal(o_n.cpu().numpy().view(np.uint32), want["_nodes"])
+    assert np.array_equal(o_r.cpu().numpy().view(np.uint64), want["_ref_offsets"]) and np.array_equal(o_a.cpu().numpy(), want["_allele_frequencies"])
+    assert np.array_equal(o_f.cpu().numpy().view(np.uint16), want["_frequencies"])
+    # count on the device
+    index = gki.DeviceIndex(h2i, nk, o_k, o_n, modulo)
+    index.count_reads(reads, k)
+    got = index.node_counts(n_nodes)
+    assert np.array_equal(got, c_oracle.read_node_counts(want, h_reads, k, n_nodes))
+    # checksum-of-checksums: total node count == sum over entries of their k-mer's hit count
+    assert got.sum() == float(index.entry_counts().astype(np.int64).sum())
+
+
 def test_large_modulo_device_build(gki):
     """default-sized tables (modulo 452930477) stay on the device: tables checked through their invariants"""
     import torch
