@@ -511,14 +511,27 @@ def measure(args, cfg, name, rank, world, local_rank, full):
         if world > 1:
             dist.all_reduce(bw)                                   # sum over ranks: aggregate host read bandwidth
         host_read_gbs = float(bw.item())
+        # ... and what the copy engine moves from the same pinned batch over this GPU's PCIe link
+        barrier()
+        ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ca.record()
+        reads.copy_(host_reads, non_blocking=True)
+        cb.record()
+        torch.cuda.synchronize()
+        pcie = torch.tensor([R * L / (ca.elapsed_time(cb) / 1e3) / 1e9], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(pcie)
+        pcie_gbs = float(pcie.item())
         ascii_gbs = e2e_value / nk_per_read * L / 1e9
+        ceiling = host_read_gbs + pcie_gbs
         e2e = {"value": e2e_value, "unit": "kmers/s",
                "h2d_bytes_per_step": int(R * L), "d2h_bytes_per_step": int(counts.shape[0] * 8), "steps": e2e_steps,
                "host_memory": "pinned", "pack_lanes": lanes,
-               "host_read_gbs": host_read_gbs, "host_ascii_gbs_consumed": ascii_gbs, "host_frac": ascii_gbs / host_read_gbs if host_read_gbs else None,
+               "host_read_gbs": host_read_gbs, "pcie_h2d_gbs": pcie_gbs, "host_ascii_gbs_consumed": ascii_gbs, "host_frac": ascii_gbs / ceiling if ceiling else None,
                "note": "per GPU bytes of the caller's ASCII reads (1 byte per base); inside the call pack_lanes host threads re-encode "
                        "chunks to 2 bits per base before the bus while the copy engine moves the other chunks as ASCII (csrc/count.cu); "
-                       "host_frac = ASCII bytes read per second / the lanes' measured host-DRAM read bandwidth on the same batch (all ranks at once)"}
+                       "host_frac = ASCII bytes consumed per second / (host-DRAM read bandwidth of the packing lanes on this batch + copy-engine "
+                       "rate of the same pinned batch), both measured here, summed over the ranks (all ranks probe at once)"}
         # the call a KAGE user makes (cfki:33-40): pageable numpy reads through CounterKmerIndex, node counts returned as a fresh numpy array
         pageable = np.empty((R, L), dtype=np.uint8)
         pageable[:] = host_reads.numpy()

@@ -70,6 +70,8 @@ _SIGNATURES = {
     "gki_index_build": [c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gki_partition_by_bucket_range": [c_vp, c_i64, c_u64, c_i32, c_vp, c_vp, c_vp],
     "gki_index_build_range": [c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_u64, c_u64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
+    "gki_partition_pack": [c_vp, c_vp, c_vp, c_vp, c_i64, c_u64, c_i32, c_vp, c_vp, c_vp],
+    "gki_index_build_records": [c_vp, c_i64, c_u64, c_u64, c_u64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp],
     "gki_group_by_key": [c_vp, c_i32, c_i64, c_u64, c_i32, c_vp, c_vp, c_vp, c_vp],
     "gki_gather": [c_vp, c_i32, c_vp, c_i64, c_vp, c_vp],
     "gki_mark_non_first_occurrences": [c_vp, c_i64, c_vp, c_vp],

@@ -571,7 +571,7 @@ __device__ __forceinline__ uint32_t slab_bin_of(uint32_t bucket, const SlabParam
 // HINT (experiment, GKI_SLAB_HINT): L2 eviction priority of the slab stores (1: evict_last, 3: evict_normal stated explicitly,
 // 4: evict_first) and, with bit 3 (8) added, evict_first on the streamed input loads
 template <int UNROLL, int HINT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, UNROLL >= 4 ? 5 : 8)
 slab_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
                     const float *__restrict__ af, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
                     uint32_t *__restrict__ overflow) {
@@ -777,6 +777,147 @@ slab_finish_kernel(SlabParams p, const uint32_t *__restrict__ count, const uint3
     }
 }
 
+// ---- hash-range partitioned build, sender side: ONE stable partition pass that emits whole 32-byte records ----------------------
+// record = {kmer, ref_offset, node | af << 32, bucket}.  Every rank orders its FlatKmers shard by the rank that owns the bucket
+// (fan-out = number of ranks, so each warp writes long runs per owner: whole lines) keeping the input order inside an owner, and
+// the records travel with ONE all-to-all instead of one gather + one all-to-all per column.  The receiver builds its slice straight
+// from the records (slab_scatter_records_kernel): its input index is the position in the received array, which is the global
+// input order (rank-major) restricted to its bucket range.
+constexpr int PP_THREADS = 256;
+constexpr int PP_ITEMS = 8;
+constexpr int PP_TILE = PP_THREADS * PP_ITEMS;
+constexpr int PP_MAX_PARTS = 32;
+__global__ void __launch_bounds__(PP_THREADS) part_hist_kernel(const uint64_t *__restrict__ kmers, int64_t n, FastMod fm, uint32_t part_size, int n_parts,
+                                                              uint32_t *__restrict__ hist, int64_t n_tiles) {
+    __shared__ uint32_t h[PP_MAX_PARTS];
+    if (threadIdx.x < PP_MAX_PARTS) h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * PP_TILE;
+#pragma unroll
+    for (int it = 0; it < PP_ITEMS; it++) {
+        const int64_t i = base + it * PP_THREADS + threadIdx.x;
+        if (i < n) atomicAdd(&h[fastmod(__ldg(kmers + i), fm) / part_size], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < n_parts) hist[(int64_t)threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+// element order inside a tile: warp-major, then item, then lane -- i.e. memory order (stable)
+__global__ void __launch_bounds__(PP_THREADS)
+part_scatter_records_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
+                            const float *__restrict__ af, FastMod fm, uint32_t part_size, int n_parts, const uint32_t *__restrict__ offsets,
+                            int64_t n_tiles, BinRecord *__restrict__ out) {
+    constexpr int WARPS = PP_THREADS / 32;
+    __shared__ uint32_t warp_hist[WARPS][PP_MAX_PARTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = threadIdx.x; d < WARPS * PP_MAX_PARTS; d += PP_THREADS) (&warp_hist[0][0])[d] = 0;
+    __syncthreads();
+    const int64_t warp_base = (int64_t)blockIdx.x * PP_TILE + (int64_t)warp * (PP_ITEMS * 32);
+    unsigned long long km[PP_ITEMS];
+    uint32_t bucket[PP_ITEMS], rank[PP_ITEMS];
+#pragma unroll
+    for (int it = 0; it < PP_ITEMS; it++) {
+        const int64_t i = warp_base + it * 32 + lane;
+        km[it] = i < n ? __ldg(kmers + i) : 0ull;
+    }
+#pragma unroll
+    for (int it = 0; it < PP_ITEMS; it++) {
+        const int64_t i = warp_base + it * 32 + lane;
+        const bool ok = i < n;
+        const uint32_t okmask = __ballot_sync(0xffffffffu, ok);
+        bucket[it] = fastmod(km[it], fm);
+        rank[it] = 0;
+        if (ok) {
+            const uint32_t d = bucket[it] / part_size;
+            const uint32_t peers = digit_peers<5>(d, okmask);
+            const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (lane == leader) {
+                base = warp_hist[warp][d];
+                warp_hist[warp][d] = base + __popc(peers);
+            }
+            base = __shfl_sync(peers, base, leader);
+            rank[it] = base + before;
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < n_parts) {   // per-warp counts -> start positions in the output
+        uint32_t run = offsets[(int64_t)threadIdx.x * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < WARPS; w++) {
+            const uint32_t c = warp_hist[w][threadIdx.x];
+            warp_hist[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < PP_ITEMS; it++) {
+        const int64_t i = warp_base + it * 32 + lane;
+        if (i >= n) continue;
+        const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
+        const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
+        const unsigned long long r = ref ? __ldg(ref + i) : 0ull;
+        BinRecord *dst = out + warp_hist[warp][bucket[it] / part_size] + rank[it];
+        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(km[it]), "l"(r), "l"(nd | (a << 32)), "l"((unsigned long long)bucket[it]) : "memory");
+    }
+}
+__global__ void part_counts_from_offsets_kernel(const uint32_t *__restrict__ offsets, int64_t n_tiles, int n_parts, int64_t n, long long *__restrict__ counts) {
+    const int p = threadIdx.x;
+    if (p >= n_parts) return;
+    const long long lo = offsets[(int64_t)p * n_tiles], hi = p + 1 < n_parts ? offsets[(int64_t)(p + 1) * n_tiles] : n;
+    counts[p] = hi - lo;
+}
+// receiver: the slab scatter fed by records (index = position in the record array)
+template <int UNROLL>
+__global__ void __launch_bounds__(256, 5)
+slab_scatter_records_kernel(int64_t n, const BinRecord *__restrict__ in, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
+                            uint32_t *__restrict__ overflow) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
+        BinRecord rec[UNROLL];
+        uint32_t bin[UNROLL], bl[UNROLL], pos[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            rec[u] = i < n ? load_record(in + i) : BinRecord{0, 0, 0, 0};
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            const uint32_t b = (uint32_t)rec[u].index - p.bucket_lo;
+            bin[u] = slab_bin_of(b, p);
+            bl[u] = b - bin[u] * p.nb;
+            pos[u] = SLAB_CAP;
+            if (i < n && bin[u] < p.n_bins) pos[u] = atomicAdd(count + bin[u], 1u);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            const int64_t i = base + u * stride;
+            if (i >= n) continue;
+            if (pos[u] >= (uint32_t)SLAB_CAP) {
+                *overflow = 1u;
+                continue;
+            }
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slab + (size_t)bin[u] * SLAB_CAP + pos[u]), "l"(rec[u].kmer), "l"(rec[u].ref),
+                         "l"(rec[u].node_af), "l"((unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32))
+                         : "memory");
+        }
+    }
+}
+// fallback paths take columns
+__global__ void unpack_records_kernel(const BinRecord *__restrict__ in, int64_t n, uint64_t *__restrict__ kmers, uint32_t *__restrict__ nodes,
+                                      uint64_t *__restrict__ ref, float *__restrict__ af) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const BinRecord r = load_record(in + i);
+        kmers[i] = r.kmer;
+        if (nodes) nodes[i] = (uint32_t)r.node_af;
+        if (ref) ref[i] = r.ref;
+        if (af) af[i] = __uint_as_float((uint32_t)(r.node_af >> 32));
+    }
+}
+
 // set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
 // (k-mer, ref_offset) pair
 // (the bucket of entry e is the key of its sort element, or, after the binned build, kmers[e] % modulo - bucket_lo)
@@ -920,9 +1061,17 @@ extern "C" {
 static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
                        uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset, int32_t flags,
                        int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out,
-                       float *af_out, uint16_t *freq_out, uint32_t *perm_out, gki_stream_t stream) {
+                       float *af_out, uint16_t *freq_out, uint32_t *perm_out, gki_stream_t stream, const void *records = nullptr) {
+    // records (device, gki_partition_pack layout) replace the four input columns when given
     CallScope call(stream);
     cudaStream_t s = call.stream;
+    if (records) {
+        GKI_REQUIRE(is_device_ptr(records) && (((uintptr_t)records & 31) == 0), GKI_ERR_INVALID, "gki_index_build_records: records must be 32-byte aligned device memory");
+        kmers = (const uint64_t *)records;   // placeholders for the presence checks below; never dereferenced as columns
+        nodes = (const uint32_t *)records;
+        ref_offsets = (const uint64_t *)records;
+        af = (const float *)records;
+    }
     GKI_REQUIRE(bucket_lo < bucket_hi && bucket_hi <= modulo, GKI_ERR_INVALID, "gki_index_build: bad bucket range");
     GKI_REQUIRE(position_offset >= 0 && position_offset + n < (1ll << 31), GKI_ERR_UNSUPPORTED, "gki_index_build: positions must stay < 2^31");
     const uint64_t table_len = bucket_hi - bucket_lo;
@@ -935,10 +1084,33 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     const bool want_freq = freq_out && !(flags & GKI_BUILD_SKIP_FREQUENCIES);
 
     DevIn d_kmers, d_nodes, d_ref, d_af;
-    GKI_TRY(d_kmers.stage(kmers, (size_t)n * 8, s));
-    GKI_TRY(d_nodes.stage(nodes_out ? nodes : nullptr, (size_t)n * 4, s));
-    GKI_TRY(d_ref.stage((ref_out || want_freq) ? ref_offsets : nullptr, (size_t)n * 8, s));
-    GKI_TRY(d_af.stage(af_out ? af : nullptr, (size_t)n * 4, s));
+    if (!records) {
+        GKI_TRY(d_kmers.stage(kmers, (size_t)n * 8, s));
+        GKI_TRY(d_nodes.stage(nodes_out ? nodes : nullptr, (size_t)n * 4, s));
+        GKI_TRY(d_ref.stage((ref_out || want_freq) ? ref_offsets : nullptr, (size_t)n * 8, s));
+        GKI_TRY(d_af.stage(af_out ? af : nullptr, (size_t)n * 4, s));
+    }
+    auto columns_from_records = [&]() -> int {   // the fallback paths read columns
+        if (!records || d_kmers.dptr) return GKI_OK;
+        GKI_TRY(d_kmers.scratch.alloc((size_t)n * 8, s));
+        d_kmers.dptr = d_kmers.scratch.ptr;
+        if (nodes_out) {
+            GKI_TRY(d_nodes.scratch.alloc((size_t)n * 4, s));
+            d_nodes.dptr = d_nodes.scratch.ptr;
+        }
+        if (ref_out || want_freq) {
+            GKI_TRY(d_ref.scratch.alloc((size_t)n * 8, s));
+            d_ref.dptr = d_ref.scratch.ptr;
+        }
+        if (af_out) {
+            GKI_TRY(d_af.scratch.alloc((size_t)n * 4, s));
+            d_af.dptr = d_af.scratch.ptr;
+        }
+        unpack_records_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>((const BinRecord *)records, n, (uint64_t *)d_kmers.dptr,
+                                                                                         (uint32_t *)d_nodes.dptr, (uint64_t *)d_ref.dptr, (float *)d_af.dptr);
+        GKI_CHECK_LAUNCH();
+        return GKI_OK;
+    };
     DevOut o_h2i, o_nk, o_kmers, o_nodes, o_ref, o_af, o_freq, o_perm;
     GKI_TRY(o_h2i.prepare(hashes_to_index, (size_t)table_len * 4, s));
     GKI_TRY(o_nk.prepare(n_kmers, (size_t)table_len * 4, s));
@@ -958,7 +1130,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         GKI_TRY(tmp_kmers.alloc((size_t)n * 8, s));
         kmers_sorted = tmp_kmers.as<uint64_t>();
     }
-    if (want_freq && !ref_sorted && d_ref.dptr) {
+    if (want_freq && !ref_sorted && (d_ref.dptr || records)) {
         GKI_TRY(tmp_ref.alloc((size_t)n * 8, s));
         ref_sorted = tmp_ref.as<uint64_t>();
     }
@@ -1006,12 +1178,15 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
 #define GKI_SLAB_SCATTER(H)                                                                                                              \
     slab_scatter_kernel<4, H><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), \
                                                     sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>())
+            if (records) {
+                slab_scatter_records_kernel<4><<<sgrid, 256, 0, s>>>(n, (const BinRecord *)records, sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>());
+            } else
             switch (hint) {
                 case 1: GKI_SLAB_SCATTER(1); break;
-                case 3: GKI_SLAB_SCATTER(3); break;
-                case 4: GKI_SLAB_SCATTER(4); break;
-                case 9: GKI_SLAB_SCATTER(9); break;
                 case 8: GKI_SLAB_SCATTER(8); break;
+                case 102: slab_scatter_kernel<2, 0><<<grid_for(n, 256 * 2, device_info().sms * 8), 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>()); break;
+                case 101: slab_scatter_kernel<1, 0><<<grid_for(n, 256, device_info().sms * 8), 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>()); break;
+                case 202: slab_scatter_kernel<2, 0><<<grid_for(n, 256 * 2, device_info().sms * 16), 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>()); break;
                 default: GKI_SLAB_SCATTER(0); break;
             }
 #undef GKI_SLAB_SCATTER
@@ -1036,6 +1211,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         }
     }
 
+    if (!binned) GKI_TRY(columns_from_records());
     // ---- binned path (see bin_finish_kernel): applies when every bin of 2^shift buckets holds at most BIN_CAP entries ----
     if (!binned && n >= (1 << 15) && allow_binned) {
         BinParams bp;
@@ -1171,6 +1347,51 @@ int gki_index_build_range(const uint64_t *kmers, const uint32_t *nodes, const ui
     GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build_range: need 1 <= modulo < 2^32");
     return build_range(kmers, nodes, ref_offsets, af, n, modulo, bucket_lo, bucket_hi, position_offset, flags, hashes_to_index, n_kmers,
                        kmers_out, nodes_out, ref_out, af_out, freq_out, nullptr, stream);
+}
+
+int gki_index_build_records(const void *records, int64_t n, uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset,
+                            int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out,
+                            float *af_out, uint16_t *freq_out, gki_stream_t stream) {
+    GKI_REQUIRE(records, GKI_ERR_INVALID, "gki_index_build_records: records is NULL");
+    GKI_REQUIRE(modulo >= 1 && modulo < (1ull << 32), GKI_ERR_UNSUPPORTED, "gki_index_build_records: need 1 <= modulo < 2^32");
+    return build_range(nullptr, nullptr, nullptr, nullptr, n, modulo, bucket_lo, bucket_hi, position_offset, flags, hashes_to_index, n_kmers,
+                       kmers_out, nodes_out, ref_out, af_out, freq_out, nullptr, stream, records);
+}
+
+int gki_partition_pack(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n, uint64_t modulo,
+                       int32_t n_parts, void *records_out, int64_t *counts_out, gki_stream_t stream) {
+    CallScope call(stream);
+    cudaStream_t s = call.stream;
+    GKI_REQUIRE(n >= 0 && n < (1ll << 31) && n_parts >= 1 && n_parts <= PP_MAX_PARTS && modulo >= 1 && modulo < (1ull << 32) && counts_out &&
+                    (n == 0 || (kmers && records_out)),
+                GKI_ERR_INVALID, "gki_partition_pack: bad arguments (n_parts <= 32)");
+    GKI_REQUIRE(n == 0 || (is_device_ptr(records_out) && (((uintptr_t)records_out & 31) == 0)), GKI_ERR_INVALID,
+                "gki_partition_pack: records_out must be 32-byte aligned device memory");
+    DevOut o_counts;
+    GKI_TRY(o_counts.prepare(counts_out, (size_t)n_parts * 8, s));
+    GKI_CUDA(cudaMemsetAsync(o_counts.dptr, 0, (size_t)n_parts * 8, s));
+    if (n > 0) {
+        DevIn d_kmers, d_nodes, d_ref, d_af;
+        GKI_TRY(d_kmers.stage(kmers, (size_t)n * 8, s));
+        GKI_TRY(d_nodes.stage(nodes, (size_t)n * 4, s));
+        GKI_TRY(d_ref.stage(ref_offsets, (size_t)n * 8, s));
+        GKI_TRY(d_af.stage(af, (size_t)n * 4, s));
+        const uint32_t part_size = (uint32_t)((modulo + n_parts - 1) / n_parts);
+        const int64_t n_tiles = (n + PP_TILE - 1) / PP_TILE;
+        const FastMod fm = make_fastmod(modulo);
+        Scratch hist;
+        GKI_TRY(hist.alloc((size_t)n_parts * n_tiles * 4, s));
+        part_hist_kernel<<<(unsigned)n_tiles, PP_THREADS, 0, s>>>(d_kmers.as<uint64_t>(), n, fm, part_size, n_parts, hist.as<uint32_t>(), n_tiles);
+        GKI_CHECK_LAUNCH();
+        GKI_TRY(exclusive_scan_u32(hist.as<uint32_t>(), hist.as<uint32_t>(), (int64_t)n_parts * n_tiles, nullptr, s));
+        part_counts_from_offsets_kernel<<<1, PP_MAX_PARTS, 0, s>>>(hist.as<uint32_t>(), n_tiles, n_parts, n, (long long *)o_counts.dptr);
+        GKI_CHECK_LAUNCH();
+        part_scatter_records_kernel<<<(unsigned)n_tiles, PP_THREADS, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(),
+                                                                             fm, part_size, n_parts, hist.as<uint32_t>(), n_tiles, (BinRecord *)records_out);
+        GKI_CHECK_LAUNCH();
+    }
+    GKI_TRY(o_counts.finish(s));
+    return call.finish();
 }
 
 int gki_partition_by_bucket_range(const uint64_t *kmers, int64_t n, uint64_t modulo, int32_t n_parts, uint32_t *perm_out,

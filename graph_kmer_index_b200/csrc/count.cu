@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -692,6 +693,46 @@ __global__ void node_counts_csr_kernel(TableView t, const uint32_t *__restrict__
         if (wrap16) w &= 0xFFFFu;
         const uint32_t node = nd & 0x7fffffffu;
         if (w && (int64_t)node < n_out) atomicAdd(out + node, (double)w);
+    }
+}
+
+// get_node_counts when the node-count vector is larger than L2 keeps (C3: 50 M nodes = 400 MB of float64): every addition is then a
+// read-modify-write of a random HBM line, two DRAM accesses each against a ceiling of ~37 G random accesses/s (590 M additions:
+// 31 ms).  Instead the per-entry weights are materialised once in slot order (streaming), and the additions are made in passes over
+// node ranges whose counts stay in L2: each pass streams (node, weight) pairs -- 8 bytes per entry -- and adds the ones of its range.
+__global__ void entry_weights_kernel(TableView t, const uint32_t *__restrict__ cs_slot, const uint32_t *__restrict__ cs_node, int64_t n,
+                                     uint32_t *__restrict__ w, bool wrap16) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t v = read_orientation(slot_counters(t, __ldg(cs_slot + i)), __ldg(cs_node + i) >> 31);
+        w[i] = wrap16 ? (v & 0xFFFFu) : v;
+    }
+}
+struct U32x8 {
+    uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ld_stream_256(const void *p) {   // streamed once per pass: must not displace the counts of the pass's range
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    U32x8 r;
+    r.v[0] = (uint32_t)a; r.v[1] = (uint32_t)(a >> 32); r.v[2] = (uint32_t)b; r.v[3] = (uint32_t)(b >> 32);
+    r.v[4] = (uint32_t)c; r.v[5] = (uint32_t)(c >> 32); r.v[6] = (uint32_t)d; r.v[7] = (uint32_t)(d >> 32);
+    return r;
+}
+__global__ void node_counts_slice_kernel(const uint32_t *__restrict__ cs_node, const uint32_t *__restrict__ w, int64_t n, double *__restrict__ out,
+                                         uint32_t lo, uint32_t hi) {
+    const int64_t n8 = n >> 3;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n8; q += (int64_t)gridDim.x * blockDim.x) {
+        const U32x8 nd = ld_stream_256(cs_node + 8 * q), wt = ld_stream_256(w + 8 * q);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t a = nd.v[j] & 0x7fffffffu;
+            if (wt.v[j] && a >= lo && a < hi) atomicAdd(out + a, (double)wt.v[j]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+        const int64_t i = (n8 << 3) + threadIdx.x;
+        const uint32_t a = cs_node[i] & 0x7fffffffu;
+        if (w[i] && a >= lo && a < hi) atomicAdd(out + a, (double)w[i]);
     }
 }
 
@@ -1380,8 +1421,28 @@ int gki_count_packed_reads(gki_index_t *ix, const uint64_t *packed, int64_t n_re
     if (n_reads == 0 || read_len < k) return GKI_OK;
     GKI_REQUIRE(packed, GKI_ERR_INVALID, "gki_count_packed_reads: packed is NULL");
     GKI_TRY(ensure_table(ix, k, call.stream));
+    const int64_t row_bytes = (int64_t)((read_len + 31) / 32) * 8;
+    if (!is_device_ptr(packed) && n_reads * row_bytes >= ((int64_t)48 << 20)) {
+        // a large host batch crosses the bus in chunks: the copy of chunk c+1 overlaps the count kernel of chunk c
+        cudaStream_t s = call.stream;
+        int64_t chunk_reads = (((int64_t)32 << 20) / row_bytes) & ~31ll;
+        GKI_TRY(ensure_staging(ix, (size_t)chunk_reads * row_bytes + 16));
+        int c = 0;
+        for (int64_t off = 0; off < n_reads; off += chunk_reads, ++c) {
+            const int bsel = c & 1;
+            const int64_t cnt = n_reads - off < chunk_reads ? n_reads - off : chunk_reads;
+            if (c >= 2) GKI_CUDA(cudaStreamWaitEvent(ix->copy_stream, ix->done[bsel], 0));
+            GKI_CUDA(cudaMemcpyAsync(ix->stage[bsel], (const char *)packed + off * row_bytes, (size_t)(cnt * row_bytes), cudaMemcpyHostToDevice, ix->copy_stream));
+            GKI_CUDA(cudaEventRecord(ix->ready[bsel], ix->copy_stream));
+            GKI_CUDA(cudaStreamWaitEvent(s, ix->ready[bsel], 0));
+            GKI_TRY(launch_count_packed_reads(ix, (const uint64_t *)ix->stage[bsel], cnt, read_len, k, both_strands, s));
+            GKI_CUDA(cudaEventRecord(ix->done[bsel], s));
+        }
+        GKI_CUDA(cudaStreamSynchronize(s));
+        return GKI_OK;
+    }
     DevIn d;
-    GKI_TRY(d.stage(packed, (size_t)n_reads * ((read_len + 31) / 32) * 8, call.stream));
+    GKI_TRY(d.stage(packed, (size_t)(n_reads * row_bytes), call.stream));
     GKI_TRY(launch_count_packed_reads(ix, d.as<uint64_t>(), n_reads, read_len, k, both_strands, call.stream));
     return call.finish();
 }
@@ -1470,7 +1531,23 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
     if (ix->table.buckets) {
         const bool wrap = (flags & GKI_COUNTS_WRAP_UINT16) != 0;
         const int grid = grid_for(ix->n, 256 * 4, device_info().sms * 16);
-        if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);
+        size_t slice_bytes = (size_t)64 << 20;   // node counts per pass: must stay in L2 (126 MB) next to the streams
+        if (const char *e = getenv("GKI_NODE_SLICE_MB")) slice_bytes = (size_t)(atoi(e) > 0 ? atoi(e) : 0) << 20;
+        if (ix->cs_slot && slice_bytes && (size_t)n_out * 8 > slice_bytes + (slice_bytes >> 1)) {
+            Scratch w;
+            GKI_TRY(w.alloc((size_t)ix->n * 4, call.stream));
+            entry_weights_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, w.as<uint32_t>(), wrap);
+            GKI_CHECK_LAUNCH();
+            const int64_t passes = ((int64_t)n_out * 8 + (int64_t)slice_bytes - 1) / (int64_t)slice_bytes;
+            const int64_t per = (n_out + passes - 1) / passes;
+            const int grid4 = grid_for(ix->n / 8 + 1, 256, device_info().sms * 16);
+            for (int64_t p = 0; p < passes; p++) {
+                const int64_t lo = p * per, hi = std::min<int64_t>(n_out, lo + per);
+                if (lo >= hi) break;
+                node_counts_slice_kernel<<<grid4, 256, 0, call.stream>>>(ix->cs_node, w.as<uint32_t>(), ix->n, o.as<double>(), (uint32_t)lo, (uint32_t)hi);
+                GKI_CHECK_LAUNCH();
+            }
+        } else if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);
         else node_counts_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->kmers, ix->nodes, ix->n, o.as<double>(), n_out, wrap);
         GKI_CHECK_LAUNCH();
     }

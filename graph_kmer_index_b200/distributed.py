@@ -122,11 +122,12 @@ def build_index_partitioned(hashes, nodes, ref_offsets, allele_frequencies, modu
     """Hash-range partitioned index build over the ranks of the default process group (NCCL, one process per GPU).
 
     Every rank passes its own shard of the FlatKmers as device tensors (int64 / int32 / int64 / float32 views of the
-    reference's uint64 / uint32 / uint64 / float32 columns); the global input order is rank-major.  Entries travel to
-    the rank that owns their bucket range (one all-to-all per column), each rank builds its slice with
-    gki_index_build_range, and the slices concatenated in rank order are exactly the single-GPU index of the
-    concatenated FlatKmers.  Returns a dict of device tensors: the local slice, or -- with replicate=True -- the whole
-    index on every rank."""
+    reference's uint64 / uint32 / uint64 / float32 columns); the global input order is rank-major.  Every rank orders its
+    shard by the rank that owns the bucket range and packs it into 32-byte records in one pass (gki_partition_pack); the
+    per-destination counts of all ranks travel with one all-gather, the records with ONE all-to-all; each rank builds its
+    slice straight from the records it received (gki_index_build_records), and the slices concatenated in rank order are
+    exactly the single-GPU index of the concatenated FlatKmers.  Returns a dict of device tensors: the local slice, or --
+    with replicate=True -- the whole index on every rank (one all-gather per array)."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -135,76 +136,73 @@ def build_index_partitioned(hashes, nodes, ref_offsets, allele_frequencies, modu
     dev = hashes.device
     n = int(hashes.shape[0])
     stream = _lib.current_stream()
-    cols = {"kmers": hashes, "nodes": nodes, "ref_offsets": ref_offsets, "allele_frequencies": allele_frequencies}
-    cols = {k: v for k, v in cols.items() if v is not None}
-    # 1. order the local entries by owner
-    perm = torch.empty(n, dtype=torch.int32, device=dev)
+    have = {"nodes": nodes is not None, "ref_offsets": ref_offsets is not None, "allele_frequencies": allele_frequencies is not None}
+    # 1. order the local entries by owner, packed
+    records = torch.empty((max(n, 1), 4), dtype=torch.int64, device=dev)
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    _lib.call("gki_partition_by_bucket_range", _lib.ptr(hashes), n, int(modulo), world, _lib.ptr(perm), _lib.ptr(counts), stream)
-    send = {}
-    for name, col in cols.items():
-        out = torch.empty_like(col)
-        _lib.call("gki_gather", _lib.ptr(col), col.element_size(), _lib.ptr(perm), n, _lib.ptr(out), stream)
-        send[name] = out
-    # 2. all-to-all by bucket range
-    recv_counts = torch.empty_like(counts)
+    _lib.call("gki_partition_pack", _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref_offsets), _lib.ptr(allele_frequencies), n, int(modulo), world,
+              _lib.ptr(records), _lib.ptr(counts), stream)
+    # 2. who sends how much to whom: one all-gather of the count vectors, one read-back
+    matrix = torch.empty((world, world), dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_to_all_single(recv_counts, counts)
+        dist.all_gather_into_tensor(matrix, counts)
     else:
-        recv_counts.copy_(counts)
-    in_splits, out_splits = counts.tolist(), recv_counts.tolist()
-    n_local = int(sum(out_splits))
-    recv = {}
-    for name, col in send.items():
-        buf = torch.empty(n_local, dtype=col.dtype, device=dev)
-        if world > 1:
-            dist.all_to_all_single(buf, col, output_split_sizes=out_splits, input_split_sizes=in_splits)
-        else:
-            buf.copy_(col)
-        recv[name] = buf
-    # 3. global position of the first local entry = entries owned by lower ranks
-    totals = torch.zeros(world, dtype=torch.int64, device=dev)
-    totals[rank] = n_local
+        matrix[0] = counts
+    matrix = matrix.cpu()
+    in_splits, out_splits = matrix[rank].tolist(), matrix[:, rank].tolist()
+    totals = matrix.sum(dim=0).tolist()                      # entries owned by every rank
+    n_local, offset = int(totals[rank]), int(sum(totals[:rank]))
+    # 3. ONE all-to-all of the records
+    recv = torch.empty((max(n_local, 1), 4), dtype=torch.int64, device=dev)
     if world > 1:
-        dist.all_reduce(totals)
-    totals = totals.tolist()
-    offset = int(sum(totals[:rank]))
-    # 4. local slice
+        dist.all_to_all_single(recv[:n_local], records[:n], output_split_sizes=out_splits, input_split_sizes=in_splits)
+    else:
+        recv[:n_local].copy_(records[:n])
+    del records
+    # 4. local slice, built from the records
     lo, hi = bucket_range(modulo, rank, world)
     h2i = torch.empty(hi - lo, dtype=torch.int32, device=dev)
     nk = torch.empty(hi - lo, dtype=torch.int32, device=dev)
-    outs = {name: torch.empty_like(col) for name, col in recv.items()}
+    outs = {"kmers": torch.empty(n_local, dtype=torch.int64, device=dev)}
+    if have["nodes"]:
+        outs["nodes"] = torch.empty(n_local, dtype=torch.int32, device=dev)
+    if have["ref_offsets"]:
+        outs["ref_offsets"] = torch.empty(n_local, dtype=torch.int64, device=dev)
+    if have["allele_frequencies"]:
+        outs["allele_frequencies"] = torch.empty(n_local, dtype=torch.float32, device=dev)
     freq = torch.empty(n_local, dtype=torch.int16, device=dev)
     if n_local:
-        _lib.call("gki_index_build_range", _lib.ptr(recv["kmers"]), _lib.ptr(recv.get("nodes")), _lib.ptr(recv.get("ref_offsets")),
-                  _lib.ptr(recv.get("allele_frequencies")), n_local, int(modulo), lo, hi, offset,
+        _lib.call("gki_index_build_records", _lib.ptr(recv), n_local, int(modulo), lo, hi, offset,
                   _lib.GKI_BUILD_SKIP_FREQUENCIES if skip_frequencies else 0, _lib.ptr(h2i), _lib.ptr(nk), _lib.ptr(outs["kmers"]),
                   _lib.ptr(outs.get("nodes")), _lib.ptr(outs.get("ref_offsets")), _lib.ptr(outs.get("allele_frequencies")), _lib.ptr(freq), stream)
     else:
         h2i.zero_()
         nk.zero_()
+    del recv
     local = dict(hashes_to_index=h2i, n_kmers=nk, frequencies=freq, bucket_range=(lo, hi), position_offset=offset, n_total=int(sum(totals)), **outs)
     if not replicate or world == 1:
         return local
-    # 5. replicate: every rank broadcasts its slice into the full arrays
+    # 5. replicate: one all-gather per array (slices padded to the largest, NCCL gathers equal sizes), cut back to size on arrival
     n_total = int(sum(totals))
-    full = dict(hashes_to_index=torch.empty(int(modulo), dtype=torch.int32, device=dev),
-                n_kmers=torch.empty(int(modulo), dtype=torch.int32, device=dev),
-                frequencies=torch.empty(n_total, dtype=torch.int16, device=dev))
+
+    def gather(local_tensor, sizes, total):
+        widest = max(sizes)
+        padded = torch.zeros(widest, dtype=local_tensor.dtype, device=dev)
+        padded[:local_tensor.shape[0]] = local_tensor
+        everyone = torch.empty((world, widest), dtype=local_tensor.dtype, device=dev)
+        dist.all_gather_into_tensor(everyone.view(torch.uint8).view(-1), padded.view(torch.uint8))      # byte view: NCCL has no int16
+        full = torch.empty(total, dtype=local_tensor.dtype, device=dev)
+        at = 0
+        for r in range(world):
+            full[at:at + sizes[r]] = everyone[r, :sizes[r]]
+            at += sizes[r]
+        return full
+
+    table_sizes = [bucket_range(modulo, r, world)[1] - bucket_range(modulo, r, world)[0] for r in range(world)]
+    full = dict(hashes_to_index=gather(h2i, table_sizes, int(modulo)), n_kmers=gather(nk, table_sizes, int(modulo)),
+                frequencies=gather(freq, totals, n_total))
     for name, col in outs.items():
-        full[name] = torch.empty(n_total, dtype=col.dtype, device=dev)
-    pos = 0
-    for r in range(world):
-        rlo, rhi = bucket_range(modulo, r, world)
-        slices = [(name, full[name][rlo:rhi]) for name in ("hashes_to_index", "n_kmers")]
-        slices += [(name, full[name][pos:pos + totals[r]]) for name in ["frequencies"] + list(outs)]
-        for name, sl in slices:
-            if sl.numel() == 0:
-                continue
-            if r == rank:
-                sl.copy_(local[name])
-            dist.broadcast(sl.view(torch.uint8), src=r)      # byte view: NCCL has no int16
-        pos += totals[r]
+        full[name] = gather(col, totals, n_total)
     full.update(bucket_range=(0, int(modulo)), position_offset=0, n_total=n_total)
     return full
 

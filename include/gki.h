@@ -105,6 +105,16 @@ int gki_index_build(const uint64_t *kmers, const uint32_t *nodes, const uint64_t
  *   position_offset (= entries owned by lower ranks) added, so the concatenation over ranks IS the global index. */
 int gki_partition_by_bucket_range(const uint64_t *kmers, int64_t n, uint64_t modulo, int32_t n_parts, uint32_t *perm_out,
                                   int64_t *counts_out, gki_stream_t stream);
+/* The same two steps with ONE exchange: gki_partition_pack orders the local FlatKmers by owner (stable) and emits them as packed
+ * 32-byte records {kmer, ref_offset, node | allele_frequency bits << 32, bucket} into records_out (device memory, n records,
+ * n_parts <= 32; absent columns travel as zeros); the caller sends counts_out[p] records to rank p with a single all-to-all
+ * and hands what it received, in source-rank order, to gki_index_build_records (arguments as gki_index_build_range). */
+int gki_partition_pack(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af, int64_t n,
+                       uint64_t modulo, int32_t n_parts, void *records_out, int64_t *counts_out, gki_stream_t stream);
+int gki_index_build_records(const void *records, int64_t n, uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi,
+                            int64_t position_offset, int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers,
+                            uint64_t *kmers_out, uint32_t *nodes_out, uint64_t *ref_out, float *af_out, uint16_t *freq_out,
+                            gki_stream_t stream);
 int gki_index_build_range(const uint64_t *kmers, const uint32_t *nodes, const uint64_t *ref_offsets, const float *af,
                           int64_t n, uint64_t modulo, uint64_t bucket_lo, uint64_t bucket_hi, int64_t position_offset,
                           int32_t flags, int32_t *hashes_to_index, uint32_t *n_kmers, uint64_t *kmers_out,

@@ -446,9 +446,70 @@ def test_partitioned_build_emulated_on_one_gpu(gki, world, n, heavy):
     assert np.array_equal(cat["freq"].view(np.uint16), want["_frequencies"])
 
 
-def test_node_counts_with_more_nodes_than_l2(gki):
-    """node ids spread over 12 M (96 MB of float64 counts, more than L2 keeps): same counts as the oracle"""
+@pytest.mark.parametrize("world,n,heavy,columns", [(1, 50_000, True, "all"), (2, 50_000, True, "all"), (8, 50_000, False, "all"), (2, 400_000, False, "all"),
+                                                   (3, 600_000, False, "all"), (4, 500_000, False, "narrow"), (32, 300_000, True, "all")])
+def test_partitioned_build_with_packed_records_emulated_on_one_gpu(gki, world, n, heavy, columns):
+    """the one-exchange form of the hash-range partitioned build (gki_partition_pack -> all-to-all of 32-byte records ->
+    gki_index_build_records), ranks emulated one after another: the slices concatenated in rank order are the oracle's index"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    from graph_kmer_index_b200.distributed import bucket_range, shard_bounds
+    modulo, k = (100_003 if heavy else 1_000_003), 31
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 777, k)
+    hashes = hashes.copy()
+    if heavy:
+        hashes[::17] = hashes[3]
+    else:
+        m3 = len(hashes[1::3])
+        hashes[:3 * m3:3] = hashes[1::3]
+    narrow = columns == "narrow"
+    want = c_oracle.build_index(hashes, nodes, ref if not narrow else np.zeros(n, np.uint64), af if not narrow else np.zeros(n, np.float32), modulo,
+                                skip_frequencies=narrow)
+    dev = torch.device("cuda")
+    sent = []                                   # sent[src] = (records, bounds)
+    for lo, hi in [shard_bounds(n, r, world) for r in range(world)]:
+        m = hi - lo
+        t = lambda a, dt: torch.from_numpy(a[lo:hi].view(dt)).to(dev)
+        records = torch.zeros((max(m, 1), 4), dtype=torch.int64, device=dev)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        _lib.call("gki_partition_pack", _lib.ptr(t(hashes, np.int64)), _lib.ptr(t(nodes, np.int32)), None if narrow else _lib.ptr(t(ref, np.int64)),
+                  None if narrow else _lib.ptr(t(af, np.float32)), m, modulo, world, _lib.ptr(records), _lib.ptr(counts), None)
+        torch.cuda.synchronize()
+        assert int(counts.sum()) == m
+        sent.append((records, np.concatenate([[0], np.cumsum(counts.cpu().numpy())])))
+    got = {key: [] for key in ("h2i", "nk", "kmers", "nodes", "ref", "af", "freq")}
+    offset = 0
+    for r in range(world):
+        recv = torch.cat([rec[b[r]:b[r + 1]] for rec, b in sent]).contiguous()
+        m = int(recv.shape[0])
+        lo, hi = bucket_range(modulo, r, world)
+        h2i = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+        nk = torch.zeros(hi - lo, dtype=torch.int32, device=dev)
+        o = dict(kmers=torch.empty(m, dtype=torch.int64, device=dev), nodes=torch.empty(m, dtype=torch.int32, device=dev),
+                 ref=torch.empty(m, dtype=torch.int64, device=dev), af=torch.empty(m, dtype=torch.float32, device=dev))
+        fr = torch.empty(m, dtype=torch.int16, device=dev)
+        if m:
+            _lib.call("gki_index_build_records", _lib.ptr(recv), m, modulo, lo, hi, offset, 1 if narrow else 0, _lib.ptr(h2i), _lib.ptr(nk), _lib.ptr(o["kmers"]),
+                      _lib.ptr(o["nodes"]), None if narrow else _lib.ptr(o["ref"]), None if narrow else _lib.ptr(o["af"]), _lib.ptr(fr), None)
+        torch.cuda.synchronize()
+        offset += m
+        for key, tns in (("h2i", h2i), ("nk", nk), ("kmers", o["kmers"]), ("nodes", o["nodes"]), ("ref", o["ref"]), ("af", o["af"]), ("freq", fr)):
+            got[key].append(tns.cpu().numpy())
+    cat = {key: np.concatenate(v) for key, v in got.items()}
+    assert np.array_equal(cat["h2i"], want["_hashes_to_index"]) and np.array_equal(cat["nk"].view(np.uint32), want["_n_kmers"])
+    assert np.array_equal(cat["kmers"].view(np.uint64), want["_kmers"]) and np.array_equal(cat["nodes"].view(np.uint32), want["_nodes"])
+    if not narrow:
+        assert np.array_equal(cat["ref"].view(np.uint64), want["_ref_offsets"]) and np.array_equal(cat["af"], want["_allele_frequencies"])
+    assert np.array_equal(cat["freq"].view(np.uint16), want["_frequencies"])
+
+
+@pytest.mark.parametrize("slice_mb", [None, "16", "1", "0"])
+def test_node_counts_with_more_nodes_than_l2(gki, monkeypatch, slice_mb):
+    """node ids spread over 12 M (96 MB of float64 counts, more than L2 keeps): same counts as the oracle, in one pass and in
+    passes over node ranges (gki_node_counts: weights materialised once, one pass per range of GKI_NODE_SLICE_MB of counts)"""
     from graph_kmer_index_b200 import synthetic
+    if slice_mb is not None:
+        monkeypatch.setenv("GKI_NODE_SLICE_MB", slice_mb)
     n, k, modulo, n_nodes = 300000, 31, 1000003, 12_000_000
     hashes, _, ref, af = synthetic.flat_kmers(n, 1000, k)
     rng = np.random.default_rng(8)
@@ -462,6 +523,9 @@ def test_node_counts_with_more_nodes_than_l2(gki):
     dev.prepare_counting(k)
     dev.count_reads(reads, k)
     assert np.array_equal(dev.node_counts(n_nodes), want)
+    assert np.array_equal(dev.node_counts(n_nodes + 12345), np.concatenate([want, np.zeros(12345)]))
+    want16 = c_oracle.node_counts_from_entry_counts(idx, c_oracle.count_reads(idx, reads, k) & np.uint32(0xffff), n_nodes)
+    assert np.array_equal(dev.node_counts(n_nodes, wrap_uint16=True), want16)
     dev.close()
 
 

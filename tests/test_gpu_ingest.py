@@ -163,3 +163,33 @@ def test_host_pipeline_other_shapes(gki, monkeypatch, L, k, table_k):
     dev.count_reads(reads[sample], k)
     assert np.array_equal(dev.node_counts(1000), c_oracle.read_node_counts(idx, reads[sample], k, 1000))
     dev.close()
+
+
+def test_large_host_packed_batch_is_chunked(gki):
+    """a host batch of 2-bit rows above 48 MB crosses the bus in chunks that overlap the count kernels: same counts as the same rows
+    resident on the device (which the tests above pin to the oracle)"""
+    import torch
+    from graph_kmer_index_b200 import _lib, synthetic
+    from graph_kmer_index_b200.read_kmers import pack_reads
+    n, k, L, modulo = 200000, 31, 150, 1000003
+    idx, dev = make_index(gki, n, k, modulo)
+    n_reads = 1_400_003
+    glen = synthetic.genome_length(n, k)
+    genome = torch.empty(glen, dtype=torch.uint8, device="cuda")
+    _lib.call("gki_synth_genome", _lib.ptr(genome), glen, None)
+    d_reads = torch.empty((n_reads, L), dtype=torch.uint8, device="cuda")
+    _lib.call("gki_synth_reads", _lib.ptr(genome), glen, 0, n_reads, L, 300, 0, _lib.ptr(d_reads), None)
+    torch.cuda.synchronize()
+    packed, dirty = pack_reads(d_reads.cpu().numpy(), n_threads=4)
+    assert len(dirty) == 0 and packed.nbytes > (48 << 20)
+    dev.count_packed_reads(torch.from_numpy(packed.view(np.int64)).cuda(), L, k)
+    want = dev.node_counts(1000)
+    assert want.sum() > 0
+    dev.reset_counts()
+    dev.count_packed_reads(packed, L, k)                                    # pageable host rows, chunked
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.reset_counts()
+    pinned = torch.from_numpy(packed.view(np.int64)).pin_memory()
+    dev.count_packed_reads(pinned, L, k)                                    # pinned host rows, chunked
+    assert np.array_equal(dev.node_counts(1000), want)
+    dev.close()
