@@ -1037,8 +1037,8 @@ struct Pipeline {
     PackJob job;
     std::atomic<int64_t> next{0};
     std::atomic<int> failed{0};
-    uint64_t calls = 0;              // large host batches seen; rate[d]: bytes/s of the last one run without (0) / with (1) the copy lane
-    double rate[2] = {0.0, 0.0};
+    uint64_t calls = 0;              // large host batches seen; rate[m]: bytes/s of the last one run in mode m: packing lanes alone (0),
+    double rate[3] = {0.0, 0.0, 0.0};   // lanes + the copy-engine lane (1), the copy engine alone (2)
     std::vector<int64_t> deferred;   // units left to the ASCII path (too many dirty reads); guarded by mu
     std::string error;               // guarded by mu
 
@@ -1167,6 +1167,26 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
     GKI_TRY(ensure_staging(ix, (size_t)ASCII_UNITS * UNIT_READS * read_len + 16));
     GKI_CUDA(cudaEventRecord(p->start, s));            // lane kernels follow whatever the caller queued on s
     for (PackLane &L : p->lanes) GKI_CUDA(cudaStreamWaitEvent(L.stream, p->start, 0));
+    // The copy engine and the packing threads read the same host memory, and which mix pays depends on the host and on how many
+    // ranks share it: on the 16-thread bench box 14 packers alone are faster than packers + an ASCII transfer lane (13.7 ms vs 15.5 ms
+    // per 1.5 GB), on the 24-thread two-GPU box the copy lane adds 19 %, and with eight ranks on one host (three lanes each, all
+    // reading one memory system) every GPU's own PCIe link alone can be the fastest way in.  So the pipeline tries its three modes
+    // -- lanes alone (0), lanes + copy lane (1), copy engine alone (2) -- twice each on its first large calls and keeps the fastest
+    // (bytes per second of the whole call), looking at another mode again every 64th call.  GKI_PIPELINE_DMA=0/1/2 overrides.
+    int mode = row_offsets ? 0 : 1;
+    const bool adaptive = !row_offsets && !getenv("GKI_PIPELINE_DMA");
+    if (const char *e = getenv("GKI_PIPELINE_DMA")) mode = row_offsets ? 0 : (atoi(e) < 0 ? 0 : (atoi(e) > 2 ? 2 : atoi(e)));
+    if (adaptive) {
+        const uint64_t call_no = p->calls++;
+        int best = 0;
+        for (int m = 1; m < 3; m++)
+            if (p->rate[m] > p->rate[best]) best = m;
+        if (call_no == 0) mode = 1;                                   // first call: warm-up, not recorded
+        else if (call_no <= 6) mode = (int)(call_no % 3);             // every mode twice (the better trial is kept)
+        else if (call_no % 64 == 63) mode = (best + 1 + (int)((call_no / 64) & 1)) % 3;   // a look at a losing mode
+        else mode = best;
+    }
+    const bool dma_lane = mode >= 1, use_lanes = mode <= 1;
     {
         std::lock_guard<std::mutex> lock(p->mu);
         p->job.reads = reads;
@@ -1181,10 +1201,10 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
         p->failed.store(0);
         p->deferred.clear();
         p->error.clear();
-        p->running = n_lanes;
-        p->generation++;
+        p->running = use_lanes ? n_lanes : 0;
+        if (use_lanes) p->generation++;
     }
-    p->cv.notify_all();
+    if (use_lanes) p->cv.notify_all();
     // the calling thread feeds the copy engine with ASCII transfers (double-buffered staging, kernels on s)
     int slot = 0;
     bool staged[2] = {false, false};
@@ -1211,20 +1231,6 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
         return GKI_OK;
     };
     int rc = GKI_OK;
-    // The copy engine and the packing threads read the same host memory, and whether an ASCII transfer next to the packers pays
-    // depends on the host: on the 16-thread bench box 14 packers alone are faster (13.7 ms vs 15.5 ms per 1.5 GB), on the
-    // 24-thread two-GPU box the copy lane adds 19 %.  So the pipeline tries both twice on its first large calls and keeps the faster
-    // (bytes per second of the whole call), looking at the other again every 64th call.  GKI_PIPELINE_DMA=0/1 overrides.
-    bool dma_lane = !row_offsets;
-    const bool adaptive = !row_offsets && !getenv("GKI_PIPELINE_DMA");
-    if (const char *e = getenv("GKI_PIPELINE_DMA")) dma_lane = !row_offsets && atoi(e) != 0;
-    if (adaptive) {
-        const uint64_t call_no = p->calls++;
-        if (call_no == 0) dma_lane = true;                                                   // first call: warm-up, not recorded
-        else if (call_no <= 4) dma_lane = (call_no & 1) != 0;                                // then with / without, twice each (best kept)
-        else if (call_no % 64 == 63) dma_lane = !(p->rate[1] >= p->rate[0]);                 // a look at the losing side
-        else dma_lane = p->rate[1] >= p->rate[0];
-    }
     const auto t_start = std::chrono::steady_clock::now();
     while (dma_lane && rc == GKI_OK && !p->failed.load(std::memory_order_relaxed)) {
         const int64_t u = p->next.fetch_add(ASCII_UNITS);
@@ -1243,10 +1249,10 @@ static int count_reads_host_pipeline(gki_index *ix, const uint8_t *reads, const 
         const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
         if (secs > 0 && p->calls > 1) {
             const double rate = (double)n_reads * read_len / secs;
-            double &slot = p->rate[dma_lane ? 1 : 0];
-            slot = (p->calls <= 5 && slot > rate) ? slot : rate;   // exploration keeps the better of its two trials per mode
-            if (getenv("GKI_PIPELINE_DEBUG")) fprintf(stderr, "[gki pipeline] call %llu dma=%d %.1f GB/s (best: without %.1f, with %.1f)\n",
-                                                      (unsigned long long)p->calls, (int)dma_lane, rate / 1e9, p->rate[0] / 1e9, p->rate[1] / 1e9);
+            double &slot = p->rate[mode];
+            slot = (p->calls <= 7 && slot > rate) ? slot : rate;   // exploration keeps the better of its two trials per mode
+            if (getenv("GKI_PIPELINE_DEBUG")) fprintf(stderr, "[gki pipeline] call %llu mode=%d %.1f GB/s (best: lanes %.1f, lanes+copy %.1f, copy %.1f)\n",
+                                                      (unsigned long long)p->calls, mode, rate / 1e9, p->rate[0] / 1e9, p->rate[1] / 1e9, p->rate[2] / 1e9);
         }
     }
     if (rc == GKI_OK && p->failed.load()) {

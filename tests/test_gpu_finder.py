@@ -188,3 +188,38 @@ def test_kmer_index2_after_the_reference_tests():
         rows = flat._hashes == kmer
         assert index.get_kmer_frequency(kmer) == len(set(zip(flat._start_nodes[rows].tolist(), flat._start_offsets[rows].tolist())))
         assert np.array_equal(index.get_nodes(kmer), flat._nodes[rows])            # rows of a key come back in input order
+
+
+def test_config5_chunk_digests():
+    """BASELINE config 5 at full size (100 k variants, 30 Mbp, k=31, max_variant_nodes=5): every critical-path chunk of the device
+    finder has the row count and the SHA-256 of the ordered rows that the UNMODIFIED reference produced for that chunk
+    (tests/golden/finder_c5.json from make_golden_c5.py, chunked like `graph_kmer_index index -t T`, cli:588-608)."""
+    import hashlib
+    import json
+    import os
+    import graph_kmer_index_b200 as gki
+    from graph_kmer_index_b200 import synthetic
+    from conftest import GOLDEN
+    path = os.path.join(GOLDEN, "finder_c5.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/finder_c5.json not generated")
+    g = json.load(open(path))
+    seqs, edges, linear, af = synthetic.variant_graph(g["n_variants"], spacing=g["spacing"], seed=g["seed"], p_deletion=g["p_deletion"])
+    arrays = Graph.from_dicts(seqs, edges, linear, af).to_arrays()
+    crit = gki.CriticalGraphPaths.from_graph(arrays, g["k"])
+    assert len(crit) == g["n_critical_paths"]
+    total = 0
+    for (s, e), want_rows, want_sha in zip(g["chunks"], g["rows"], g["sha256"]):
+        finder = gki.DenseKmerFinder(arrays, g["k"], critical_graph_paths=crit, max_variant_nodes=g["max_variant_nodes"],
+                                     start_at_critical_path_number=s, stop_at_critical_path_number=e)
+        finder.find()
+        r = finder._results
+        h = hashlib.sha256()
+        for key, dtype in (("kmers", np.int64), ("nodes", np.int32), ("start_nodes", np.int32), ("start_offsets", np.int16), ("allele_frequencies", np.float64)):
+            a = np.ascontiguousarray(r[key])
+            assert a.dtype == dtype, (key, a.dtype)
+            h.update(a.tobytes())
+        assert len(r["kmers"]) == want_rows, (s, e, len(r["kmers"]), want_rows)
+        assert h.hexdigest() == want_sha, (s, e)
+        total += want_rows
+    assert total == g["total_rows"]

@@ -470,10 +470,11 @@ def test_partitioned_build_with_packed_records_emulated_on_one_gpu(gki, world, n
     for lo, hi in [shard_bounds(n, r, world) for r in range(world)]:
         m = hi - lo
         t = lambda a, dt: torch.from_numpy(a[lo:hi].view(dt)).to(dev)
+        d_h, d_n, d_r, d_a = t(hashes, np.int64), t(nodes, np.int32), t(ref, np.int64), t(af, np.float32)      # alive until the call has run
         records = torch.zeros((max(m, 1), 4), dtype=torch.int64, device=dev)
         counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        _lib.call("gki_partition_pack", _lib.ptr(t(hashes, np.int64)), _lib.ptr(t(nodes, np.int32)), None if narrow else _lib.ptr(t(ref, np.int64)),
-                  None if narrow else _lib.ptr(t(af, np.float32)), m, modulo, world, _lib.ptr(records), _lib.ptr(counts), None)
+        _lib.call("gki_partition_pack", _lib.ptr(d_h), _lib.ptr(d_n), None if narrow else _lib.ptr(d_r), None if narrow else _lib.ptr(d_a), m, modulo, world,
+                  _lib.ptr(records), _lib.ptr(counts), None)
         torch.cuda.synchronize()
         assert int(counts.sum()) == m
         sent.append((records, np.concatenate([[0], np.cumsum(counts.cpu().numpy())])))

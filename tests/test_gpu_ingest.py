@@ -60,12 +60,15 @@ def test_count_packed_reads_vs_oracle(gki, monkeypatch, minimizer_filter, n, mod
     dev.close()
 
 
-@pytest.mark.parametrize("threads", ["12", "3", "1", "0"])     # 12: packing lanes only, no copy-engine lane
-def test_host_pipeline_vs_device_path(gki, monkeypatch, threads):
-    """a host batch large enough for the packing lanes: same node counts as the device-resident path and the oracle"""
+@pytest.mark.parametrize("threads,mode", [("12", None), ("3", None), ("1", None), ("0", None), ("3", "0"), ("3", "1"), ("3", "2")])
+def test_host_pipeline_vs_device_path(gki, monkeypatch, threads, mode):
+    """a host batch large enough for the packing lanes: same node counts as the device-resident path and the oracle, with the mode
+    chosen adaptively (calls cycle through lanes alone / lanes + copy lane / copy engine alone) or forced by GKI_PIPELINE_DMA"""
     import torch
     from graph_kmer_index_b200 import synthetic
     monkeypatch.setenv("GKI_PACK_THREADS", threads)
+    if mode is not None:
+        monkeypatch.setenv("GKI_PIPELINE_DMA", mode)
     n, k, L, modulo = 200000, 31, 150, 1000003
     idx, dev = make_index(gki, n, k, modulo)
     n_reads = 5 * 131072 + 777
