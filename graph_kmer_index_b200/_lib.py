@@ -40,7 +40,8 @@ def build(force=False, verbose=False):
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()      # linked beside the target and renamed: a reader never sees a half-written library
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
+    knobs = ["-DGKI_EXPERIMENT_KNOBS"] if os.environ.get("GKI_BUILD_EXPERIMENT_KNOBS") == "1" else []   # profiles/ sweeps only (csrc/common.cuh)
+    cmd = [nvcc] + NVCC_FLAGS + knobs + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + _sources()
     try:
         out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     except FileNotFoundError as e:

@@ -50,6 +50,17 @@ struct CallScope {
 };
 void note_host_io();
 
+// ------------------------------------------------------------------ experiment knobs
+// Environment variables that only exist for the sweeps under profiles/ (kernel variants, occupancy, tile sizes) are read only in a
+// library built with -DGKI_EXPERIMENT_KNOBS; the shipped build answers "unset" and compiles none of the variant kernels.
+// Operational and test-forcing variables (GKI_PACK_THREADS, GKI_PIPELINE_DMA, GKI_BUILD_PATH, GKI_FILTER_*, ...) use getenv directly.
+#ifdef GKI_EXPERIMENT_KNOBS
+#include <stdlib.h>
+inline const char *experiment_knob(const char *name) { return getenv(name); }
+#else
+inline const char *experiment_knob(const char *) { return nullptr; }
+#endif
+
 // ------------------------------------------------------------------ device properties
 struct DeviceInfo {
     int device = -1;

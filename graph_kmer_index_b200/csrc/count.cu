@@ -758,7 +758,7 @@ void destroy_count_table(gki_index *ix) {
 // Build the table on first use.  k > 0 selects canonical keys (needs every index k-mer < 4^k), k == 0 raw keys.
 static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     if (ix->table.buckets) return GKI_OK;
-    if (const char *e = getenv("GKI_L2_FETCH")) {   // experiment knob: L2 fetch granularity for misses (32 / 64 / 128 bytes)
+    if (const char *e = experiment_knob("GKI_L2_FETCH")) {   // experiment knob: L2 fetch granularity for misses (32 / 64 / 128 bytes)
         GKI_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
     }
     if (k < 0 || k > 31) k = 0;
@@ -900,7 +900,7 @@ static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t 
     int blocks_per_sm = 0;
     GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ>, COUNT_THREADS, smem));
     if (blocks_per_sm < 1) blocks_per_sm = 1;
-    if (const char *e = getenv("GKI_COUNT_CTAS")) {   // experiment knob: fewer resident CTAs per SM (occupancy sensitivity)
+    if (const char *e = experiment_knob("GKI_COUNT_CTAS")) {   // experiment knob: fewer resident CTAs per SM (occupancy sensitivity)
         const int v = atoi(e);
         if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v;
     }
@@ -940,7 +940,7 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     };
     auto warp_bytes = [&](int rpw) { return mz_offset(rpw) + (size_t)b.mz_len * 4; };
     int rpw = 8;
-    if (const char *e = getenv("GKI_RPW")) rpw = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
+    if (const char *e = experiment_knob("GKI_RPW")) rpw = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
     while (rpw > 1 && warp_bytes(rpw) * COUNT_WARPS > 56 * 1024) rpw >>= 1;
     GKI_REQUIRE(warp_bytes(rpw) * COUNT_WARPS <= 200 * 1024, GKI_ERR_UNSUPPORTED, "gki_count_reads: read_len %d too long for the tile path", read_len);
     b.rpw = rpw;
@@ -954,11 +954,13 @@ static int launch_count_reads(gki_index *ix, const uint8_t *dreads, int64_t n_re
     b.bulk_ok = (stride == read_len) && (((uintptr_t)dreads & 15) == 0) && (((int64_t)rpw * read_len) % 16 == 0);
     if (!both) return launch_count_reads_t<false, false, 4>(ix, b, s);
     if (ix->table.k != k) return launch_count_reads_t<true, false, 4>(ix, b, s);
-    int hints = 0;   // experiment knobs (profiles/tune_count.py): 7 = L2 eviction hints, 16 = drop the survivors, 64 = 64-byte L2 fills
-    if (const char *e = getenv("GKI_HINTS")) hints = atoi(e);
+#ifdef GKI_EXPERIMENT_KNOBS   // kernel variants of profiles/tune_count.py: 7 = L2 eviction hints, 16 = drop the survivors, 64 = 64-byte L2 fills
+    int hints = 0;
+    if (const char *e = experiment_knob("GKI_HINTS")) hints = atoi(e);
     if (hints == 7) return launch_count_reads_t<true, true, 4, 7>(ix, b, s);
     if (hints == 16) return launch_count_reads_t<true, true, 4, 16>(ix, b, s);
     if (hints == 64) return launch_count_reads_t<true, true, 4, 64>(ix, b, s);
+#endif
     return launch_paired<false>(ix, b, s);
 }
 

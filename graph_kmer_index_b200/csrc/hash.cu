@@ -248,7 +248,7 @@ int gki_hash_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int6
             attr_set = true;
         }
         int ctas_per_sm = 8;   // measured: 4 -> 0.881 ms, 6 -> 0.844 ms, 8 -> 0.822 ms for 2 M x 150 bp reads (registers allow 8)
-        if (const char *e = getenv("GKI_HASH_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 8;
+        if (const char *e = experiment_knob("GKI_HASH_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 8;
         int grid = grid_for(b.n_tiles, 1, device_info().sms * ctas_per_sm);
         hash_reads_kernel<<<grid, HASH_THREADS, smem, call.stream>>>(b, of.as<uint64_t>(), orc.as<uint64_t>());
         GKI_CHECK_LAUNCH();

@@ -1,6 +1,8 @@
 """Sweep the K3 layout knobs on the c2 workload: Bloom filter budget (GKI_FILTER_MAX_MB), bits per key
 (GKI_FILTER_K), raw vs canonical keys (GKI_TABLE_RAW).  Prints kernel ms per launch; checks that the node counts are
-identical for every setting.  Usage: python profiles/tune_count.py [entries] [reads]"""
+identical for every setting.  Usage: python profiles/tune_count.py [entries] [reads]
+The kernel-variant knobs (GKI_HINTS, GKI_RPW, GKI_COUNT_CTAS) only exist in a library built with GKI_BUILD_EXPERIMENT_KNOBS=1
+(graph_kmer_index_b200/_lib.py: -DGKI_EXPERIMENT_KNOBS, csrc/common.cuh); the shipped build ignores them."""
 import json
 import os
 import sys
