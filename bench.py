@@ -502,26 +502,21 @@ def measure(args, cfg, name, rank, world, local_rank, full):
         assert float(host_counts.sum().item()) == (total_counts if world == 1 else float(counts.sum().item()))
         lanes = int(os.environ.get("GKI_PACK_THREADS", max((os.cpu_count() or 2) - 2, 0) if world == 1 else
                                    max((os.cpu_count() or 2) // int(os.environ.get("LOCAL_WORLD_SIZE", world)) - 1, 0)))
-        # the ceiling of the host side: what this rank's lanes can read from the batch per second (all ranks probe at the same time, as
-        # they pack at the same time), against the ASCII bytes per second the e2e rate consumes
+        # The ceiling of the host side, measured under contention: this rank's packing lanes sweep the batch (gki_host_read_bandwidth) WHILE
+        # the copy engine moves the same pinned batch to the device -- the two ways the reads leave host memory, competing for it as they
+        # do inside the call; every rank probes at the same time, as every rank packs and copies at the same time.
         gbs = ctypes.c_double()
-        barrier()
-        _lib.call("gki_host_read_bandwidth", host_reads.data_ptr(), int(R) * int(L), max(lanes, 1), ctypes.byref(gbs))
-        bw = torch.tensor([gbs.value], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(bw)                                   # sum over ranks: aggregate host read bandwidth
-        host_read_gbs = float(bw.item())
-        # ... and what the copy engine moves from the same pinned batch over this GPU's PCIe link
         barrier()
         ca, cb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ca.record()
         reads.copy_(host_reads, non_blocking=True)
         cb.record()
+        _lib.call("gki_host_read_bandwidth", host_reads.data_ptr(), int(R) * int(L), max(lanes, 1), ctypes.byref(gbs))
         torch.cuda.synchronize()
-        pcie = torch.tensor([R * L / (ca.elapsed_time(cb) / 1e3) / 1e9], dtype=torch.float64, device=dev)
+        both = torch.tensor([gbs.value, R * L / (ca.elapsed_time(cb) / 1e3) / 1e9], dtype=torch.float64, device=dev)
         if world > 1:
-            dist.all_reduce(pcie)
-        pcie_gbs = float(pcie.item())
+            dist.all_reduce(both)                                 # sums over the ranks
+        host_read_gbs, pcie_gbs = float(both[0].item()), float(both[1].item())
         ascii_gbs = e2e_value / nk_per_read * L / 1e9
         ceiling = host_read_gbs + pcie_gbs
         e2e = {"value": e2e_value, "unit": "kmers/s",
@@ -531,7 +526,8 @@ def measure(args, cfg, name, rank, world, local_rank, full):
                "note": "per GPU bytes of the caller's ASCII reads (1 byte per base); inside the call pack_lanes host threads re-encode "
                        "chunks to 2 bits per base before the bus while the copy engine moves the other chunks as ASCII (csrc/count.cu); "
                        "host_frac = ASCII bytes consumed per second / (host-DRAM read bandwidth of the packing lanes on this batch + copy-engine "
-                       "rate of the same pinned batch), both measured here, summed over the ranks (all ranks probe at once)"}
+                       "rate of the same pinned batch), the two measured here at the same time (they compete for host memory as inside the call) "
+                       "and summed over the ranks (all ranks probe at once)"}
         # the call a KAGE user makes (cfki:33-40): pageable numpy reads through CounterKmerIndex, node counts returned as a fresh numpy array
         pageable = np.empty((R, L), dtype=np.uint8)
         pageable[:] = host_reads.numpy()
@@ -541,15 +537,17 @@ def measure(args, cfg, name, rank, world, local_rank, full):
         def e2e_pageable_step():
             counter.reset()
             counter.count_reads(pageable, k)
-            got["counts"] = counter.get_node_counts(n_nodes)
-            if world > 1:
-                c = torch.from_numpy(got["counts"]).to(dev)
-                distributed.allreduce_node_counts(c)
-                got["counts"] = c.cpu().numpy()
+            if world == 1:
+                got["counts"] = counter.get_node_counts(n_nodes)
+            else:                                        # what distributed.count_reads_sharded does after counting its shard
+                index.node_counts(n_nodes, out=counts)
+                distributed.allreduce_node_counts(counts)
+                got["counts"] = counts.cpu().numpy()
 
         pg_steps = max(1, min(args.steps, 5))
         e2e["pageable_numpy"] = {"value": run_e2e(e2e_pageable_step, 8, pg_steps), "unit": "kmers/s", "steps": pg_steps,
-                                 "call": "CounterKmerIndex.reset(); .count_reads(numpy uint8 reads, k); .get_node_counts(n_nodes) -> numpy float64"}
+                                 "call": "CounterKmerIndex.reset(); .count_reads(numpy uint8 reads, k); .get_node_counts(n_nodes) -> numpy float64"
+                                         if world == 1 else "CounterKmerIndex.reset(); .count_reads(numpy uint8 reads, k); node counts all-reduced on the device -> numpy float64"}
         assert float(got["counts"].sum()) == float(host_counts.sum().item())
         # callers that already hold 2-bit packed reads (read_kmers.pack_reads layout): gki_count_packed_reads on a pinned host batch
         if world == 1 or full:

@@ -556,6 +556,13 @@ bin_finish_small_kernel(BinParams p, const uint32_t *__restrict__ bin_start, con
 //       dense tables are written for every bucket of the bin, empty ones included (no memset, no table scatter).
 // A bin that receives more than SLAB_CAP records (tiny modulo, one k-mer repeated thousands of times) raises a flag and the build
 // falls back to the 16-entry-bin path above, then to the radix path.
+// What bounds the scatter (profiles/r2/calibrate_append.jsonl, calibrate_store_groups.jsonl, slab_scatter_l2_hints.log): a 32-byte store
+// whose sector is not already in L2 costs one request out of ~36-40 G/s chip-wide, for 8 M tiny bins and for 40 K append cursors alike
+// and whatever the L2 eviction hint; stores to resident sectors retire at 160+ G/s and whole-line stores cost one request per line.  A
+// windowed form that exploited this (entries partitioned into windows of 296 bins with smem-staged tiles, then a persistent kernel
+// scattering each window into an L2-resident ring of slabs and finishing the previous window) was built, was bit-exact, and ran 3x
+// SLOWER (9.8 ms vs 3.0 ms at 60 M entries): with only a window's 296 bin counters live, the slot-assigning atomics serialise per
+// address (~110 ns each).  It was removed; profiles/r2/window_build_experiment_*.
 constexpr int SLAB_CAP = 2048;        // records per slab (64 KB of shared memory)
 constexpr int SLAB_THREADS = 512;
 constexpr int SLAB_NB_MAX = 16384;    // buckets per bin (packed 16-bit counters in shared memory)
@@ -811,316 +818,6 @@ slab_finish_kernel(SlabParams p, const uint32_t *__restrict__ count, const uint3
     for (uint32_t bin = blockIdx.x; bin < p.n_bins; bin += gridDim.x) {
         const uint32_t c = min(__ldg(count + bin), (uint32_t)SLAB_CAP);
         slab_finish_bin(p, m, phase, slab + (size_t)bin * SLAB_CAP, c, __ldg(bin_start + bin), bin, o, tables_vec);
-    }
-}
-
-// ---- windowed build: the slab scatter confined to L2 ------------------------------------------------------------------------------
-// What bounds the slab scatter above is not bytes: a 32-byte store whose sector is not yet in L2 costs one request of a budget of
-// ~36-40 G/s chip-wide, whether the destination is one of 8 M tiny bins or one of 40 K append cursors, and whatever the L2 eviction
-// hint (profiles/r2/calibrate_append.jsonl, calibrate_store_groups.jsonl, slab_scatter_l2_hints.log); stores whose sectors ARE resident
-// retire at 160+ G/s, and stores that cover whole lines cost one request per line.  So:
-//   pass A  (window_partition_kernel): the entries are partitioned into WINDOWS of consecutive bins with tiles staged in shared memory
-//           -- a tile's records of one window leave as one contiguous run (whole lines) -- into fixed-capacity window regions.
-//   pass B/C (window_build_kernel, persistent, cooperative launch): window after window, every CTA first scatters its share of the
-//           window's records into the window's slabs, which live in a RING of three slab buffers that is written and read again and
-//           again and therefore stays in L2 (the stores hit resident sectors, the slabs never travel to HBM), then finishes the one bin
-//           of the PREVIOUS window it owns (slab_finish_bin: bulk copy from L2, ordering in shared memory, columns + tables out).
-//           Windows are chained by counters in global memory (release / acquire), not by grid-wide barriers: a CTA waits only for
-//           events of earlier iterations, so the waits are almost always already satisfied.
-// Record traffic through HBM: 24 (in) + 32 (window regions out) + 32 (in) + 24 (columns out) bytes per entry, all of it streamed.
-struct WindowParams {
-    SlabParams sp;
-    uint64_t win_magic;   // ceil(2^64 / (nb * bpw)): window of a bucket
-    uint32_t bpw;         // bins per window = CTAs of the build kernel
-    uint32_t n_windows;
-    uint32_t wcap;        // records per window region
-};
-constexpr int WP_THREADS = 512;
-constexpr int WIN_RING = 3;
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t *p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-// pass A.  ITEMS records per thread; dynamic shared memory: TILE records | TILE window ids | 3 x n_windows words.
-template <int ITEMS>
-__global__ void __launch_bounds__(WP_THREADS)
-window_partition_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
-                        const float *__restrict__ af, const BinRecord *__restrict__ records_in, WindowParams wp, uint32_t *__restrict__ wcursor,
-                        BinRecord *__restrict__ stage, uint32_t *__restrict__ flags) {
-    constexpr int T = WP_THREADS, TILE = WP_THREADS * ITEMS;
-    extern __shared__ __align__(128) unsigned char wp_smem[];
-    BinRecord *srec = (BinRecord *)wp_smem;
-    uint16_t *swin = (uint16_t *)(wp_smem + (size_t)TILE * 32);
-    uint32_t *wcnt = (uint32_t *)(swin + TILE);
-    uint32_t *wloff = wcnt + wp.n_windows, *wbase = wloff + wp.n_windows;
-    __shared__ uint32_t warp_tot[T / 32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t W = wp.n_windows;
-    const uint32_t per = (W + T - 1) / T;          // window counters per thread in the scan
-    const int64_t n_tiles = (n + TILE - 1) / TILE;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t base = tile * TILE;
-        for (uint32_t w = tid; w < W; w += T) wcnt[w] = 0;
-        __syncthreads();
-        unsigned long long km[ITEMS];
-        uint32_t bucket[ITEMS], win[ITEMS], rank[ITEMS];
-#pragma unroll
-        for (int r = 0; r < ITEMS; r++) {
-            const int64_t i = base + r * T + tid;
-            km[r] = 0ull;
-            bucket[r] = 0;
-            if (i < n) {
-                if (records_in) {
-                    const BinRecord in = load_record(records_in + i);
-                    km[r] = in.kmer;
-                    bucket[r] = (uint32_t)in.index - wp.sp.bucket_lo;
-                } else {
-                    km[r] = __ldg(kmers + i);
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < ITEMS; r++) {
-            const int64_t i = base + r * T + tid;
-            if (!records_in) bucket[r] = fastmod(km[r], wp.sp.fm) - wp.sp.bucket_lo;
-            win[r] = (uint32_t)__umul64hi((uint64_t)bucket[r], wp.win_magic);
-            rank[r] = 0;
-            if (i < n) {
-                if (win[r] < W) rank[r] = atomicAdd(wcnt + win[r], 1u);
-                else flags[0] = 1u;                                       // a bucket outside the range being built
-            }
-        }
-        __syncthreads();
-        // exclusive scan of the window counts (positions inside the tile) + one reservation per non-empty (tile, window)
-        uint32_t sum = 0;
-        for (uint32_t q = 0; q < per; q++) {
-            const uint32_t w = tid * per + q;
-            if (w < W) sum += wcnt[w];
-        }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        if (lane == 31) warp_tot[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            const uint32_t wv = lane < T / 32 ? warp_tot[lane] : 0u;
-            uint32_t winc = wv;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
-                if (lane >= d) winc += t;
-            }
-            if (lane < T / 32) warp_tot[lane] = winc - wv;
-        }
-        __syncthreads();
-        uint32_t run = warp_tot[warp] + inc - sum;
-        for (uint32_t q = 0; q < per; q++) {
-            const uint32_t w = tid * per + q;
-            if (w < W) {
-                const uint32_t c = wcnt[w];
-                wloff[w] = run;
-                run += c;
-                uint32_t b = 0;
-                if (c) {
-                    b = atomicAdd(wcursor + w, c);
-                    if (b + c > wp.wcap) flags[0] = 1u;
-                }
-                wbase[w] = b;
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < ITEMS; r++) {
-            const int64_t i = base + r * T + tid;
-            if (i < n && win[r] < W) {
-                unsigned long long rf, ndaf;
-                if (records_in) {
-                    const BinRecord in = load_record(records_in + i);
-                    rf = in.ref;
-                    ndaf = in.node_af;
-                } else {
-                    const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
-                    const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
-                    rf = ref ? __ldg(ref + i) : 0ull;
-                    ndaf = nd | (a << 32);
-                }
-                const uint32_t slot = wloff[win[r]] + rank[r];
-                uint4 *dst = (uint4 *)(srec + slot);
-                dst[0] = make_uint4((uint32_t)km[r], (uint32_t)(km[r] >> 32), (uint32_t)rf, (uint32_t)(rf >> 32));
-                dst[1] = make_uint4((uint32_t)ndaf, (uint32_t)(ndaf >> 32), (uint32_t)i, bucket[r]);
-                swin[slot] = (uint16_t)win[r];
-            }
-        }
-        __syncthreads();
-        const uint32_t here = (uint32_t)min((int64_t)TILE, n - base);
-        for (uint32_t j = tid; j < here; j += T) {
-            const uint32_t w = swin[j];
-            const uint32_t pos = wbase[w] + (j - wloff[w]);
-            if (pos < wp.wcap) {
-                const uint4 *src = (const uint4 *)(srec + j);
-                const uint4 a = src[0], b = src[1];
-                asm volatile("st.global.v8.u32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(stage + (size_t)w * wp.wcap + pos), "r"(a.x), "r"(a.y), "r"(a.z),
-                             "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
-                             : "memory");
-            }
-        }
-        __syncthreads();
-    }
-}
-
-// exclusive prefix of the window counts (n_windows <= 8192, one block)
-__global__ void __launch_bounds__(1024) window_starts_kernel(const uint32_t *__restrict__ wcount, uint32_t n_windows, uint32_t *__restrict__ wstart) {
-    __shared__ uint32_t warp_tot[32];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (n_windows + 1023) / 1024;
-    uint32_t sum = 0;
-    for (uint32_t q = 0; q < per; q++) {
-        const uint32_t w = tid * per + q;
-        if (w < n_windows) sum += wcount[w];
-    }
-    uint32_t inc = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t wv = warp_tot[lane];
-        uint32_t winc = wv;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, d);
-            if (lane >= d) winc += t;
-        }
-        warp_tot[lane] = winc - wv;
-    }
-    __syncthreads();
-    uint32_t run = warp_tot[warp] + inc - sum;
-    for (uint32_t q = 0; q < per; q++) {
-        const uint32_t w = tid * per + q;
-        if (w < n_windows) {
-            wstart[w] = run;
-            run += wcount[w];
-        }
-    }
-}
-
-// wait until *ctr >= target.  Bounded: a wait that does not end (which would mean a bug, or CTAs that are not co-resident) raises
-// flags[1] and every CTA leaves; the host then rebuilds on the slab path.
-__device__ __forceinline__ bool window_wait(const uint32_t *ctr, uint32_t target, volatile uint32_t *flags) {
-    uint32_t spins = 0;
-    while (ld_acquire_u32(ctr) < target) {
-        if (flags[1]) return false;
-        if (++spins > (1u << 21)) {
-            flags[1] = 1u;
-            return false;
-        }
-        __nanosleep(128);
-    }
-    return true;
-}
-
-// pass B/C.  Cooperative launch, gridDim.x == wp.bpw CTAs, all resident.  bin_count: one zeroed counter per bin; done / fdone: one
-// zeroed counter per window; flags: [0] overflow, [1] wait timed out.
-__global__ void __launch_bounds__(SLAB_THREADS, 2)
-window_build_kernel(WindowParams wp, const BinRecord *__restrict__ stage, const uint32_t *__restrict__ wcount, const uint32_t *__restrict__ wstart,
-                    BinRecord *__restrict__ ring, uint32_t *__restrict__ bin_count, uint32_t *__restrict__ done, uint32_t *__restrict__ fdone,
-                    uint32_t *__restrict__ flags, SlabOut o) {
-    constexpr int T = SLAB_THREADS;
-    extern __shared__ __align__(128) unsigned char slab_smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t warp_tot[T / 32 + 1];
-    __shared__ uint32_t s_ok, s_gstart;
-    const SlabSmem m = slab_smem_layout(slab_smem, &bar, warp_tot);
-    const SlabParams &p = wp.sp;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t G = gridDim.x, cta = blockIdx.x, W = wp.n_windows;
-    const size_t ring_stride = (size_t)wp.bpw * SLAB_CAP;
-    if (tid == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t phase = 0;
-    const bool tables_vec = (p.nb % 4 == 0) && ((((uintptr_t)o.h2i | (uintptr_t)o.nk) & 15) == 0);
-    for (uint32_t it = 0; it <= W; it++) {
-        if (it < W) {
-            // ---- S(it): this CTA's share of window `it` goes into the window's slabs (ring buffer it % 3) ----
-            if (it >= WIN_RING) {   // the buffer was last read by the finish phase of window it - 3
-                if (tid == 0) s_ok = window_wait(fdone + (it - WIN_RING), G, flags) ? 1u : 0u;
-                __syncthreads();
-                if (!s_ok) return;
-                __syncthreads();
-            }
-            const uint32_t n_w = min(__ldg(wcount + it), wp.wcap);
-            const uint32_t lo = (uint32_t)((uint64_t)n_w * cta / G), hi = (uint32_t)((uint64_t)n_w * (cta + 1) / G);
-            const BinRecord *src = stage + (size_t)it * wp.wcap;
-            BinRecord *slabs = ring + (size_t)(it % WIN_RING) * ring_stride;
-            const uint32_t first_bin = it * wp.bpw;
-            for (uint32_t i = lo + tid; i < hi; i += T) {
-                const BinRecord r = load_record(src + i);
-                const uint32_t bucket = (uint32_t)(r.index >> 32);
-                const uint32_t bin = slab_bin_of(bucket, p);
-                const uint32_t bl = bucket - bin * p.nb;
-                const uint32_t pos = atomicAdd(bin_count + bin, 1u);
-                if (pos < (uint32_t)SLAB_CAP && bin - first_bin < wp.bpw) {
-                    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slabs + (size_t)(bin - first_bin) * SLAB_CAP + pos), "l"(r.kmer), "l"(r.ref),
-                                 "l"(r.node_af), "l"((r.index & 0xffffffffull) | ((unsigned long long)bl << 32))
-                                 : "memory");
-                } else {
-                    flags[0] = 1u;
-                }
-            }
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(done + it, 1u);
-            }
-        }
-        if (it >= 1) {
-            // ---- F(it - 1): the bin of the previous window that this CTA owns ----
-            const uint32_t v = it - 1;
-            if (tid == 0) {
-                const bool ok = window_wait(done + v, G, flags);
-                __threadfence();
-                s_ok = ok ? 1u : 0u;
-            }
-            __syncthreads();
-            if (!s_ok) return;
-            const uint32_t bin = v * wp.bpw + cta;
-            // output position of the bin: window start + records of the window's earlier bins
-            uint32_t part = 0;
-            if ((uint32_t)tid < cta && v * wp.bpw + tid < p.n_bins) part = min(ld_acquire_u32(bin_count + v * wp.bpw + tid), (uint32_t)SLAB_CAP);
-#pragma unroll
-            for (int d = 16; d; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-            if (lane == 0) warp_tot[warp] = part;
-            __syncthreads();
-            if (tid == 0) {
-                uint32_t tot = 0;
-                for (int q = 0; q < T / 32; q++) tot += warp_tot[q];
-                s_gstart = __ldg(wstart + v) + tot;
-                fence_proxy_async_all();   // the slab was written through the generic proxy by other CTAs; the bulk copy reads it through the async proxy
-            }
-            __syncthreads();
-            if (bin < p.n_bins) {
-                const uint32_t c = min(ld_acquire_u32(bin_count + bin), (uint32_t)SLAB_CAP);
-                slab_finish_bin(p, m, phase, ring + (size_t)(v % WIN_RING) * ring_stride + (size_t)cta * SLAB_CAP, c, s_gstart, bin, o, tables_vec);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                __threadfence();
-                atomicAdd(fdone + v, 1u);
-            }
-        }
     }
 }
 
@@ -1486,9 +1183,9 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     bool binned = false;
     SortBuffers bufs;
     const unsigned long long *sorted = nullptr;
-    const char *force_path = getenv("GKI_BUILD_PATH");   // tests force a path: "window" (first choice of large builds), "slab", "binned", "radix"
-    const bool allow_slab = !force_path || !strcmp(force_path, "slab") || !strcmp(force_path, "window");
-    const bool allow_binned = (!force_path || !strcmp(force_path, "binned") || !strcmp(force_path, "slab") || !strcmp(force_path, "window"));
+    const char *force_path = getenv("GKI_BUILD_PATH");   // tests force a path: "slab" (default first choice), "binned", "radix"
+    const bool allow_slab = !force_path || !strcmp(force_path, "slab");
+    const bool allow_binned = (!force_path || !strcmp(force_path, "binned") || !strcmp(force_path, "slab"));
     // ---- slab path (see slab_finish_kernel): bins of nb buckets expected to hold ~3/4 of a slab ----
     bool fold_offset = false;
     if (n >= (1 << 15) && allow_slab) {
@@ -1514,65 +1211,8 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         sp.position_offset = fold_offset ? (int32_t)position_offset : 0;
         const size_t smem = (size_t)SLAB_CAP * 38 + (size_t)SLAB_THREADS * chunk * 2;
         const SlabOut so{o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>()};
-        // ---- windowed form (window_build_kernel): large builds, slabs kept in L2 ----
-        const bool want_window = force_path ? !strcmp(force_path, "window") : (n >= (int64_t)(experiment_knob("GKI_WINDOW_MIN") ? atoll(experiment_knob("GKI_WINDOW_MIN")) : (4 << 20)));
-        if (want_window && smem <= device_info().smem_optin) {
-            int coop = 0, per_sm = 0;
-            GKI_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device_info().device));
-            GKI_CUDA(cudaFuncSetAttribute(window_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            GKI_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, window_build_kernel, SLAB_THREADS, smem));
-            WindowParams wp;
-            wp.sp = sp;
-            wp.bpw = (uint32_t)std::min<int64_t>((int64_t)per_sm * device_info().sms, SLAB_THREADS);
-            const uint64_t n_windows = wp.bpw ? (n_bins + wp.bpw - 1) / wp.bpw : 0;
-            const size_t part_smem = (size_t)WP_THREADS * 4 * 34 + (size_t)n_windows * 12;
-            const size_t part_smem_big = (size_t)WP_THREADS * 8 * 34 + (size_t)n_windows * 12;
-            const bool big_tiles = n_windows > 512;
-            if (coop && wp.bpw >= 2 && n_windows >= 2 && n_windows <= 8192 && (big_tiles ? part_smem_big : part_smem) <= device_info().smem_optin) {
-                wp.n_windows = (uint32_t)n_windows;
-                wp.win_magic = (~0ull) / ((uint64_t)nb * wp.bpw) + 1ull;
-                const double per_window = (double)n * (double)nb * wp.bpw / (double)table_len;
-                wp.wcap = (uint32_t)((uint64_t)(per_window * 1.05 + 8192.0) & ~3ull);
-                Scratch stage, ring, counters;
-                const size_t n_counters = (size_t)n_bins + wp.bpw + 4 * n_windows + 16;   // bin_count | wcursor | wstart | done | fdone | flags
-                if (stage.try_alloc((size_t)n_windows * wp.wcap * sizeof(BinRecord), s) &&
-                    ring.try_alloc((size_t)WIN_RING * wp.bpw * SLAB_CAP * sizeof(BinRecord), s) && counters.try_alloc(n_counters * 4, s)) {
-                    GKI_CUDA(cudaMemsetAsync(counters.ptr, 0, n_counters * 4, s));
-                    uint32_t *bin_count = counters.as<uint32_t>(), *wcursor = bin_count + n_bins + wp.bpw, *wstart = wcursor + n_windows,
-                             *done = wstart + n_windows, *fdone = done + n_windows, *wflags = fdone + n_windows;
-                    const BinRecord *rec_in = (const BinRecord *)records;
-                    if (big_tiles) {
-                        GKI_CUDA(cudaFuncSetAttribute(window_partition_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem_big));
-                        window_partition_kernel<8><<<grid_for((n + WP_THREADS * 8 - 1) / (WP_THREADS * 8), 1, device_info().sms), WP_THREADS, part_smem_big, s>>>(
-                            n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), rec_in, wp, wcursor, stage.as<BinRecord>(), wflags);
-                    } else {
-                        GKI_CUDA(cudaFuncSetAttribute(window_partition_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem));
-                        window_partition_kernel<4><<<grid_for((n + WP_THREADS * 4 - 1) / (WP_THREADS * 4), 1, device_info().sms * 2), WP_THREADS, part_smem, s>>>(
-                            n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), rec_in, wp, wcursor, stage.as<BinRecord>(), wflags);
-                    }
-                    GKI_CHECK_LAUNCH();
-                    window_starts_kernel<<<1, 1024, 0, s>>>(wcursor, wp.n_windows, wstart);
-                    GKI_CHECK_LAUNCH();
-                    const BinRecord *stage_p = stage.as<BinRecord>();
-                    const uint32_t *wcount_p = wcursor, *wstart_p = wstart;
-                    BinRecord *ring_p = ring.as<BinRecord>();
-                    SlabOut so_arg = so;
-                    void *args[] = {(void *)&wp, (void *)&stage_p, (void *)&wcount_p, (void *)&wstart_p, (void *)&ring_p, (void *)&bin_count,
-                                    (void *)&done, (void *)&fdone, (void *)&wflags, (void *)&so_arg};
-                    GKI_CUDA(cudaLaunchCooperativeKernel((const void *)window_build_kernel, dim3(wp.bpw), dim3(SLAB_THREADS), args, smem, s));
-                    count_launch();
-                    uint32_t host_flags[2] = {0, 0};
-                    GKI_CUDA(cudaMemcpyAsync(host_flags, wflags, 8, cudaMemcpyDeviceToHost, s));
-                    GKI_CUDA(cudaStreamSynchronize(s));
-                    if (!host_flags[0] && !host_flags[1]) binned = true;
-                    else if (getenv("GKI_BUILD_DEBUG")) fprintf(stderr, "[gki build] windowed path gave up (overflow %u, wait timeout %u)\n", host_flags[0], host_flags[1]);
-                }
-            }
-        }
         Scratch counts, starts, slab, flag;
-        if (binned) {
-            // done by the windowed form
-        } else if (n_bins < (1ull << 31) / SLAB_CAP * 64 && smem <= device_info().smem_optin && slab.try_alloc((size_t)n_bins * SLAB_CAP * sizeof(BinRecord), s)) {
+        if (n_bins < (1ull << 31) / SLAB_CAP * 64 && smem <= device_info().smem_optin && slab.try_alloc((size_t)n_bins * SLAB_CAP * sizeof(BinRecord), s)) {
             GKI_TRY(counts.alloc((size_t)(n_bins + 1) * 4, s));
             GKI_TRY(starts.alloc((size_t)(n_bins + 1) * 4, s));
             GKI_TRY(flag.alloc(4, s));

@@ -39,7 +39,7 @@ def compulsory_bytes(columns, flags):
     return per_entry * n + 8 * modulo
 
 
-paths = sys.argv[2].split(",") if len(sys.argv) > 2 else ["window", "slab", "binned", "radix"]
+paths = sys.argv[2].split(",") if len(sys.argv) > 2 else ["slab", "binned", "radix"]
 only = sys.argv[3] if len(sys.argv) > 3 else None       # "all1": all columns, skip_frequencies (the ncu target)
 sums = {}
 for path in paths:

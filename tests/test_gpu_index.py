@@ -95,8 +95,7 @@ def test_build_vs_oracle(gki, n, modulo, skip):
                                                (100000, 65521, False, 3), (2000000, 452930477 // 8, False, 40), (3000000, 1000003, True, 2),
                                                (1500000, 300007, False, 4)])
 def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
-    """the build paths (window: window partition + L2-resident slab ring in one persistent kernel, taken by the three largest cases;
-    slab: append-scatter + per-slab ordering in shared memory; binned: 16-entry bins; radix) against the
+    """the three build paths (slab: append-scatter + per-slab ordering in shared memory; binned: 16-entry bins; radix) against the
     oracle and against each other: moderate repeats of a k-mer (several nodes / ref offsets), all columns, frequencies, and the
     permutation output"""
     import ctypes
@@ -112,13 +111,13 @@ def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
     af = rng.random(n).astype(np.float32)
     want = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=skip)
     flat = gki.FlatKmers(hashes, nodes, ref, af)
-    for path in ("window", "slab", "binned", "radix"):
+    for path in ("slab", "binned", "radix"):
         monkeypatch.setenv("GKI_BUILD_PATH", path)
         index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo, skip_frequencies=skip)
         assert_index_equal(index, want)
     # kmers + nodes only and the permutation
     outs = {}
-    for path in ("window", "slab", "binned", "radix"):
+    for path in ("slab", "binned", "radix"):
         monkeypatch.setenv("GKI_BUILD_PATH", path)
         h2i, nk = np.empty(modulo, np.int32), np.empty(modulo, np.uint32)
         k_o, n_o, perm = np.empty(n, np.uint64), np.empty(n, np.uint32), np.empty(n, np.uint32)
@@ -126,7 +125,7 @@ def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
                   _lib.ptr(k_o), _lib.ptr(n_o), None, None, None, _lib.ptr(perm), None)
         outs[path] = (h2i, nk, k_o, n_o, perm)
     monkeypatch.delenv("GKI_BUILD_PATH")
-    for path in ("window", "binned", "radix"):
+    for path in ("binned", "radix"):
         for a, b in zip(outs["slab"], outs[path]):
             assert np.array_equal(a, b)
     h2i, nk, k_o, n_o, perm = outs["slab"]
