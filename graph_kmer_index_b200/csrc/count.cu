@@ -1359,16 +1359,7 @@ int gki_host_read_bandwidth(const void *host, int64_t bytes, int32_t n_threads, 
     std::vector<uint64_t> sums((size_t)T * 8, 0);
     auto body = [&](int t) {
         const int64_t w0 = n_words * t / T, w1 = n_words * (t + 1) / T;
-        uint64_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        int64_t i = w0;
-        for (; i + 8 <= w1; i += 8) {
-            a0 += words[i] + words[i + 4];
-            a1 += words[i + 1] + words[i + 5];
-            a2 += words[i + 2] + words[i + 6];
-            a3 += words[i + 3] + words[i + 7];
-        }
-        for (; i < w1; i++) a0 += words[i];
-        sums[(size_t)t * 8] = a0 + a1 + a2 + a3;
+        sums[(size_t)t * 8] = sweep_words(words + w0, w1 - w0);
     };
     const auto t0 = std::chrono::steady_clock::now();
     std::vector<std::thread> threads;

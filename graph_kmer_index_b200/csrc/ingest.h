@@ -15,6 +15,7 @@ namespace gki {
 // non-NULL and its index to `dirty_index` when that is non-NULL -- the first dirty_cap of them; the rest are only counted.
 // Returns the number of clean rows; *n_dirty the others.  force_scalar != 0 selects the table-driven path (tests).
 // row_offsets (may be NULL): row r starts at reads + row_offsets[r] instead of reads + r * row_stride (sequence lines of a file).
+uint64_t sweep_words(const uint64_t *words, int64_t n);   // sum of n 64-bit words (a plain read sweep, AVX-512 where available)
 int64_t pack_rows(const uint8_t *reads, int64_t row_stride, const int64_t *row_offsets, int32_t read_len, int64_t r0, int64_t r1,
                   uint64_t *packed, uint8_t *dirty_rows, int64_t *dirty_index, int64_t dirty_cap, int64_t *n_dirty, int force_scalar);
 

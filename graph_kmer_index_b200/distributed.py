@@ -207,6 +207,127 @@ def build_index_partitioned(hashes, nodes, ref_offsets, allele_frequencies, modu
     return full
 
 
+class PartitionedCounterIndex:
+    """Counting against an index that is hash-range PARTITIONED over the ranks instead of replicated -- for indexes larger than
+    one GPU's memory.  Every rank passes its shard of the FlatKmers (device tensors, as build_index_partitioned); the entries travel to
+    the rank that owns their bucket range (gki_partition_pack -> one all-to-all) and every rank builds an ordinary index over the
+    entries it owns.  count_reads hashes the rank's own reads (K1, both strands), routes every k-mer hash to the owner of its bucket
+    (kmer % modulo, the same ranges) with one all-to-all per chunk of reads, and the owner counts what it receives
+    (gki_count_kmers).  get_node_counts sums the ranks' node counts with one all-reduce: every index entry lives on exactly one rank.
+    The reference's analogue of the routing is has_kmers_parallel's slicing of the queries (cfki:222-232); results equal the
+    replicated path's bit for bit.  Each read k-mer crosses NVLink as 8 bytes here, where the replicated path reads 150 bytes per
+    read: this is the fallback for indexes that do not fit, not the fast path."""
+
+    def __init__(self, hashes, nodes, modulo):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .collision_free_kmer_index import DeviceIndex
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.modulo = int(modulo)
+        self.dev = hashes.device
+        n = int(hashes.shape[0])
+        stream = _lib.current_stream()
+        records = torch.empty((max(n, 1), 4), dtype=torch.int64, device=self.dev)
+        counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+        _lib.call("gki_partition_pack", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, self.modulo, self.world, _lib.ptr(records), _lib.ptr(counts), stream)
+        matrix = torch.empty((self.world, self.world), dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_gather_into_tensor(matrix, counts)
+        else:
+            matrix[0] = counts
+        matrix = matrix.cpu()
+        in_splits, out_splits = matrix[self.rank].tolist(), matrix[:, self.rank].tolist()
+        n_local = int(sum(out_splits))
+        recv = torch.empty((max(n_local, 1), 4), dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_to_all_single(recv[:n_local], records[:n], output_split_sizes=out_splits, input_split_sizes=in_splits)
+        else:
+            recv[:n_local].copy_(records[:n])
+        del records
+        # an ordinary index over the owned entries (tables span the whole modulo: buckets of other ranks stay empty)
+        h2i = torch.empty(self.modulo, dtype=torch.int32, device=self.dev)
+        nk = torch.empty(self.modulo, dtype=torch.int32, device=self.dev)
+        kmers = torch.empty(max(n_local, 1), dtype=torch.int64, device=self.dev)
+        nds = torch.empty(max(n_local, 1), dtype=torch.int32, device=self.dev)
+        self.n_local = n_local
+        self.index = None
+        max_node = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        if n_local:
+            _lib.call("gki_index_build_records", _lib.ptr(recv), n_local, self.modulo, 0, self.modulo, 0, _lib.GKI_BUILD_SKIP_FREQUENCIES, _lib.ptr(h2i),
+                      _lib.ptr(nk), _lib.ptr(kmers), _lib.ptr(nds), None, None, None, stream)
+            self.index = DeviceIndex(h2i, nk, kmers[:n_local], nds[:n_local], self.modulo)
+            max_node[0] = self.index.max_node
+        if self.world > 1:
+            dist.all_reduce(max_node, op=dist.ReduceOp.MAX)
+        self.max_node = int(max_node.item())
+        del recv, h2i, nk, kmers, nds
+
+    def reset_counts(self):
+        if self.index is not None:
+            self.index.reset_counts()
+
+    def count_reads(self, reads, k, chunk_reads=1 << 19):
+        """reads: this rank's (n_reads, L) uint8 ASCII rows (numpy, or a torch tensor on host / device).  Every rank must call it
+        (the exchange is collective) with the same chunk_reads; ranks with fewer chunks send empty ones."""
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .read_kmers import hash_read_matrix
+        n_reads = int(reads.shape[0])
+        n_chunks = torch.tensor([(n_reads + chunk_reads - 1) // chunk_reads], dtype=torch.int64, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(n_chunks, op=dist.ReduceOp.MAX)
+        stream = _lib.current_stream()
+        for c in range(int(n_chunks.item())):
+            part = reads[c * chunk_reads:(c + 1) * chunk_reads]
+            if isinstance(part, np.ndarray):
+                part = torch.from_numpy(np.ascontiguousarray(part))
+            part = part.to(self.dev)
+            m = int(part.shape[0])
+            if m and part.shape[1] >= k:
+                fwd, rc = hash_read_matrix(part, k)                                  # K1: both strands
+                hashes = torch.cat([fwd.reshape(-1).view(torch.int64), rc.reshape(-1).view(torch.int64)])
+                del fwd, rc
+            else:
+                hashes = torch.empty(0, dtype=torch.int64, device=self.dev)
+            nq = int(hashes.shape[0])
+            perm = torch.empty(max(nq, 1), dtype=torch.int32, device=self.dev)
+            counts = torch.zeros(self.world, dtype=torch.int64, device=self.dev)
+            _lib.call("gki_partition_by_bucket_range", _lib.ptr(hashes), nq, self.modulo, self.world, _lib.ptr(perm), _lib.ptr(counts), stream)
+            grouped = torch.empty(max(nq, 1), dtype=torch.int64, device=self.dev)
+            if nq:
+                _lib.call("gki_gather", _lib.ptr(hashes), 8, _lib.ptr(perm), nq, _lib.ptr(grouped), stream)
+            matrix = torch.empty((self.world, self.world), dtype=torch.int64, device=self.dev)
+            if self.world > 1:
+                dist.all_gather_into_tensor(matrix, counts)
+            else:
+                matrix[0] = counts
+            matrix = matrix.cpu()
+            in_splits, out_splits = matrix[self.rank].tolist(), matrix[:, self.rank].tolist()
+            n_in = int(sum(out_splits))
+            recv = torch.empty(max(n_in, 1), dtype=torch.int64, device=self.dev)
+            if self.world > 1:
+                dist.all_to_all_single(recv[:n_in], grouped[:nq], output_split_sizes=out_splits, input_split_sizes=in_splits)
+            else:
+                recv[:n_in].copy_(grouped[:nq])
+            if n_in and self.index is not None:
+                self.index.count_kmers(recv[:n_in])
+            del hashes, perm, grouped, recv
+
+    def get_node_counts(self, min_nodes=0):
+        """float64 numpy array on every rank: the node counts of the whole (partitioned) index."""
+        import torch
+        n_out = max(int(min_nodes), self.max_node + 1)
+        counts = torch.zeros(n_out, dtype=torch.float64, device=self.dev)
+        if self.index is not None:
+            self.index.node_counts(n_out, out=counts)
+        allreduce_node_counts(counts)
+        return counts.cpu().numpy()
+
+
 def critical_path_chunks(n_paths, n_chunks):
     """(start, end) chunks of the critical paths exactly as `graph_kmer_index index -t T` cuts them
     (command_line_interface.py:588-603: n_paths // n_chunks paths per chunk, the remainder in further chunks)."""

@@ -49,6 +49,9 @@ int gki_set_device(int device);
 /* number of kernel launches issued by this library so far (bench.py's gpu_launches). */
 int64_t gki_launch_count(void);
 
+/* return the library's cached device scratch (stream-ordered pool) to the driver; synchronises the device */
+int gki_release_scratch(void);
+
 /* ------------------------------------------------------------------ K1: encoding + hashing */
 
 /* flat_kmers.py:134-145 letter_sequence_to_numeric: ASCII (case-insensitive) -> a0 c1 g2 t3,
@@ -240,6 +243,21 @@ int gki_lookup_entries(gki_index_t *index, const uint64_t *queries, int64_t nq, 
 /* `counter[keys]` for arbitrary keys (cfki:40): out[i] = current counter of queries[i], 0 when absent. */
 int gki_query_counts(gki_index_t *index, const uint64_t *queries, int64_t nq, uint32_t *out, gki_stream_t stream);
 
+/* ------------------------------------------------------------------ multi-GPU
+ * Reads shard over the ranks, the index is replicated, the ranks' node-count vectors are summed by ONE
+ * NCCL all-reduce.  Reference analogue: the parent summing / concatenating its workers' results (shared_mem.py:164-171, cfki:222-232).
+ * gki_allreduce_counts takes the host application's ncclComm_t (as void*: this header does not include nccl.h) and sums `counts`
+ * (device memory, n elements of float64 -- exact below 2^53, the dtype of get_node_counts, cfki:39-40 -- or uint64) in place over its
+ * ranks, on `stream`.  NCCL is bound at run time (libnccl.so.2 of the process, or GKI_NCCL_LIBRARY).  A host without a communicator
+ * of its own gets one from gki_nccl_unique_id (rank 0; send the 128 bytes to every rank by any means) + gki_nccl_comm_create. */
+#define GKI_COUNTS_FLOAT64 0
+#define GKI_COUNTS_UINT64 1
+int gki_nccl_unique_id(void *id128);
+int gki_nccl_comm_create(const void *id128, int32_t rank, int32_t world_size, void **nccl_comm_out);
+int gki_nccl_comm_destroy(void *nccl_comm);
+int gki_allreduce_counts(void *nccl_comm, void *counts, int64_t n, int32_t dtype, gki_stream_t stream);
+
+
 /* ------------------------------------------------------------------ DenseKmerFinder (BASELINE config 5)
  * The variant graph is passed as flat CSR arrays: seq_offsets[n_nodes+1] / seq (base codes 0..3; an empty node is a
  * dummy node), edge_offsets[n_nodes+1] / edges, is_linear[n_nodes] (linear-ref node or linear-ref dummy node),
@@ -285,22 +303,6 @@ int gki_synth_reads(const uint8_t *genome_codes, int64_t genome_len, int64_t fir
  * one; bit 1: loads ask for a 64-byte L2 fill (ld.global.nc.L2::64B) instead of the default whole line.
  * *ms receives the kernel time. Synchronous. */
 int gki_calibrate_random_gather(int64_t table_bytes, int64_t n_gathers, int32_t dependent_loads, float *ms);
-/* ---- multi-GPU: reads shard over the ranks, the index is replicated, the ranks' node-count vectors are summed by ONE
- * NCCL all-reduce.  Reference analogue: the parent summing / concatenating its workers' results (shared_mem.py:164-171, cfki:222-232).
- * gki_allreduce_counts takes the host application's ncclComm_t (as void*: this header does not include nccl.h) and sums `counts`
- * (device memory, n elements of float64 -- exact below 2^53, the dtype of get_node_counts, cfki:39-40 -- or uint64) in place over its
- * ranks, on `stream`.  NCCL is bound at run time (libnccl.so.2 of the process, or GKI_NCCL_LIBRARY).  A host without a communicator
- * of its own gets one from gki_nccl_unique_id (rank 0; send the 128 bytes to every rank by any means) + gki_nccl_comm_create. */
-#define GKI_COUNTS_FLOAT64 0
-#define GKI_COUNTS_UINT64 1
-int gki_nccl_unique_id(void *id128);
-int gki_nccl_comm_create(const void *id128, int32_t rank, int32_t world_size, void **nccl_comm_out);
-int gki_nccl_comm_destroy(void *nccl_comm);
-int gki_allreduce_counts(void *nccl_comm, void *counts, int64_t n, int32_t dtype, gki_stream_t stream);
-
-/* return the library's cached device scratch (stream-ordered pool) to the driver; synchronises the device */
-int gki_release_scratch(void);
-
 /* n random stores or atomics (the measurements the index-build design rests on).  mode 0/1/2: 32/16/8-byte stores to random
  * slots of an n-slot array; 3: returning atomicAdd on n_bins random counters; 4: the same without a return value; 5: returning
  * atomicAdd picks a slot inside the counter's own bin of a (n_bins x n/n_bins) array and a 32-byte record is stored there;

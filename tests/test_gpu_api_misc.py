@@ -210,3 +210,22 @@ def test_counts_allreduce_through_the_c_abi_single_rank(gki):
         _lib.call("gki_allreduce_counts", comm, host.ctypes.data, 8, _lib.GKI_COUNTS_FLOAT64, stream)
     _lib.call("gki_nccl_comm_destroy", comm)
     _lib.call("gki_release_scratch")
+
+
+def test_partitioned_counter_index_single_rank(gki):
+    """distributed.PartitionedCounterIndex with one rank (no process group): entries and read k-mers all route to rank 0; node counts
+    equal the oracle's.  Two ranks: tests/test_gpu_multi.py."""
+    import torch
+    from graph_kmer_index_b200 import distributed, synthetic
+    from oracle import c_oracle
+    n, n_nodes, modulo, k = 60_000, 3_000, 200_003, 31
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, n_nodes, k)
+    idx = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    reads = synthetic.reads(5_003, 150, n, k, p_hit_permille=300, n_permille=4)
+    want = c_oracle.read_node_counts(idx, reads, k, n_nodes)
+    pc = distributed.PartitionedCounterIndex(torch.from_numpy(hashes.view(np.int64)).cuda(), torch.from_numpy(nodes.view(np.int32)).cuda(), modulo)
+    pc.count_reads(reads, k, chunk_reads=1000)
+    assert np.array_equal(pc.get_node_counts(n_nodes), want) and want.sum() > 0
+    pc.reset_counts()
+    pc.count_reads(torch.from_numpy(reads).cuda(), k)
+    assert np.array_equal(pc.get_node_counts(n_nodes), want)

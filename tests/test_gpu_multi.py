@@ -41,6 +41,15 @@ WORKER = textwrap.dedent("""
     assert np.array_equal(full["ref_offsets"].cpu().numpy().view(np.uint64), w2["_ref_offsets"]), rank
     assert np.array_equal(full["allele_frequencies"].cpu().numpy(), w2["_allele_frequencies"]), rank
     assert np.array_equal(full["frequencies"].cpu().numpy().view(np.uint16), w2["_frequencies"]), rank
+    # hash-range partitioned index for counting (an index too large to replicate): entries and read k-mers are routed to the owners
+    pc = distributed.PartitionedCounterIndex(t(hashes, np.int64), t(nodes, np.int32), modulo)
+    my_lo, my_hi = distributed.shard_bounds(len(reads), rank, world)
+    pc.count_reads(reads[my_lo:my_hi], k, chunk_reads=4096)
+    got_p = pc.get_node_counts(n_nodes)
+    assert np.array_equal(got_p, want), (rank, float(got_p.sum()), float(want.sum()))
+    pc.reset_counts()
+    pc.count_reads(torch.from_numpy(reads[my_lo:my_hi]).cuda(), k)
+    assert np.array_equal(pc.get_node_counts(n_nodes), want), rank
     dist.barrier()
     if rank == 0:
         print("OK", world, int(want.sum()))
