@@ -640,6 +640,7 @@ struct SlabOut {
     uint64_t *ref_o;
     float *af_o;
     uint32_t *perm_o;
+    uint16_t *freq_o;   // NULL: frequencies not wanted (or zeroed by the caller)
 };
 struct SlabSmem {
     BinRecord *rec;        // SLAB_CAP records, filled by the bulk copy
@@ -789,6 +790,27 @@ __device__ __forceinline__ void slab_finish_bin(const SlabParams &p, const SlabS
         }
     }
     __syncthreads();
+    // set_frequencies (cfki:267-293) while the bucket's records are at hand: first[q] = no earlier entry of the bucket holds the same
+    // (k-mer, ref offset) pair; frequency = number of first-flagged entries of the bucket with the entry's k-mer (uint16, wraps).
+    // The flags reuse sidx, which is dead once `order` is complete.
+    uint8_t *first = (uint8_t *)sidx;
+    if (o.freq_o) {
+        for (uint32_t q = tid; q < c; q += T) {
+            const uint4 *src = (const uint4 *)(rec + order[q]);
+            const uint4 a = src[0];
+            const uint32_t lo = start16[src[1].w];
+            uint8_t f = 1;
+            for (uint32_t e = lo; e < q; e++) {
+                const uint4 k = *(const uint4 *)(rec + order[e]);
+                if (k.x == a.x && k.y == a.y && k.z == a.z && k.w == a.w) {
+                    f = 0;
+                    break;
+                }
+            }
+            first[q] = f;
+        }
+        __syncthreads();
+    }
     for (uint32_t q = tid; q < c; q += T) {
         const uint4 *src = (const uint4 *)(rec + order[q]);
         const uint4 a = src[0], b = src[1];
@@ -798,6 +820,15 @@ __device__ __forceinline__ void slab_finish_bin(const SlabParams &p, const SlabS
         if (nodes_o) nodes_o[dst] = b.x;
         if (af_o) af_o[dst] = __uint_as_float(b.y);
         if (perm_o) perm_o[dst] = b.z;
+        if (o.freq_o) {
+            const uint32_t lo = start16[b.w], hi = start16[b.w + 1];
+            uint32_t f = 0;
+            for (uint32_t e = lo; e < hi; e++) {
+                const uint2 k = *(const uint2 *)(rec + order[e]);
+                f += (k.x == a.x && k.y == a.y) ? first[e] : 0u;
+            }
+            o.freq_o[dst] = (uint16_t)f;
+        }
     }
     __syncthreads();   // the next bin's bulk copy and counter reset overwrite what was just read
 }
@@ -1187,7 +1218,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     const bool allow_slab = !force_path || !strcmp(force_path, "slab");
     const bool allow_binned = (!force_path || !strcmp(force_path, "binned") || !strcmp(force_path, "slab"));
     // ---- slab path (see slab_finish_kernel): bins of nb buckets expected to hold ~3/4 of a slab ----
-    bool fold_offset = false;
+    bool fold_offset = false, freq_done = false;
     if (n >= (1 << 15) && allow_slab) {
         SlabParams sp;
         sp.fm = fm;
@@ -1207,10 +1238,11 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         if (((chunk / 2) & 1u) == 0) chunk += 2;
         sp.chunk = chunk;
         sp.n_bins = (uint32_t)n_bins;
-        fold_offset = !want_freq;   // the frequency pass below reads hashes_to_index as local positions
-        sp.position_offset = fold_offset ? (int32_t)position_offset : 0;
+        fold_offset = true;          // (the separate frequency pass of the fallback paths reads hashes_to_index as local positions)
+        sp.position_offset = (int32_t)position_offset;
         const size_t smem = (size_t)SLAB_CAP * 38 + (size_t)SLAB_THREADS * chunk * 2;
-        const SlabOut so{o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>()};
+        const SlabOut so{o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), kmers_sorted, o_nodes.as<uint32_t>(), ref_sorted, o_af.as<float>(), o_perm.as<uint32_t>(),
+                         want_freq ? o_freq.as<uint16_t>() : nullptr};
         Scratch counts, starts, slab, flag;
         if (n_bins < (1ull << 31) / SLAB_CAP * 64 && smem <= device_info().smem_optin && slab.try_alloc((size_t)n_bins * SLAB_CAP * sizeof(BinRecord), s)) {
             GKI_TRY(counts.alloc((size_t)(n_bins + 1) * 4, s));
@@ -1241,6 +1273,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
                 slab_finish_kernel<<<grid, SLAB_THREADS, smem, s>>>(sp, counts.as<uint32_t>(), starts.as<uint32_t>(), slab.as<BinRecord>(), so);
                 GKI_CHECK_LAUNCH();
                 binned = true;
+                freq_done = want_freq;   // computed in the finish pass
             } else {
                 fold_offset = false;
             }
@@ -1340,7 +1373,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
     }
     }
 
-    if (freq_out) {
+    if (freq_out && !freq_done) {
         if (!want_freq) {
             GKI_CUDA(cudaMemsetAsync(o_freq.dptr, 0, (size_t)n * 2, s));   // cfki:270-274
         } else {
