@@ -755,9 +755,30 @@ void destroy_count_table(gki_index *ix) {
     ix->table_bytes = ix->filter_bytes = 0;
 }
 
+// stage times of the one-off table build, printed with GKI_BUILD_DEBUG (profiles/r2/prepare_counting_stages_c3.txt)
+struct StageClock {
+    cudaStream_t s;
+    bool on;
+    std::chrono::steady_clock::time_point t0;
+    explicit StageClock(cudaStream_t stream) : s(stream), on(getenv("GKI_BUILD_DEBUG") != nullptr) {
+        if (on) {
+            cudaStreamSynchronize(s);
+            t0 = std::chrono::steady_clock::now();
+        }
+    }
+    void lap(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[gki prepare_counting] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 // Build the table on first use.  k > 0 selects canonical keys (needs every index k-mer < 4^k), k == 0 raw keys.
 static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     if (ix->table.buckets) return GKI_OK;
+    StageClock clock(s);
     if (const char *e = experiment_knob("GKI_L2_FETCH")) {   // experiment knob: L2 fetch granularity for misses (32 / 64 / 128 bytes)
         GKI_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)));
     }
@@ -774,6 +795,7 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
     GKI_CUDA(cudaMemcpyAsync(&distinct, counters.ptr, 8, cudaMemcpyDeviceToHost, s));
     GKI_CUDA(cudaStreamSynchronize(s));
     ix->n_distinct = (int64_t)distinct;
+    clock.lap("count distinct k-mers");
 
     TableView t{};
     t.k = k;
@@ -818,26 +840,31 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
             if (const char *e = getenv("GKI_FILTER_K")) t.filter_k = atoi(e) < 1 ? 1 : (atoi(e) > 3 ? 3 : atoi(e));
             filter_bytes = fbytes;
         }
+        clock.lap("allocate + initialise table");
         table_insert_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, filter, (unsigned int *)counters.ptr + 2);
         GKI_CHECK_LAUNCH();
         GKI_CUDA(cudaMemcpyAsync(&failed, (unsigned int *)counters.ptr + 2, 4, cudaMemcpyDeviceToHost, s));
         GKI_CUDA(cudaStreamSynchronize(s));
         GKI_REQUIRE(failed == 0, GKI_ERR_CUDA, "count table: %u insertions failed", failed);
+        clock.lap("insert keys + filter bits");
         // regroup the entries by slot (one-time sort) so that get_node_counts reads the counters in table order
         if (n_slots < (1ull << 32) && ix->max_node < (1ll << 31) && !getenv("GKI_NO_CSR")) {
             Scratch a, b, hist;
             GKI_TRY(a.alloc((size_t)ix->n * 8, s));
             entry_slots_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, a.as<unsigned long long>());
             GKI_CHECK_LAUNCH();
+            clock.lap("slot of every entry");
             int bits = 1;
             while ((1ull << bits) < n_slots) bits++;
             const unsigned long long *sorted = nullptr;
             GKI_TRY(radix_sort_packed(a, b, hist, ix->n, bits, &sorted, s));
+            clock.lap("sort entries by slot");
             GKI_CUDA(cudaMalloc((void **)&cs_slot, (size_t)ix->n * 4));
             GKI_CUDA(cudaMalloc((void **)&cs_node, (size_t)ix->n * 4));
             csr_fill_kernel<<<grid_n, 256, 0, s>>>(t, sorted, ix->kmers, ix->nodes, ix->n, cs_slot, cs_node);
             GKI_CHECK_LAUNCH();
             GKI_CUDA(cudaStreamSynchronize(s));
+            clock.lap("slot-ordered entry list");
             table_bytes += (size_t)ix->n * 8;
         }
         return GKI_OK;
@@ -1530,7 +1557,7 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
     if (ix->table.buckets) {
         const bool wrap = (flags & GKI_COUNTS_WRAP_UINT16) != 0;
         const int grid = grid_for(ix->n, 256 * 4, device_info().sms * 16);
-        size_t slice_bytes = (size_t)64 << 20;   // node counts per pass: must stay in L2 (126 MB) next to the streams
+        size_t slice_bytes = (size_t)48 << 20;   // node counts per pass: must stay in L2 (126 MB) next to the streams (measured at c3: 32 MB 18.9 ms, 48 MB 15.2, 64 MB 15.4, 96 MB 17.6)
         if (const char *e = getenv("GKI_NODE_SLICE_MB")) slice_bytes = (size_t)(atoi(e) > 0 ? atoi(e) : 0) << 20;
         if (ix->cs_slot && slice_bytes && (size_t)n_out * 8 > slice_bytes + (slice_bytes >> 1)) {
             Scratch w;
