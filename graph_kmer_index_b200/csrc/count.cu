@@ -279,9 +279,26 @@ __global__ void count_distinct_kernel(IndexView ix, int64_t n, unsigned long lon
 }
 
 __global__ void table_insert_kernel(TableView t, const uint64_t *__restrict__ kmers, int64_t n, uint32_t *__restrict__ filter,
-                                    unsigned int *__restrict__ failed) {
+                                    unsigned int *__restrict__ failed, FastMod fm) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
-        Key key = make_key(__ldg(kmers + e), t.k);
+        const uint64_t km = __ldg(kmers + e);
+        // the entries are in bucket order: a k-mer that an earlier entry of the same bucket already holds (variant k-mers come with
+        // two or more nodes) has nothing to insert -- half of the random table and filter accesses at c3.  The look back is bounded;
+        // an entry it cannot decide about is simply inserted again.
+        {
+            const uint32_t bucket = fastmod(km, fm);
+            bool seen = false;
+            for (int64_t c = e - 1; c >= 0 && c >= e - 16; c--) {
+                const uint64_t other = __ldg(kmers + c);
+                if (other == km) {
+                    seen = true;
+                    break;
+                }
+                if (fastmod(other, fm) != bucket) break;
+            }
+            if (seen) continue;
+        }
+        Key key = make_key(km, t.k);
         if (key.c == SLOT_EMPTY) {
             t.buckets[t.n_buckets].key[0] = 1ull;   // mark the special bucket as present
             continue;
@@ -841,7 +858,7 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
             filter_bytes = fbytes;
         }
         clock.lap("allocate + initialise table");
-        table_insert_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, filter, (unsigned int *)counters.ptr + 2);
+        table_insert_kernel<<<grid_n, 256, 0, s>>>(t, ix->kmers, ix->n, filter, (unsigned int *)counters.ptr + 2, ix->view().fm);
         GKI_CHECK_LAUNCH();
         GKI_CUDA(cudaMemcpyAsync(&failed, (unsigned int *)counters.ptr + 2, 4, cudaMemcpyDeviceToHost, s));
         GKI_CUDA(cudaStreamSynchronize(s));
