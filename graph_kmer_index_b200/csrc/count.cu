@@ -835,10 +835,11 @@ static int ensure_table(gki_index *ix, int k, cudaStream_t s) {
                                             // below (false positives) and above (the filter starts missing L2)
         if (const char *e = getenv("GKI_FILTER_MAX_MB")) budget = (size_t)atoi(e) << 20;
         size_t want = (size_t)distinct * 2;                  // 16 bits per key
-        // Indexes too large for an L2-resident filter still profit from an HBM-resident one at 8 bits per key (measured at
-        // 500 M distinct k-mers: kernel 297 ms without, 164 ms with a 512 MB filter): a filter miss costs one small fetch
-        // from a compact region instead of a bucket line from the 32x larger table.
-        if (!getenv("GKI_FILTER_MAX_MB") && (size_t)distinct > budget) budget = (size_t)distinct;
+        // Indexes too large for an L2-resident filter still profit from an HBM-resident one (measured at 500 M distinct k-mers:
+        // kernel 297 ms without, 164 ms with a 512 MB filter): a filter miss costs one small fetch from a compact region instead
+        // of a bucket line from the 32x larger table.  16 bits per key: the fetch costs the same whatever the filter's size, and
+        // every false positive is a table line (c3, count kernel: 51.4 ms at 8 bits per key, 47.3 at 12, 46.1 at 16 and at 24).
+        if (!getenv("GKI_FILTER_MAX_MB") && (size_t)distinct > budget) budget = (size_t)distinct * 2;
         size_t fbytes = want < budget ? want : budget;
         fbytes = (fbytes + 31) & ~(size_t)31;   // whole 32-byte sectors
         if (fbytes < 64) fbytes = 64;
