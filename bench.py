@@ -724,9 +724,12 @@ def main():
         cfg3 = workload(args, "c3")
         sub_args = argparse.Namespace(**vars(args))
         sub_args.steps, sub_args.warmup = min(args.steps, 10), min(args.warmup, 3)
-        r3 = measure(sub_args, cfg3, "c3", rank, world, local_rank, False)
         extra = {"config": bench_config(cfg3, args, world, name="c3"), "steps": sub_args.steps, "warmup": sub_args.warmup}
-        extra.update({key: r3.get(key) for key in ("value", "ms_per_step", "e2e", "stages_ms", "index_build", "roofline", "cpu_baseline", "parity_checked", "index")})
+        try:
+            r3 = measure(sub_args, cfg3, "c3", rank, world, local_rank, False)
+            extra.update({key: r3.get(key) for key in ("value", "ms_per_step", "e2e", "stages_ms", "index_build", "roofline", "cpu_baseline", "parity_checked", "index")})
+        except Exception as e:            # the attached record must never cost the main line
+            extra["error"] = "%s: %s" % (type(e).__name__, e)
     if rank == 0:
         line = {"metric": "read_kmers_per_s_through_get_node_counts", "value": res["value"], "unit": "kmers/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
