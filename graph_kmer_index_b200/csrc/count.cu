@@ -717,11 +717,22 @@ __global__ void node_counts_csr_kernel(TableView t, const uint32_t *__restrict__
 // read-modify-write of a random HBM line, two DRAM accesses each against a ceiling of ~37 G random accesses/s (590 M additions:
 // 31 ms).  Instead the per-entry weights are materialised once in slot order (streaming), and the additions are made in passes over
 // node ranges whose counts stay in L2: each pass streams (node, weight) pairs -- 8 bytes per entry -- and adds the ones of its range.
+// The (node, weight) pairs are packed into ONE 32-bit word -- node in the low node_bits, weight above -- so a pass streams 4 bytes per
+// entry; the few weights that do not fit (a k-mer counted >= 2^(32 - node_bits) times) are stored as 0 there and added right away
+// with a plain atomic (they are rare, and then the counter really is hot).
 __global__ void entry_weights_kernel(TableView t, const uint32_t *__restrict__ cs_slot, const uint32_t *__restrict__ cs_node, int64_t n,
-                                     uint32_t *__restrict__ w, bool wrap16) {
+                                     uint32_t *__restrict__ packed, int node_bits, double *__restrict__ out, int64_t n_out, bool wrap16) {
+    const uint32_t w_limit = 1u << (32 - node_bits);
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t v = read_orientation(slot_counters(t, __ldg(cs_slot + i)), __ldg(cs_node + i) >> 31);
-        w[i] = wrap16 ? (v & 0xFFFFu) : v;
+        const uint32_t nd = __ldg(cs_node + i);
+        uint32_t v = read_orientation(slot_counters(t, __ldg(cs_slot + i)), nd >> 31);
+        if (wrap16) v &= 0xFFFFu;
+        const uint32_t node = nd & 0x7fffffffu;
+        if (v >= w_limit) {
+            if ((int64_t)node < n_out) atomicAdd(out + node, (double)v);
+            v = 0;
+        }
+        packed[i] = node | (v << node_bits);
     }
 }
 struct U32x8 {
@@ -735,21 +746,21 @@ __device__ __forceinline__ U32x8 ld_stream_256(const void *p) {   // streamed on
     r.v[4] = (uint32_t)c; r.v[5] = (uint32_t)(c >> 32); r.v[6] = (uint32_t)d; r.v[7] = (uint32_t)(d >> 32);
     return r;
 }
-__global__ void node_counts_slice_kernel(const uint32_t *__restrict__ cs_node, const uint32_t *__restrict__ w, int64_t n, double *__restrict__ out,
-                                         uint32_t lo, uint32_t hi) {
+__global__ void node_counts_slice_kernel(const uint32_t *__restrict__ packed, int64_t n, int node_bits, double *__restrict__ out, uint32_t lo, uint32_t hi) {
+    const uint32_t node_mask = (1u << node_bits) - 1u;
     const int64_t n8 = n >> 3;
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n8; q += (int64_t)gridDim.x * blockDim.x) {
-        const U32x8 nd = ld_stream_256(cs_node + 8 * q), wt = ld_stream_256(w + 8 * q);
+        const U32x8 p = ld_stream_256(packed + 8 * q);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const uint32_t a = nd.v[j] & 0x7fffffffu;
-            if (wt.v[j] && a >= lo && a < hi) atomicAdd(out + a, (double)wt.v[j]);
+            const uint32_t node = p.v[j] & node_mask, w = p.v[j] >> node_bits;
+            if (w && node >= lo && node < hi) atomicAdd(out + node, (double)w);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
-        const int64_t i = (n8 << 3) + threadIdx.x;
-        const uint32_t a = cs_node[i] & 0x7fffffffu;
-        if (w[i] && a >= lo && a < hi) atomicAdd(out + a, (double)w[i]);
+        const uint32_t v = packed[(n8 << 3) + threadIdx.x];
+        const uint32_t node = v & node_mask, w = v >> node_bits;
+        if (w && node >= lo && node < hi) atomicAdd(out + node, (double)w);
     }
 }
 
@@ -1577,18 +1588,20 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
         const int grid = grid_for(ix->n, 256 * 4, device_info().sms * 16);
         size_t slice_bytes = (size_t)48 << 20;   // node counts per pass: must stay in L2 (126 MB) next to the streams (measured at c3: 32 MB 18.9 ms, 48 MB 15.2, 64 MB 15.4, 96 MB 17.6)
         if (const char *e = getenv("GKI_NODE_SLICE_MB")) slice_bytes = (size_t)(atoi(e) > 0 ? atoi(e) : 0) << 20;
-        if (ix->cs_slot && slice_bytes && (size_t)n_out * 8 > slice_bytes + (slice_bytes >> 1)) {
+        if (ix->cs_slot && slice_bytes && (size_t)n_out * 8 > slice_bytes + (slice_bytes >> 1) && ix->max_node < (1ll << 28)) {
+            int node_bits = 1;
+            while ((1ll << node_bits) <= ix->max_node) node_bits++;
             Scratch w;
             GKI_TRY(w.alloc((size_t)ix->n * 4, call.stream));
-            entry_weights_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, w.as<uint32_t>(), wrap);
+            entry_weights_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, w.as<uint32_t>(), node_bits, o.as<double>(), n_out, wrap);
             GKI_CHECK_LAUNCH();
             const int64_t passes = ((int64_t)n_out * 8 + (int64_t)slice_bytes - 1) / (int64_t)slice_bytes;
             const int64_t per = (n_out + passes - 1) / passes;
-            const int grid4 = grid_for(ix->n / 8 + 1, 256, device_info().sms * 16);
+            const int grid8 = grid_for(ix->n / 8 + 1, 256, device_info().sms * 16);
             for (int64_t p = 0; p < passes; p++) {
                 const int64_t lo = p * per, hi = std::min<int64_t>(n_out, lo + per);
                 if (lo >= hi) break;
-                node_counts_slice_kernel<<<grid4, 256, 0, call.stream>>>(ix->cs_node, w.as<uint32_t>(), ix->n, o.as<double>(), (uint32_t)lo, (uint32_t)hi);
+                node_counts_slice_kernel<<<grid8, 256, 0, call.stream>>>(w.as<uint32_t>(), ix->n, node_bits, o.as<double>(), (uint32_t)lo, (uint32_t)hi);
                 GKI_CHECK_LAUNCH();
             }
         } else if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);

@@ -527,6 +527,13 @@ def test_node_counts_with_more_nodes_than_l2(gki, monkeypatch, slice_mb):
     assert np.array_equal(dev.node_counts(n_nodes + 12345), np.concatenate([want, np.zeros(12345)]))
     want16 = c_oracle.node_counts_from_entry_counts(idx, c_oracle.count_reads(idx, reads, k) & np.uint32(0xffff), n_nodes)
     assert np.array_equal(dev.node_counts(n_nodes, wrap_uint16=True), want16)
+    # k-mers counted more often than the packed (node, weight) words of the passes can hold (24 node bits leave 8 for the weight)
+    hot = np.concatenate([np.full(100_000, idx["_kmers"][5]), np.full(255, idx["_kmers"][77]), np.full(256, idx["_kmers"][1234])]).astype(np.uint64)
+    dev.count_kmers(hot)
+    ec = c_oracle.count_reads(idx, reads, k)
+    c_oracle.count_kmers(idx, hot, ec)
+    assert np.array_equal(dev.node_counts(n_nodes), c_oracle.node_counts_from_entry_counts(idx, ec, n_nodes))
+    assert np.array_equal(dev.node_counts(n_nodes, wrap_uint16=True), c_oracle.node_counts_from_entry_counts(idx, ec & np.uint32(0xffff), n_nodes))
     dev.close()
 
 
