@@ -358,16 +358,32 @@ def measure(args, cfg, name, rank, world, local_rank, full):
     s_kmers, s_nodes = torch.empty_like(hashes), torch.empty_like(nodes)
     s_ref, s_af, s_freq = torch.empty_like(ref), torch.empty_like(af), torch.empty(n, dtype=torch.int16, device=dev)
 
-    def build_all():      # the FlatKmers -> index call of cfki:422-467 with every column (skip_frequencies as the reference's throughput runs)
-        _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), n, modulo, _lib.GKI_BUILD_SKIP_FREQUENCIES,
+    def build_all(cols=None):   # the FlatKmers -> index call of cfki:422-467 with every column (skip_frequencies as the reference's throughput runs)
+        c_h, c_n, c_r, c_a = cols or (hashes, nodes, ref, af)
+        _lib.call("gki_index_build", _lib.ptr(c_h), _lib.ptr(c_n), _lib.ptr(c_r), _lib.ptr(c_a), n, modulo, _lib.GKI_BUILD_SKIP_FREQUENCIES,
                   _lib.ptr(h2i), _lib.ptr(nkm), _lib.ptr(s_kmers), _lib.ptr(s_nodes), _lib.ptr(s_ref), _lib.ptr(s_af), _lib.ptr(s_freq), None, stream)
 
     def build_narrow():   # k-mers + nodes only (what counting needs)
         _lib.call("gki_index_build", _lib.ptr(hashes), _lib.ptr(nodes), None, None, n, modulo, _lib.GKI_BUILD_SKIP_FREQUENCIES,
                   _lib.ptr(h2i), _lib.ptr(nkm), _lib.ptr(s_kmers), _lib.ptr(s_nodes), None, None, None, None, stream)
 
-    build_ms = timed(build_all)
     build_bytes = 50.0 * n + 8.0 * modulo          # 24 B/entry in, 24 + 2 B/entry out, both dense tables
+    # the same FlatKmers in the order DenseKmerFinder emits them (kmer_finder.py:223-240: the rows of a k-mer, one per node of its path,
+    # follow each other; the synthetic generator shuffles them apart, the worst case for the scatter) -- timed first, the index the steps
+    # below use is the one built from the shuffled rows
+    j = torch.arange(n, dtype=torch.int64, device=dev)
+    pos = j * synthetic.PERM_MULT          # the generator's shuffle, undone: row j was drawn from position (j * MULT + ADD) % n
+    pos += synthetic.PERM_ADD
+    pos %= n
+    order = torch.empty_like(j)
+    order[pos] = j
+    del j, pos
+    ordered = tuple(c[order] for c in (hashes, nodes, ref, af))
+    del order
+    ordered_ms = timed(lambda: build_all(ordered))
+    del ordered
+    torch.cuda.empty_cache()
+    build_ms = timed(build_all)
     del ref, af, s_ref, s_af, s_freq
     narrow_ms = timed(build_narrow)
     narrow_bytes = 24.0 * n + 8.0 * modulo
@@ -375,6 +391,8 @@ def measure(args, cfg, name, rank, world, local_rank, full):
                    "roofline": {"bound": "hbm", "bytes": build_bytes, "ms": build_ms, "achieved": build_bytes / build_ms / 1e6, "peak": peak, "unit": "GB/s",
                                 "frac": build_bytes / build_ms / 1e6 / peak, "model": "compulsory traffic 50 N + 8 modulo (SURVEY 8d)"},
                    "kmers_nodes_only": {"ms": narrow_ms, "bytes": narrow_bytes, "frac": narrow_bytes / narrow_ms / 1e6 / peak},
+                   "rows_in_finder_order": {"ms": ordered_ms, "bytes": build_bytes, "frac": build_bytes / ordered_ms / 1e6 / peak,
+                                            "what": "same entries, the rows of a k-mer adjacent as DenseKmerFinder emits them (runs of 2 here)"},
                    "note": "gki_index_build (skip_frequencies), device-resident, best of two after one warm call; slab path: append-scatter into "
                            "fixed-capacity slabs + per-slab ordering in shared memory (csrc/build.cu)"}
     part_build = None

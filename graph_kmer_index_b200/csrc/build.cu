@@ -575,59 +575,104 @@ struct SlabParams {
 };
 __device__ __forceinline__ uint32_t slab_bin_of(uint32_t bucket, const SlabParams &p) { return (uint32_t)__umul64hi((uint64_t)bucket, p.nb_magic); }
 
-// HINT (experiment, GKI_SLAB_HINT): L2 eviction priority of the slab stores (1: evict_last, 3: evict_normal stated explicitly,
-// 4: evict_first) and, with bit 3 (8) added, evict_first on the streamed input loads
-template <int UNROLL, int HINT>
-__global__ void __launch_bounds__(256, UNROLL >= 4 ? 5 : 8)
+// Rows of one k-mer sit next to each other in a FlatKmers as the finder emits it (one row per node of the k-mer's path,
+// kmer_finder.py:223-240), so neighbouring lanes often hold the same bin.  In the RUNS instantiation the first lane of such a run
+// reserves the whole run with ONE returning atomic and the run's records leave as one store request to consecutive slots: a run of two
+// costs one request out of the ~36 G/s budget instead of two (profiles/r2/calibrate_store_groups.jsonl; 60 M entries in runs of two:
+// 2.98 -> 2.39 ms, 1 B: 44.6 -> 34.2 ms, profiles/r2/slab_scatter_runs.log).  The order of the slots inside a slab is irrelevant: the
+// finish pass ranks the records of a bucket by input index.  On rows without such runs the shuffles cost 3-5 %, so a sampling kernel
+// looks at 4096 neighbouring pairs first and BOTH instantiations are launched: the one the sample did not choose returns at once.
+// The reservation has two steps, so that the atomics of a lane's UNROLL records are all in flight before the first result is used.
+struct SlabRun {
+    uint32_t base;    // value returned by the run head's atomic (meaningful on the head lane), then the record's slot
+    uint32_t head;    // lane of the run's head | valid << 5 | bucket inside the bin << 6
+};
+__device__ __forceinline__ SlabRun slab_reserve_issue(uint32_t *__restrict__ count, uint32_t bin, bool valid, int lane) {
+    const uint32_t prev = __shfl_up_sync(0xffffffffu, valid ? bin : 0xffffffffu, 1);
+    const bool head = lane == 0 || prev != bin || !valid;      // an invalid lane is a run of its own (its neighbour above sees bin 0xffffffff)
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const int head_lane = 31 - __clz(heads & (0xffffffffu >> (31 - lane)));
+    SlabRun r;
+    r.base = 0;
+    r.head = (uint32_t)head_lane | ((uint32_t)valid << 5);
+    if (head && valid) {
+        const uint32_t above = lane == 31 ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        r.base = atomicAdd(count + bin, (uint32_t)((above ? __ffs(above) - 1 : 32) - lane));
+    }
+    return r;
+}
+__device__ __forceinline__ uint32_t slab_reserve_slot(const SlabRun &r, int lane) {   // SLAB_CAP or more: invalid lane or overflowing slab
+    const int head_lane = (int)(r.head & 31u);
+    const uint32_t base = __shfl_sync(0xffffffffu, r.base, head_lane);
+    return ((r.head >> 5) & 1u) ? base + (uint32_t)(lane - head_lane) : (uint32_t)SLAB_CAP;
+}
+// *runs = 1 iff at least 1/8 of 4096 pairs of neighbouring rows, spread over the input, hold the same k-mer.  keys: the k-mer column
+// (stride_words = 1) or the k-mer field of 32-byte records (stride_words = 4).
+constexpr int SLAB_SAMPLE_PAIRS = 4096;
+__global__ void __launch_bounds__(256) slab_sample_runs_kernel(const uint64_t *__restrict__ keys, int stride_words, int64_t n, uint32_t *__restrict__ runs) {
+    __shared__ uint32_t equal;
+    if (threadIdx.x == 0) equal = 0;
+    __syncthreads();
+    uint32_t mine = 0;
+    for (int q = threadIdx.x; q < SLAB_SAMPLE_PAIRS && n >= 2; q += blockDim.x) {
+        const int64_t i = (int64_t)(((unsigned __int128)(uint64_t)(n - 1) * (uint64_t)q) / SLAB_SAMPLE_PAIRS);
+        mine += __ldg(keys + i * stride_words) == __ldg(keys + (i + 1) * stride_words);
+    }
+    if (mine) atomicAdd(&equal, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) *runs = equal >= SLAB_SAMPLE_PAIRS / 8;
+}
+
+template <int UNROLL, int MINB, bool RUNS>
+__global__ void __launch_bounds__(256, MINB)
 slab_scatter_kernel(int64_t n, const uint64_t *__restrict__ kmers, const uint32_t *__restrict__ nodes, const uint64_t *__restrict__ ref,
                     const float *__restrict__ af, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
-                    uint32_t *__restrict__ overflow) {
+                    uint32_t *__restrict__ overflow, const uint32_t *__restrict__ runs) {
+    if ((__ldg(runs) != 0u) != RUNS) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    unsigned long long pol_st = 0, pol_ld = 0;
-    if ((HINT & 7) == 1) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_st));
-    if ((HINT & 7) == 3) asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol_st));
-    if ((HINT & 7) == 4) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_st));
-    if (HINT & 8) asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ld));
-    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
+    const int lane = threadIdx.x & 31;
+    // RUNS: warp-uniform trip count, the lanes of a warp stay together for the shuffles
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; (RUNS ? base - lane : base) < n; base += stride * UNROLL) {
         unsigned long long km[UNROLL];
-        uint32_t bin[UNROLL], bl[UNROLL], pos[UNROLL];
+        uint32_t bin[UNROLL];
+        SlabRun run[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
-            km[u] = 0ull;
-            if (i < n) {
-                if (HINT & 8) asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(km[u]) : "l"(kmers + i), "l"(pol_ld));
-                else km[u] = __ldg(kmers + i);
-            }
+            km[u] = i < n ? __ldg(kmers + i) : 0ull;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
             const uint32_t b = fastmod(km[u], p.fm) - p.bucket_lo;
             bin[u] = slab_bin_of(b, p);
-            bl[u] = b - bin[u] * p.nb;
-            pos[u] = SLAB_CAP;
-            if (i < n && bin[u] < p.n_bins) pos[u] = atomicAdd(count + bin[u], 1u);
+            const bool valid = i < n && bin[u] < p.n_bins;
+            if (RUNS) {
+                run[u] = slab_reserve_issue(count, bin[u], valid, lane);
+            } else {
+                run[u].base = valid ? atomicAdd(count + bin[u], 1u) : (uint32_t)SLAB_CAP;
+                run[u].head = 0;
+            }
+            run[u].head |= (b - bin[u] * p.nb) << 6;
+        }
+        if (RUNS) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) run[u].base = slab_reserve_slot(run[u], lane);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
             if (i >= n) continue;
-            if (pos[u] >= (uint32_t)SLAB_CAP) {
+            if (run[u].base >= (uint32_t)SLAB_CAP) {
                 *overflow = 1u;
                 continue;
             }
             const unsigned long long nd = nodes ? __ldg(nodes + i) : 0u;
             const unsigned long long a = af ? __float_as_uint(__ldg(af + i)) : 0u;
             const unsigned long long r = ref ? __ldg(ref + i) : 0ull;
-            const unsigned long long tag = (unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32);
-            BinRecord *dst = slab + (size_t)bin[u] * SLAB_CAP + pos[u];
-            if (HINT & 7)
-                asm volatile("st.global.L2::cache_hint.v4.u64 [%0], {%1, %2, %3, %4}, %5;" ::"l"(dst), "l"(km[u]), "l"(r), "l"(nd | (a << 32)), "l"(tag),
-                             "l"(pol_st)
-                             : "memory");
-            else
-                asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(km[u]), "l"(r), "l"(nd | (a << 32)), "l"(tag) : "memory");
+            const unsigned long long tag = (unsigned long long)(uint32_t)i | ((unsigned long long)(run[u].head >> 6) << 32);
+            BinRecord *dst = slab + (size_t)bin[u] * SLAB_CAP + run[u].base;
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(km[u]), "l"(r), "l"(nd | (a << 32)), "l"(tag) : "memory");
         }
     }
 }
@@ -834,7 +879,9 @@ __device__ __forceinline__ void slab_finish_bin(const SlabParams &p, const SlabS
 }
 
 __global__ void __launch_bounds__(SLAB_THREADS, 2)
-slab_finish_kernel(SlabParams p, const uint32_t *__restrict__ count, const uint32_t *__restrict__ bin_start, const BinRecord *__restrict__ slab, SlabOut o) {
+slab_finish_kernel(SlabParams p, const uint32_t *__restrict__ count, const uint32_t *__restrict__ bin_start, const BinRecord *__restrict__ slab, SlabOut o,
+                   const uint32_t *__restrict__ overflow) {
+    if (__ldg(overflow)) return;   // a slab overflowed in the scatter: the caller falls back to another path
     extern __shared__ __align__(128) unsigned char slab_smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t warp_tot[SLAB_THREADS / 32 + 1];
@@ -945,14 +992,17 @@ __global__ void part_counts_from_offsets_kernel(const uint32_t *__restrict__ off
     counts[p] = hi - lo;
 }
 // receiver: the slab scatter fed by records (index = position in the record array)
-template <int UNROLL>
-__global__ void __launch_bounds__(256, 5)
+template <int UNROLL, int MINB, bool RUNS>
+__global__ void __launch_bounds__(256, MINB)
 slab_scatter_records_kernel(int64_t n, const BinRecord *__restrict__ in, SlabParams p, uint32_t *__restrict__ count, BinRecord *__restrict__ slab,
-                            uint32_t *__restrict__ overflow) {
+                            uint32_t *__restrict__ overflow, const uint32_t *__restrict__ runs) {
+    if ((__ldg(runs) != 0u) != RUNS) return;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * UNROLL) {
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; (RUNS ? base - lane : base) < n; base += stride * UNROLL) {
         BinRecord rec[UNROLL];
-        uint32_t bin[UNROLL], bl[UNROLL], pos[UNROLL];
+        uint32_t bin[UNROLL];
+        SlabRun run[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
@@ -963,20 +1013,29 @@ slab_scatter_records_kernel(int64_t n, const BinRecord *__restrict__ in, SlabPar
             const int64_t i = base + u * stride;
             const uint32_t b = (uint32_t)rec[u].index - p.bucket_lo;
             bin[u] = slab_bin_of(b, p);
-            bl[u] = b - bin[u] * p.nb;
-            pos[u] = SLAB_CAP;
-            if (i < n && bin[u] < p.n_bins) pos[u] = atomicAdd(count + bin[u], 1u);
+            const bool valid = i < n && bin[u] < p.n_bins;
+            if (RUNS) {
+                run[u] = slab_reserve_issue(count, bin[u], valid, lane);
+            } else {
+                run[u].base = valid ? atomicAdd(count + bin[u], 1u) : (uint32_t)SLAB_CAP;
+                run[u].head = 0;
+            }
+            run[u].head |= (b - bin[u] * p.nb) << 6;
+        }
+        if (RUNS) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) run[u].base = slab_reserve_slot(run[u], lane);
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) {
             const int64_t i = base + u * stride;
             if (i >= n) continue;
-            if (pos[u] >= (uint32_t)SLAB_CAP) {
+            if (run[u].base >= (uint32_t)SLAB_CAP) {
                 *overflow = 1u;
                 continue;
             }
-            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slab + (size_t)bin[u] * SLAB_CAP + pos[u]), "l"(rec[u].kmer), "l"(rec[u].ref),
-                         "l"(rec[u].node_af), "l"((unsigned long long)(uint32_t)i | ((unsigned long long)bl[u] << 32))
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(slab + (size_t)bin[u] * SLAB_CAP + run[u].base), "l"(rec[u].kmer), "l"(rec[u].ref),
+                         "l"(rec[u].node_af), "l"((unsigned long long)(uint32_t)i | ((unsigned long long)(run[u].head >> 6) << 32))
                          : "memory");
         }
     }
@@ -1247,31 +1306,41 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         if (n_bins < (1ull << 31) / SLAB_CAP * 64 && smem <= device_info().smem_optin && slab.try_alloc((size_t)n_bins * SLAB_CAP * sizeof(BinRecord), s)) {
             GKI_TRY(counts.alloc((size_t)(n_bins + 1) * 4, s));
             GKI_TRY(starts.alloc((size_t)(n_bins + 1) * 4, s));
-            GKI_TRY(flag.alloc(4, s));
+            GKI_TRY(flag.alloc(8, s));                      // [overflow, runs]
             GKI_CUDA(cudaMemsetAsync(counts.ptr, 0, (size_t)(n_bins + 1) * 4, s));
-            GKI_CUDA(cudaMemsetAsync(flag.ptr, 0, 4, s));
+            GKI_CUDA(cudaMemsetAsync(flag.ptr, 0, 8, s));
+            // the scatter kernel for rows with / without runs of one k-mer: chosen on the device by a sample of neighbouring pairs
+            uint32_t *runs_flag = flag.as<uint32_t>() + 1;
+            const char *force_runs = getenv("GKI_SLAB_RUNS");   // tests force a kernel: "0" / "1"
+            if (force_runs) {
+                const uint32_t v = force_runs[0] == '1';
+                GKI_CUDA(cudaMemcpyAsync(runs_flag, &v, 4, cudaMemcpyHostToDevice, s));
+            } else {
+                slab_sample_runs_kernel<<<1, 256, 0, s>>>(records ? (const uint64_t *)records : d_kmers.as<uint64_t>(), records ? 4 : 1, n, runs_flag);
+                GKI_CHECK_LAUNCH();
+            }
             const int sgrid = grid_for(n, 256 * 4, device_info().sms * 8);
             if (records) {
-                slab_scatter_records_kernel<4><<<sgrid, 256, 0, s>>>(n, (const BinRecord *)records, sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>());
+                slab_scatter_records_kernel<4, 5, false><<<sgrid, 256, 0, s>>>(n, (const BinRecord *)records, sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>(), runs_flag);
+                GKI_CHECK_LAUNCH();
+                slab_scatter_records_kernel<3, 5, true><<<sgrid, 256, 0, s>>>(n, (const BinRecord *)records, sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>(), runs_flag);
             } else {
-#ifdef GKI_EXPERIMENT_KNOBS   // L2 eviction hints on the slab stores / input loads (no effect measured: profiles/r2/slab_scatter_l2_hints.log)
-                const int hint = experiment_knob("GKI_SLAB_HINT") ? atoi(experiment_knob("GKI_SLAB_HINT")) : 0;
-                if (hint == 1) slab_scatter_kernel<4, 1><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>());
-                else if (hint == 8) slab_scatter_kernel<4, 8><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>());
-                else
-#endif
-                slab_scatter_kernel<4, 0><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>());
+                slab_scatter_kernel<4, 5, false><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>(), runs_flag);
+                GKI_CHECK_LAUNCH();
+                slab_scatter_kernel<3, 5, true><<<sgrid, 256, 0, s>>>(n, d_kmers.as<uint64_t>(), d_nodes.as<uint32_t>(), d_ref.as<uint64_t>(), d_af.as<float>(), sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>(), runs_flag);
             }
+            GKI_CHECK_LAUNCH();
+            GKI_TRY(exclusive_scan_u32(counts.as<uint32_t>(), starts.as<uint32_t>(), (int64_t)n_bins + 1, nullptr, s));
+            // the finish pass is queued behind the scatter without a host round trip: it looks at the overflow flag itself and
+            // leaves at once when a slab overflowed (the fallback paths below then write every output)
+            GKI_CUDA(cudaFuncSetAttribute(slab_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const int grid = (int)std::min<uint64_t>(n_bins, (uint64_t)device_info().sms * 2);
+            slab_finish_kernel<<<grid, SLAB_THREADS, smem, s>>>(sp, counts.as<uint32_t>(), starts.as<uint32_t>(), slab.as<BinRecord>(), so, flag.as<uint32_t>());
             GKI_CHECK_LAUNCH();
             uint32_t overflow = 0;
             GKI_CUDA(cudaMemcpyAsync(&overflow, flag.ptr, 4, cudaMemcpyDeviceToHost, s));
-            GKI_TRY(exclusive_scan_u32(counts.as<uint32_t>(), starts.as<uint32_t>(), (int64_t)n_bins + 1, nullptr, s));
             GKI_CUDA(cudaStreamSynchronize(s));
             if (!overflow) {
-                GKI_CUDA(cudaFuncSetAttribute(slab_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                const int grid = (int)std::min<uint64_t>(n_bins, (uint64_t)device_info().sms * 2);
-                slab_finish_kernel<<<grid, SLAB_THREADS, smem, s>>>(sp, counts.as<uint32_t>(), starts.as<uint32_t>(), slab.as<BinRecord>(), so);
-                GKI_CHECK_LAUNCH();
                 binned = true;
                 freq_done = want_freq;   // computed in the finish pass
             } else {

@@ -19,6 +19,15 @@ nodes = torch.empty(n, dtype=torch.int32, device=dev)
 ref = torch.empty(n, dtype=torch.int64, device=dev)
 af = torch.empty(n, dtype=torch.float32, device=dev)
 _lib.call("gki_synth_flat_kmers", _lib.ptr(genome), n, n // 10, k, _lib.ptr(hashes), _lib.ptr(nodes), _lib.ptr(ref), _lib.ptr(af), None)
+if os.environ.get("GKI_SYNTH_ORDER") == "finder":      # rows of a k-mer adjacent, as DenseKmerFinder emits them (the generator shuffles them apart)
+    j = torch.arange(n, dtype=torch.int64, device=dev)
+    pos = (j * synthetic.PERM_MULT + synthetic.PERM_ADD) % n
+    order = torch.empty_like(j)
+    order[pos] = j
+    del j, pos
+    hashes, nodes, ref, af = (c[order] for c in (hashes, nodes, ref, af))
+    del order
+    torch.cuda.empty_cache()
 h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
 nkm = torch.empty(modulo, dtype=torch.int32, device=dev)
 o_k, o_r, o_n, o_a = torch.empty_like(hashes), torch.empty_like(ref), torch.empty_like(nodes), torch.empty_like(af)
@@ -64,4 +73,4 @@ for path in paths:
         by = compulsory_bytes(columns, flags)
         print(json.dumps(dict(path=path, columns=columns, skip_frequencies=bool(flags), entries=n, ms=best, g_entries_per_s=n / best / 1e6,
                               compulsory_bytes=by, compulsory_gbs=by / best / 1e6, frac_of_measured_hbm=by / best / 1e6 / 6552.3,
-                              slab_mean=os.environ.get("GKI_SLAB_MEAN"))), flush=True)
+                              slab_mean=os.environ.get("GKI_SLAB_MEAN"), order=os.environ.get("GKI_SYNTH_ORDER", "shuffled"))), flush=True)

@@ -115,6 +115,10 @@ def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
         monkeypatch.setenv("GKI_BUILD_PATH", path)
         index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo, skip_frequencies=skip)
         assert_index_equal(index, want)
+    monkeypatch.setenv("GKI_BUILD_PATH", "slab")
+    monkeypatch.setenv("GKI_SLAB_RUNS", "1")               # the run-reserving scatter kernel on rows the sample would not give it
+    assert_index_equal(gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo, skip_frequencies=skip), want)
+    monkeypatch.delenv("GKI_SLAB_RUNS")
     # kmers + nodes only and the permutation
     outs = {}
     for path in ("slab", "binned", "radix"):
@@ -131,6 +135,39 @@ def test_build_paths_vs_oracle(gki, monkeypatch, n, modulo, skip, dup):
     h2i, nk, k_o, n_o, perm = outs["slab"]
     assert np.array_equal(h2i, want["_hashes_to_index"]) and np.array_equal(nk, want["_n_kmers"])
     assert np.array_equal(k_o, hashes[perm]) and np.array_equal(n_o, nodes[perm]) and np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("n,modulo", [(400_003, 19999999), (1_200_001, 452930477 // 16), (70_001, 65521)])
+def test_build_rows_of_a_kmer_adjacent_as_the_finder_emits_them(gki, monkeypatch, n, modulo):
+    """FlatKmers in the order DenseKmerFinder produces (kmer_finder.py:223-240): the rows of one k-mer -- one per node of its path --
+    follow each other.  The slab scatter reserves the slots of such a run of lanes with one atomic; runs of 1-5 rows, runs of 40 and
+    of 100 rows (longer than a warp), a run across the end of the array."""
+    from graph_kmer_index_b200 import _lib, synthetic
+    rng = np.random.default_rng(n)
+    base_h, _, base_r, _ = synthetic.flat_kmers(n, max(n // 10, 1), 31)
+    lens = rng.integers(1, 6, size=n)
+    lens[::997] = 40
+    lens[5::4999] = 100
+    owner = np.repeat(np.arange(n), lens)[:n]                     # row -> k-mer number; the last run is cut by the end of the array
+    hashes, ref = base_h[owner], (base_r[owner] + (rng.integers(0, 2, size=n)).astype(np.uint64))
+    nodes = rng.integers(0, max(n // 10, 1), size=n).astype(np.uint32)
+    af = rng.random(n).astype(np.float32)
+    want = c_oracle.build_index(hashes, nodes, ref, af, modulo)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    for path, runs in (("slab", None), ("slab", "0"), ("slab", "1"), ("radix", None)):
+        monkeypatch.setenv("GKI_BUILD_PATH", path)
+        if runs is None:
+            monkeypatch.delenv("GKI_SLAB_RUNS", raising=False)      # the sample of neighbouring rows chooses the scatter kernel
+        else:
+            monkeypatch.setenv("GKI_SLAB_RUNS", runs)
+        assert_index_equal(gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo), want)
+    monkeypatch.delenv("GKI_SLAB_RUNS", raising=False)
+    monkeypatch.setenv("GKI_BUILD_PATH", "slab")
+    h2i, nk, perm = np.empty(modulo, np.int32), np.empty(modulo, np.uint32), np.empty(n, np.uint32)
+    _lib.call("gki_index_build", _lib.ptr(hashes), None, None, None, n, modulo, 1, _lib.ptr(h2i), _lib.ptr(nk), None, None, None, None, None,
+              _lib.ptr(perm), None)
+    assert np.array_equal(h2i, want["_hashes_to_index"]) and np.array_equal(nk, want["_n_kmers"])
+    assert np.array_equal(hashes[perm], want["_kmers"]) and np.array_equal(np.sort(perm), np.arange(n, dtype=np.uint32))
 
 
 def test_build_dtypes_and_defaults(gki):
@@ -448,10 +485,14 @@ def test_partitioned_build_emulated_on_one_gpu(gki, world, n, heavy):
 
 @pytest.mark.parametrize("world,n,heavy,columns", [(1, 50_000, True, "all"), (2, 50_000, True, "all"), (8, 50_000, False, "all"), (2, 400_000, False, "all"),
                                                    (3, 600_000, False, "all"), (4, 500_000, False, "narrow"), (32, 300_000, True, "all")])
-def test_partitioned_build_with_packed_records_emulated_on_one_gpu(gki, world, n, heavy, columns):
+@pytest.mark.parametrize("runs", [None, "1"])
+def test_partitioned_build_with_packed_records_emulated_on_one_gpu(gki, monkeypatch, world, n, heavy, columns, runs):
     """the one-exchange form of the hash-range partitioned build (gki_partition_pack -> all-to-all of 32-byte records ->
-    gki_index_build_records), ranks emulated one after another: the slices concatenated in rank order are the oracle's index"""
+    gki_index_build_records), ranks emulated one after another: the slices concatenated in rank order are the oracle's index;
+    `runs`: the scatter kernel chosen by the sample of neighbouring rows / the run-reserving one forced"""
     import torch
+    if runs is not None:
+        monkeypatch.setenv("GKI_SLAB_RUNS", runs)
     from graph_kmer_index_b200 import _lib, synthetic
     from graph_kmer_index_b200.distributed import bucket_range, shard_bounds
     modulo, k = (100_003 if heavy else 1_000_003), 31
