@@ -175,6 +175,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
 }
 // same with an L2 eviction policy (createpolicy): read batches stream through L2 once and should not displace
 // resident structures
+// asks L2 for `bytes` (multiple of 16) at a 16-byte aligned global address; no shared memory, no barrier
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar, unsigned long long policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(dst_smem)),
