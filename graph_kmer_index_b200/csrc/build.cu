@@ -1060,12 +1060,21 @@ __global__ void unpack_records_kernel(const BinRecord *__restrict__ in, int64_t 
 // set_frequencies (cfki:267-293), pass 1: first[e] = 1 iff no earlier entry of the bucket has the same
 // (k-mer, ref_offset) pair
 // (the bucket of entry e is the key of its sort element, or, after the binned build, kmers[e] % modulo - bucket_lo)
+// Both passes compare an entry with the other entries of its bucket, quadratic in the bucket length: buckets of more than
+// HEAVY_BUCKET entries (one k-mer thousands of times: poly-A, N runs; or a tiny modulo) are left to the hash-set passes below
+// and counted in *n_heavy.
+constexpr uint32_t HEAVY_BUCKET = 256;
 __global__ void freq_first_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
-                                  const uint64_t *__restrict__ ref, const int32_t *__restrict__ h2i, int64_t n,
-                                  uint8_t *__restrict__ first, FastMod fm, uint32_t bucket_lo) {
+                                  const uint64_t *__restrict__ ref, const int32_t *__restrict__ h2i, const uint32_t *__restrict__ nk, int64_t n,
+                                  uint8_t *__restrict__ first, FastMod fm, uint32_t bucket_lo, unsigned long long *__restrict__ n_heavy) {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         uint64_t km = __ldg(kmers + e);
-        int64_t s = h2i[sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo];
+        const uint32_t b = sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo;
+        if (nk[b] > HEAVY_BUCKET) {
+            atomicAdd(n_heavy, 1ull);
+            continue;
+        }
+        int64_t s = h2i[b];
         uint64_t ro = ref ? __ldg(ref + e) : 0ull;
         uint8_t f = 1;
         for (int64_t c = e - 1; c >= s; c--) {
@@ -1084,6 +1093,7 @@ __global__ void freq_count_kernel(const unsigned long long *__restrict__ sorted,
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         uint64_t km = __ldg(kmers + e);
         uint32_t b = sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo;
+        if (nk[b] > HEAVY_BUCKET) continue;
         int64_t s = h2i[b], t = s + nk[b];
         uint32_t c = 0;
         for (int64_t a = s; a < t; a++) c += (__ldg(kmers + a) == km) & first[a];
@@ -1091,23 +1101,97 @@ __global__ void freq_count_kernel(const unsigned long long *__restrict__ sorted,
     }
 }
 
-// flat_kmers.py:98-125: keep[i] = 0 for the first occurrence of a hash.  After the stable sort by
-// (hash % M) an earlier occurrence of the same hash sits earlier in the same key run.
-__global__ void non_first_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ hashes, int64_t n,
-                                 uint8_t *__restrict__ keep) {
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
-        unsigned long long mine = __ldg(sorted + p);
-        uint32_t key = elem_key(mine);
-        uint32_t me = elem_idx(mine);
-        uint64_t h = __ldg(hashes + me);
-        uint8_t seen = 0;
-        for (int64_t c = p - 1; c >= 0 && elem_key(__ldg(sorted + c)) == key; c--) {
-            if (__ldg(hashes + elem_idx(__ldg(sorted + c))) == h) {
-                seen = 1;
-                break;
+// ---- the same two passes for heavy buckets, linear in their length: open-addressing sets of ENTRY NUMBERS ----
+// A slot holds the number of the entry that claimed it (compare-and-swap on an empty slot); a later entry compares its key with the
+// key of the slot's entry (the columns are read-only here) and walks on if they differ.  Pass 1 claims a slot per distinct
+// (k-mer, ref offset) pair: the claimant is the pair's one `first` entry (the reference counts a set, cfki:288: which entry
+// stands for the pair does not matter).  Pass 2 claims a slot per distinct k-mer and adds the first-flagged entries to its
+// counter, lanes of a warp holding the same slot add once.  Pass 3 reads the counter back for every entry.
+constexpr uint32_t HSET_EMPTY = 0xffffffffu;
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+// slot of the entry with key (km, ro) in `slots` (mask + 1 slots, a power of two); INSERT: entry e claims an empty slot (claimed = true),
+// otherwise HSET_EMPTY when the key is absent.  key1 == nullptr: the key is km alone.
+template <bool INSERT>
+__device__ __forceinline__ uint32_t hset_slot(uint32_t *__restrict__ slots, uint32_t mask, uint32_t e, uint64_t km, uint64_t ro,
+                                              const uint64_t *__restrict__ key0, const uint64_t *__restrict__ key1, bool &claimed) {
+    uint32_t h = (uint32_t)mix64(km + mix64(key1 ? ro + 0x9E3779B97F4A7C15ull : 0ull)) & mask;
+    claimed = false;
+    for (;;) {
+        uint32_t o = __ldcg(slots + h);
+        if (o == HSET_EMPTY) {
+            if (!INSERT) return HSET_EMPTY;
+            o = atomicCAS(slots + h, HSET_EMPTY, e);
+            if (o == HSET_EMPTY) {
+                claimed = true;
+                return h;
             }
         }
-        keep[me] = seen;
+        if (__ldg(key0 + o) == km && (!key1 || __ldg(key1 + o) == ro)) return h;
+        h = (h + 1u) & mask;
+    }
+}
+__global__ void freq_heavy_pairs_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
+                                        const uint64_t *__restrict__ ref, const uint32_t *__restrict__ nk, int64_t n, FastMod fm,
+                                        uint32_t bucket_lo, uint32_t *__restrict__ slots, uint32_t mask, uint8_t *__restrict__ first) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t km = __ldg(kmers + e);
+        const uint32_t b = sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo;
+        if (nk[b] <= HEAVY_BUCKET) continue;
+        bool claimed;
+        hset_slot<true>(slots, mask, (uint32_t)e, km, ref ? __ldg(ref + e) : 0ull, kmers, ref, claimed);
+        first[e] = claimed;
+    }
+}
+// COUNT: first-flagged entries are added to their k-mer's counter; otherwise the counter is read back into freq
+template <bool COUNT>
+__global__ void freq_heavy_kmers_kernel(const unsigned long long *__restrict__ sorted, const uint64_t *__restrict__ kmers,
+                                        const uint32_t *__restrict__ nk, int64_t n, FastMod fm, uint32_t bucket_lo,
+                                        uint32_t *__restrict__ slots, uint32_t mask, const uint8_t *__restrict__ first,
+                                        uint32_t *__restrict__ counts, uint16_t *__restrict__ freq) {
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count (the lanes vote)
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e - lane < n; e += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t slot = HSET_EMPTY;
+        if (e < n) {
+            const uint64_t km = __ldg(kmers + e);
+            const uint32_t b = sorted ? elem_key(__ldg(sorted + e)) : fastmod(km, fm) - bucket_lo;
+            if (nk[b] > HEAVY_BUCKET && (!COUNT || first[e])) {
+                bool claimed;
+                slot = COUNT ? hset_slot<true>(slots, mask, (uint32_t)e, km, 0ull, kmers, nullptr, claimed)
+                             : hset_slot<false>(slots, mask, (uint32_t)e, km, 0ull, kmers, nullptr, claimed);
+                if (!COUNT) freq[e] = slot == HSET_EMPTY ? (uint16_t)0 : (uint16_t)__ldcg(counts + slot);
+            }
+        }
+        if (COUNT && __any_sync(0xffffffffu, slot != HSET_EMPTY)) {
+            const uint32_t same = __match_any_sync(0xffffffffu, slot);
+            if (slot != HSET_EMPTY && lane == __ffs(same) - 1) atomicAdd(counts + slot, (uint32_t)__popc(same));
+        }
+    }
+}
+
+// flat_kmers.py:98-125: keep[i] = 0 for the first occurrence of a hash, 1 for every later one.  A set of entry numbers keyed by
+// the hash (as above) with the smallest entry number seen per slot; linear whatever the multiplicity of a hash.
+__global__ void first_occurrence_min_kernel(const uint64_t *__restrict__ hashes, int64_t n, uint32_t *__restrict__ slots, uint32_t mask,
+                                            uint32_t *__restrict__ min_entry) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool claimed;
+        const uint32_t slot = hset_slot<true>(slots, mask, (uint32_t)i, __ldg(hashes + i), 0ull, hashes, nullptr, claimed);
+        if (__ldcg(min_entry + slot) > (uint32_t)i) atomicMin(min_entry + slot, (uint32_t)i);
+    }
+}
+__global__ void non_first_kernel(const uint64_t *__restrict__ hashes, int64_t n, uint32_t *__restrict__ slots, uint32_t mask,
+                                 const uint32_t *__restrict__ min_entry, uint8_t *__restrict__ keep) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        bool claimed;
+        const uint32_t slot = hset_slot<false>(slots, mask, (uint32_t)i, __ldg(hashes + i), 0ull, hashes, nullptr, claimed);
+        keep[i] = __ldg(min_entry + slot) != (uint32_t)i;
     }
 }
 
@@ -1451,13 +1535,40 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
         if (!want_freq) {
             GKI_CUDA(cudaMemsetAsync(o_freq.dptr, 0, (size_t)n * 2, s));   // cfki:270-274
         } else {
-            Scratch first;
+            Scratch first, heavy;
             GKI_TRY(first.alloc((size_t)n, s));
-            freq_first_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), n, first.as<uint8_t>(), fm, (uint32_t)bucket_lo);
+            GKI_TRY(heavy.alloc(8, s));
+            GKI_CUDA(cudaMemsetAsync(heavy.ptr, 0, 8, s));
+            freq_first_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), n, first.as<uint8_t>(), fm,
+                                                     (uint32_t)bucket_lo, heavy.as<unsigned long long>());
             GKI_CHECK_LAUNCH();
             freq_count_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, o_h2i.as<int32_t>(), o_nk.as<uint32_t>(), first.as<uint8_t>(), n,
                                                      o_freq.as<uint16_t>(), fm, (uint32_t)bucket_lo);
             GKI_CHECK_LAUNCH();
+            unsigned long long n_heavy = 0;
+            GKI_CUDA(cudaMemcpyAsync(&n_heavy, heavy.ptr, 8, cudaMemcpyDeviceToHost, s));
+            GKI_CUDA(cudaStreamSynchronize(s));
+            if (n_heavy) {   // entries of buckets longer than HEAVY_BUCKET: the hash-set passes (linear in the bucket length)
+                uint64_t cap = 1024;
+                while (cap < 2 * n_heavy) cap <<= 1;
+                Scratch pairs, kslots, kcounts;
+                GKI_TRY(pairs.alloc((size_t)cap * 4, s));
+                GKI_TRY(kslots.alloc((size_t)cap * 4, s));
+                GKI_TRY(kcounts.alloc((size_t)cap * 4, s));
+                GKI_CUDA(cudaMemsetAsync(pairs.ptr, 0xff, (size_t)cap * 4, s));
+                GKI_CUDA(cudaMemsetAsync(kslots.ptr, 0xff, (size_t)cap * 4, s));
+                GKI_CUDA(cudaMemsetAsync(kcounts.ptr, 0, (size_t)cap * 4, s));
+                const uint32_t hmask = (uint32_t)(cap - 1);
+                freq_heavy_pairs_kernel<<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, ref_sorted, o_nk.as<uint32_t>(), n, fm, (uint32_t)bucket_lo,
+                                                               pairs.as<uint32_t>(), hmask, first.as<uint8_t>());
+                GKI_CHECK_LAUNCH();
+                freq_heavy_kmers_kernel<true><<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, o_nk.as<uint32_t>(), n, fm, (uint32_t)bucket_lo, kslots.as<uint32_t>(),
+                                                                     hmask, first.as<uint8_t>(), kcounts.as<uint32_t>(), o_freq.as<uint16_t>());
+                GKI_CHECK_LAUNCH();
+                freq_heavy_kmers_kernel<false><<<grid_n, 256, 0, s>>>(sorted, kmers_sorted, o_nk.as<uint32_t>(), n, fm, (uint32_t)bucket_lo, kslots.as<uint32_t>(),
+                                                                      hmask, first.as<uint8_t>(), kcounts.as<uint32_t>(), o_freq.as<uint16_t>());
+                GKI_CHECK_LAUNCH();
+            }
         }
     }
     if (position_offset && !fold_offset) {
@@ -1678,12 +1789,17 @@ int gki_mark_non_first_occurrences(const uint64_t *hashes, int64_t n, uint8_t *k
     DevOut o;
     GKI_TRY(d_h.stage(hashes, (size_t)n * 8, s));
     GKI_TRY(o.prepare(keep, (size_t)n, s));
-    uint64_t m = (uint64_t)(2 * n + 1025) | 1ull;   // sparse odd table size: runs of distinct hashes stay short
-    if (m >= (1ull << 32)) m = (1ull << 32) - 1;
-    SortBuffers bufs;
-    const unsigned long long *sorted;
-    GKI_TRY(sort_by_bucket(d_h.as<uint64_t>(), n, m, 0u, 0u, m - 1, bufs, &sorted, s));
-    non_first_kernel<<<grid_for(n, 256 * 4, device_info().sms * 16), 256, 0, s>>>(sorted, d_h.as<uint64_t>(), n, o.as<uint8_t>());
+    uint64_t cap = 1024;
+    while (cap < 2 * (uint64_t)n) cap <<= 1;
+    Scratch slots, min_entry;
+    GKI_TRY(slots.alloc((size_t)cap * 4, s));
+    GKI_TRY(min_entry.alloc((size_t)cap * 4, s));
+    GKI_CUDA(cudaMemsetAsync(slots.ptr, 0xff, (size_t)cap * 4, s));
+    GKI_CUDA(cudaMemsetAsync(min_entry.ptr, 0xff, (size_t)cap * 4, s));
+    const int grid = grid_for(n, 256 * 4, device_info().sms * 16);
+    first_occurrence_min_kernel<<<grid, 256, 0, s>>>(d_h.as<uint64_t>(), n, slots.as<uint32_t>(), (uint32_t)(cap - 1), min_entry.as<uint32_t>());
+    GKI_CHECK_LAUNCH();
+    non_first_kernel<<<grid, 256, 0, s>>>(d_h.as<uint64_t>(), n, slots.as<uint32_t>(), (uint32_t)(cap - 1), min_entry.as<uint32_t>(), o.as<uint8_t>());
     GKI_CHECK_LAUNCH();
     GKI_TRY(o.finish(s));
     return call.finish();

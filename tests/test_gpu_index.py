@@ -218,6 +218,46 @@ def test_singletons_and_set_frequencies(gki):
     assert len(both._hashes) == 8000 and both._nodes.dtype == np.uint32 and both._ref_offsets.dtype == np.uint64
 
 
+def test_one_kmer_hundreds_of_thousands_of_times(gki):
+    """a k-mer present 200 000 times (poly-A, N runs on real graphs) and one present 70 000 times at distinct ref offsets: the build
+    falls back to the radix path and its frequency passes, and the first-occurrence marking, must stay linear in the length of such
+    a bucket (pairwise comparison would be 10^10 loads here).  Frequencies are checked against cfki:286-290 restated with np.unique
+    (the C oracle compares pairwise too), the other arrays against the oracle without frequencies."""
+    import time
+    from graph_kmer_index_b200 import synthetic
+    n, modulo = 600_000, 1_000_003
+    hashes, nodes, ref, af = synthetic.flat_kmers(n, 5000, 31)
+    rng = np.random.default_rng(11)
+    hashes, ref = hashes.copy(), ref.copy()
+    a = rng.choice(n, 270_000, replace=False)
+    hashes[a[:200_000]] = hashes[a[0]]
+    ref[a[:200_000]] = rng.integers(0, 1000, 200_000).astype(np.uint64)          # 1000 distinct ref offsets
+    hashes[a[200_000:]] = hashes[a[200_000]]
+    ref[a[200_000:]] = np.arange(70_000, dtype=np.uint64) + np.uint64(5)          # 70 000 distinct: the uint16 frequency wraps (cfki:270)
+    flat = gki.FlatKmers(hashes, nodes, ref, af)
+    gki.CollisionFreeKmerIndex.from_flat_kmers(gki.FlatKmers(hashes[:50_000], nodes[:50_000], ref[:50_000], af[:50_000]), modulo=modulo)   # warm
+    t0 = time.perf_counter()
+    index = gki.CollisionFreeKmerIndex.from_flat_kmers(flat, modulo=modulo)
+    seconds = time.perf_counter() - t0
+    want = c_oracle.build_index(hashes, nodes, ref, af, modulo, skip_frequencies=True)
+    for key in ("_hashes_to_index", "_n_kmers", "_kmers", "_nodes", "_ref_offsets", "_allele_frequencies"):
+        assert np.array_equal(getattr(index, key), want[key]), key
+    pairs = np.unique(np.stack([hashes, ref], axis=1), axis=0)
+    kmers_u, refs_per_kmer = np.unique(pairs[:, 0], return_counts=True)
+    freq = refs_per_kmer[np.searchsorted(kmers_u, index._kmers)].astype(np.uint16)
+    assert np.array_equal(index._frequencies, freq)
+    assert refs_per_kmer.max() >= 70_000 and 1000 <= int(index._frequencies[index._kmers == hashes[a[0]]][0]) <= 1001      # one wraps uint16, one does not
+    assert seconds < 5.0, seconds
+    t0 = time.perf_counter()
+    kept = flat.get_new_without_singletons()
+    seconds = time.perf_counter() - t0
+    _, first = np.unique(hashes, return_index=True)
+    keep = np.ones(n, dtype=bool)
+    keep[first] = False
+    assert np.array_equal(kept._hashes, hashes[keep]) and np.array_equal(kept._nodes, nodes[keep]) and np.array_equal(kept._ref_offsets, ref[keep])
+    assert seconds < 5.0, seconds
+
+
 @pytest.mark.parametrize("name", ["index_small", "index_sparse"])
 def test_lookup_and_counts_golden(gki, name):
     g = load_golden(name)
