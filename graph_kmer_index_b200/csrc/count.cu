@@ -467,8 +467,20 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
         fence_mbar_init();
     }
     __syncwarp();
-    const int64_t total_warps = (int64_t)gridDim.x * COUNT_WARPS;
-    int64_t wt = (int64_t)blockIdx.x * COUNT_WARPS + warp;
+    // A CTA owns a contiguous range of tiles and its warps take them one by one from a shared counter: a warp that drew costly reads
+    // (reads from the indexed sequence probe the table at every window) takes fewer tiles, and the CTA's slots are not held by one
+    // slow warp while seven have finished.
+    __shared__ uint32_t cta_taken;
+    const int64_t per_cta = (b.n_wtiles + gridDim.x - 1) / gridDim.x;
+    const int64_t c0 = (int64_t)blockIdx.x * per_cta, c1 = min(c0 + per_cta, b.n_wtiles);
+    if (threadIdx.x == 0) cta_taken = COUNT_WARPS;       // the first tile of every warp is its own
+    __syncthreads();
+    auto take = [&]() -> int64_t {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&cta_taken, 1u);
+        return c0 + (int64_t)__shfl_sync(0xffffffffu, t, 0);
+    };
+    int64_t wt = c0 + warp;
     auto uses_bulk = [&](int64_t tile) { return b.bulk_ok && (tile + 1) * (int64_t)b.rpw <= b.n_reads; };
     auto issue = [&](int64_t tile, int stage) {   // stage: PACKED only (code stage and its mbarrier)
         void *dst = PACKED ? (void *)(stage ? valid : codes) : (void *)ascii;
@@ -478,11 +490,11 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
         if (HINTS & 4) bulk_g2s_hint(dst, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, mb, pol_stream);
         else bulk_g2s(dst, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, mb);
     };
-    if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt, 0);
+    if (wt < c1 && lane == 0 && uses_bulk(wt)) issue(wt, 0);
     uint32_t phase = 0;   // PACKED: bit s is the parity of stage s
 
-    for (int it = 0; wt < b.n_wtiles; wt += total_warps, ++it) {
-        const int64_t next = wt + total_warps;
+    for (int it = 0; wt < c1; ++it) {
+        int64_t next = c1;    // taken from the counter when its copy is issued
         const int64_t r0 = wt * (int64_t)b.rpw;
         const int n_here = (int)min((int64_t)b.rpw, b.n_reads - r0);
         const uint64_t *tile_codes = codes;
@@ -490,7 +502,8 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             const int st = it & 1;
             tile_codes = st ? valid : codes;
             __syncwarp();
-            if (next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next, st ^ 1);   // the other stage was walked last round
+            next = take();
+            if (next < c1 && lane == 0 && uses_bulk(next)) issue(next, st ^ 1);   // the other stage was walked last round
             if (uses_bulk(wt)) {
                 mbar_wait(bar + st, (phase >> st) & 1u);
                 phase ^= 1u << st;
@@ -546,7 +559,10 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             ((uint32_t *)valid)[(size_t)r * halves + h] = v32;
         }
         __syncwarp();
-        if (!PACKED && next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next, 0);   // prefetch: overlaps the walk below
+        if (!PACKED) {
+            next = take();
+            if (next < c1 && lane == 0 && uses_bulk(next)) issue(next, 0);   // prefetch: overlaps the walk below
+        }
         // ---- walk the reads ----
         for (int r = 0; r < n_here; r++) {
             const uint64_t *cw = tile_codes + (size_t)r * b.words;
@@ -658,6 +674,7 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
             }
         }
         __syncwarp();
+        wt = next;
     }
     __syncwarp();
     if (qn != qhead) probe_queue(qn - qhead);   // drain the queue
@@ -960,7 +977,13 @@ static int launch_count_reads_t(gki_index *ix, const WarpBatch &b, cudaStream_t 
         const int v = atoi(e);
         if (v >= 1 && v < blocks_per_sm) blocks_per_sm = v;
     }
-    int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm);
+    // The grid is 16 times what is resident.  Reads drawn from the indexed sequence cost several times what other reads cost (a
+    // table line per window), so warps that stride over the batch in one persistent wave finish up to 10 % apart and the launch
+    // waits for the slowest; CTAs of ~16 tiles per warp are dealt out by the hardware as slots free up.  c2: 9.10 -> 8.40 ms,
+    // c3: 46.0 -> 40.0 ms (profiles/r2/count_kernel_grid_oversubscription.log; 8: 8.57, 16: 8.43, 32: 8.41 ms).
+    int grid_mult = 16;
+    if (const char *e = experiment_knob("GKI_COUNT_GRID_MULT")) grid_mult = atoi(e) > 0 ? atoi(e) : grid_mult;
+    int grid = grid_for(b.n_wtiles, COUNT_WARPS, device_info().sms * blocks_per_sm * grid_mult);
     count_reads_kernel<BOTH, PAIRED, MINB, HINTS, PACKED, KODD, FK, MINZ><<<grid, COUNT_THREADS, smem, s>>>(ix->table, b);
     GKI_CHECK_LAUNCH();
     return GKI_OK;

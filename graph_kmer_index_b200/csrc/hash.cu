@@ -18,65 +18,173 @@ __device__ __forceinline__ void st_global_v4_u64(uint64_t *p, uint64_t a, uint64
     asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(HASH_THREADS) hash_reads_kernel(ReadBatch b, uint64_t *__restrict__ fwd,
-                                                                  uint64_t *__restrict__ rc) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint64_t mask = kmer_mask(b.k);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    for_each_tile(b, smem_raw, [&](int64_t tile, const TileSmem &t) {
-        int64_t r0 = tile * (int64_t)b.tile_reads;
-        for (int r = warp; r < b.tile_reads && r0 + r < b.n_reads; r += nwarps) {
-            const uint64_t *cw = t.codes + (size_t)r * b.words;
-            const uint64_t *vw = t.valid + (size_t)r * b.words;
-            uint64_t *of = fwd ? fwd + (r0 + r) * (int64_t)b.nk : nullptr;
-            uint64_t *orc = rc ? rc + (r0 + r) * (int64_t)b.nk : nullptr;
-            // a read made only of ACGTacgt (the usual case): every lane owns four consecutive windows, extracted once and
-            // rolled three times (x >> 2 | next base on top; the reverse complement rolls the other way), and stores each
-            // strand's four hashes with one 256-bit store
-            bool ok = true;
-            for (int w = lane; w < b.words - 1; w += 32) {
-                const int nb = min(32, b.read_len - w * 32);
-                ok &= vw[w] == (nb < 32 ? ((1ull << (2 * nb)) - 1ull) : ~0ull);
-            }
-            if (__all_sync(0xffffffffu, ok)) {
-                for (int i0 = lane * 4; i0 < b.nk; i0 += 128) {
-                    uint64_t x[4], y[4];
-                    x[0] = extract_window(cw, i0, mask);
-                    const uint32_t nxt = (uint32_t)extract_window(cw, i0 + b.k, 0x3Full);
-                    y[0] = revcomp_hash(x[0], b.k);
+// All hashes of a read made only of ACGTacgt (the usual case), by one warp: every lane owns four consecutive windows and writes each
+// strand's four hashes with one 256-bit store.  cw: the read's code words; of / orc: its rows of the two outputs.
+template <bool FWD, bool RC>
+__device__ __forceinline__ void emit_clean_read(const uint64_t *cw, int nk, int k, uint64_t mask, uint64_t *of, uint64_t *orc, int lane) {
+    const bool wide_f = FWD && (((uintptr_t)of & 31) == 0), wide_r = RC && (((uintptr_t)(orc + nk) & 31) == 0);
+    const uint32_t *cw32 = (const uint32_t *)cw;
+    for (int i0 = lane * 4; i0 < nk; i0 += 128) {
+        // the lane's first window starts on a byte boundary of the packed read (4 bases): three byte permutes bring 96 bits from
+        // there into place, and window u is those bits shifted by the constant 2u
+        const int wi = i0 >> 4;
+        const uint32_t sel = 0x3210u + 0x1111u * (((uint32_t)i0 >> 2) & 3u);
+        const uint32_t w0 = cw32[wi], w1 = cw32[wi + 1], w2 = cw32[wi + 2], w3 = cw32[wi + 3];   // (beyond the read: pad word, next read, `valid`)
+        const uint32_t a0 = __byte_perm(w0, w1, sel), a1 = __byte_perm(w1, w2, sel), a2 = __byte_perm(w2, w3, sel);
+        const int n_valid = min(4, nk - i0);
+        uint64_t x[4];
 #pragma unroll
-                    for (int u = 1; u < 4; u++) {
-                        const uint64_t nb = (nxt >> (2 * (u - 1))) & 3u;
-                        x[u] = (x[u - 1] >> 2) | (nb << (2 * (b.k - 1)));
-                        y[u] = ((y[u - 1] << 2) | (3u - nb)) & mask;
-                    }
-                    const int n_valid = min(4, b.nk - i0);
-                    if (of) {
-                        uint64_t *p = of + i0;
-                        if (n_valid == 4 && ((uintptr_t)p & 31) == 0) st_global_v4_u64(p, x[0], x[1], x[2], x[3]);
-                        else
-                            for (int u = 0; u < n_valid; u++) p[u] = x[u];
-                    }
-                    if (orc) {   // window i of the read is window nk-1-i of the reverse-complemented read
-                        uint64_t *q = orc + (b.nk - 4 - i0);
-                        if (n_valid == 4 && ((uintptr_t)q & 31) == 0) st_global_v4_u64(q, y[3], y[2], y[1], y[0]);
-                        else
-                            for (int u = 0; u < n_valid; u++) orc[b.nk - 1 - i0 - u] = y[u];
-                    }
-                }
-                continue;
-            }
-            for (int i = lane; i < b.nk; i += 32) {
-                uint64_t x = extract_window(cw, i, mask);
-                if (of) of[i] = x;
-                if (orc) {
-                    uint64_t v = extract_window(vw, i, mask);
-                    // window i of the read is window nk-1-i of the reverse-complemented read
-                    orc[b.nk - 1 - i] = revcomp_hash_masked(x, v, b.k);
-                }
+        for (int u = 0; u < 4; u++) {
+            const uint32_t lo = u ? __funnelshift_r(a0, a1, 2 * u) : a0, hi = u ? __funnelshift_r(a1, a2, 2 * u) : a1;
+            x[u] = (((uint64_t)hi << 32) | lo) & mask;
+        }
+        uint64_t y0 = 0;
+        uint32_t tops = 0;      // the bases that enter on top of windows 1..3 (two bits each)
+        if (RC) {
+            y0 = revcomp_hash(x[0], k);
+            const int ts = 2 * (k - 1);
+            tops = (uint32_t)((x[1] >> ts) & 3u) | ((uint32_t)((x[2] >> ts) & 3u) << 2) | ((uint32_t)((x[3] >> ts) & 3u) << 4);
+        }
+        if (FWD) {
+            if (n_valid == 4 && wide_f) st_global_v4_u64(of + i0, x[0], x[1], x[2], x[3]);
+            else
+                for (int u = 0; u < n_valid; u++) of[i0 + u] = x[u];
+        }
+        if (RC) {   // window i of the read is window nk-1-i of the reverse-complemented read; its hash rolls the other way
+            const uint64_t y1 = ((y0 << 2) | (3u - (tops & 3u))) & mask;
+            const uint64_t y2 = ((y1 << 2) | (3u - ((tops >> 2) & 3u))) & mask;
+            const uint64_t y3 = ((y2 << 2) | (3u - (tops >> 4))) & mask;
+            if (n_valid == 4 && wide_r) st_global_v4_u64(orc + (nk - 4 - i0), y3, y2, y1, y0);
+            else {
+                const uint64_t y[4] = {y0, y1, y2, y3};
+                for (int u = 0; u < n_valid; u++) orc[nk - 1 - i0 - u] = y[u];
             }
         }
-    });
+    }
+}
+
+// Warp-autonomous (round 2).  The first version worked on CTA-wide tiles of 32 reads between three barriers, rolled the windows with
+// 64-bit variable shifts and spent ~280 warp instructions per read whether it wrote one strand or two: 0.86 of the HBM roofline with
+// both strands, 0.49 with the forward strand alone -- the call the reference exposes (read_kmers.py:67-70).  Now 0.92 / 0.98
+// (profiles/r2/k1_warp_autonomous.log).  A warp owns tiles of `rpw` reads: its own mbarrier, its own TMA bulk copy of the ASCII
+// rows (issued for the next tile as soon as the current one is packed), a pack phase of 16-base tasks that fill the warp evenly,
+// then one read at a time.  FWD / RC: the strands written (the other strand's arithmetic is not compiled in).  The grid is NOT
+// sized to the resident CTAs: in one wave of persistent CTAs all warps pack at the same time and store at the same time, and the
+// launch is slower the fewer CTAs there are (2 M reads, forward strand: 0.419 ms with 6 x 148 CTAs, 0.365 ms with 48 x 148, 0.345 ms
+// = 0.98 of the roofline with a tile per warp; both strands 0.808 / 0.722 / 0.684 ms = 0.92); short-lived CTAs arrive staggered and keep
+// the store stream even.  The loop over tiles remains for batches larger than the grid limit.
+struct HashWarpBatch {
+    const uint8_t *reads;
+    int64_t n_reads;
+    int64_t row_stride;
+    int64_t n_wtiles;       // ceil(n_reads / rpw)
+    int32_t read_len;
+    int32_t k;
+    int32_t nk;             // read_len - k + 1
+    int32_t words;          // ceil(read_len / 32) + 1
+    int32_t rpw;            // reads per warp tile
+    int32_t bulk_ok;        // dense + aligned: full tiles are one TMA bulk copy
+    uint32_t inv_halves;    // ceil(65536 / (2 * words)): task / (2 * words) == task * inv_halves >> 16 for every task of a tile
+    uint32_t stage_bytes;   // bytes of the ASCII stage (16-byte multiple, incl. slack)
+    uint32_t warp_bytes;    // shared memory per warp
+};
+constexpr int HASH_WARPS = HASH_THREADS / 32;
+
+template <bool FWD, bool RC>
+__global__ void __launch_bounds__(HASH_THREADS, 6) hash_reads_kernel(HashWarpBatch b, uint64_t *__restrict__ fwd, uint64_t *__restrict__ rc) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char *wbase = smem_raw + (size_t)warp * b.warp_bytes;     // [mbarrier | ASCII stage | codes | valid | dirty flags]
+    uint64_t *bar = (uint64_t *)wbase;
+    uint8_t *ascii = wbase + 16;
+    uint64_t *codes = (uint64_t *)(wbase + 16 + (size_t)b.stage_bytes);
+    uint64_t *valid = codes + (size_t)b.rpw * b.words;
+    uint32_t *dirty = (uint32_t *)(valid + (size_t)b.rpw * b.words);
+    const uint64_t mask = kmer_mask(b.k);
+    const uint32_t tile_bytes = (uint32_t)b.rpw * (uint32_t)b.read_len;
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+    }
+    __syncwarp();
+    const int64_t total_warps = (int64_t)gridDim.x * HASH_WARPS;
+    int64_t wt = (int64_t)blockIdx.x * HASH_WARPS + warp;
+    auto uses_bulk = [&](int64_t tile) { return b.bulk_ok && (tile + 1) * (int64_t)b.rpw <= b.n_reads; };
+    auto issue = [&](int64_t tile) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, tile_bytes);
+        bulk_g2s(ascii, b.reads + tile * (int64_t)b.rpw * b.row_stride, tile_bytes, bar);
+    };
+    if (wt < b.n_wtiles && lane == 0 && uses_bulk(wt)) issue(wt);
+    uint32_t phase = 0;
+    const int halves = 2 * b.words;
+    for (; wt < b.n_wtiles; wt += total_warps) {
+        const int64_t next = wt + total_warps;
+        const int64_t r0 = wt * (int64_t)b.rpw;
+        const int n_here = (int)min((int64_t)b.rpw, b.n_reads - r0);
+        if (uses_bulk(wt)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {   // strided / unaligned / tail tile: the warp copies its rows itself
+            for (int r = 0; r < n_here; r++) {
+                const uint8_t *src = b.reads + (r0 + r) * b.row_stride;
+                for (int i = lane; i < b.read_len; i += 32) ascii[(size_t)r * b.read_len + i] = __ldg(src + i);
+            }
+            __syncwarp();
+        }
+        // ---- pack to 2 bits per base (+ validity); one task = 16 bases = one 32-bit half of a code word (the pad word included) ----
+        if (lane < n_here) dirty[lane] = 0;
+        __syncwarp();
+        for (int task = lane; task < n_here * halves; task += 32) {
+            const int r = (int)(((uint32_t)task * b.inv_halves) >> 16), h = task - r * halves;   // task / halves (exact, checked on the host)
+            const int first = h * 16;
+            const int nb = min(16, b.read_len - first);
+            uint32_t c32 = 0, v32 = 0;
+            if (nb > 0) {
+                const uint32_t addr = (uint32_t)r * (uint32_t)b.read_len + (uint32_t)first;
+                const uint32_t *aligned = (const uint32_t *)(ascii + (addr & ~3u));
+                const uint32_t sh = (addr & 3u) * 8u;
+                uint32_t lo = aligned[0];
+                const int nq = (nb + 3) >> 2;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (q < nq) {
+                        const uint32_t hi = aligned[q + 1];
+                        uint32_t c8, v8;
+                        encode4(__funnelshift_r(lo, hi, sh), c8, v8);
+                        lo = hi;
+                        c32 |= c8 << (8 * q);
+                        v32 |= v8 << (8 * q);
+                    }
+                }
+                const uint32_t m = nb < 16 ? ((1u << (2 * nb)) - 1u) : ~0u;
+                c32 &= m;
+                v32 &= m;
+                if (v32 != m) dirty[r] = 1;
+            }
+            ((uint32_t *)codes)[(size_t)r * halves + h] = c32;
+            ((uint32_t *)valid)[(size_t)r * halves + h] = v32;
+        }
+        __syncwarp();
+        if (next < b.n_wtiles && lane == 0 && uses_bulk(next)) issue(next);   // the stage is dead once packed: the next tile lands during the walk
+        // ---- one read at a time ----
+        for (int r = 0; r < n_here; r++) {
+            const uint64_t *cw = codes + (size_t)r * b.words;
+            uint64_t *of = FWD ? fwd + (r0 + r) * (int64_t)b.nk : nullptr;
+            uint64_t *orc = RC ? rc + (r0 + r) * (int64_t)b.nk : nullptr;
+            if (!dirty[r]) {
+                emit_clean_read<FWD, RC>(cw, b.nk, b.k, mask, of, orc, lane);
+                continue;
+            }
+            const uint64_t *vw = valid + (size_t)r * b.words;
+            for (int i = lane; i < b.nk; i += 32) {
+                const uint64_t x = extract_window(cw, i, mask);
+                if (FWD) of[i] = x;
+                if (RC) orc[b.nk - 1 - i] = revcomp_hash_masked(x, extract_window(vw, i, mask), b.k);
+            }
+        }
+        __syncwarp();   // the next round's pack overwrites codes / valid / dirty
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -238,19 +346,45 @@ int gki_hash_reads(const uint8_t *reads, int64_t n_reads, int32_t read_len, int6
     GKI_TRY(in.stage(reads, in_bytes, call.stream));
     GKI_TRY(of.prepare(fwd, (size_t)n_reads * nk * 8, call.stream));
     GKI_TRY(orc.prepare(rc, (size_t)n_reads * nk * 8, call.stream));
-    ReadBatch b;
-    size_t smem;
-    make_read_batch(in.as<uint8_t>(), n_reads, read_len, row_stride, k, b, smem);
-    if (smem <= 64 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            GKI_CUDA(cudaFuncSetAttribute(hash_reads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            attr_set = true;
+    HashWarpBatch b{};
+    b.reads = in.as<uint8_t>();
+    b.n_reads = n_reads;
+    b.row_stride = row_stride;
+    b.read_len = read_len;
+    b.k = k;
+    b.nk = (int32_t)nk;
+    b.words = (read_len + 31) / 32 + 1;
+    auto warp_bytes = [&](int rpw) {
+        const size_t stage = (((size_t)rpw * read_len + 15) & ~(size_t)15) + 16;
+        return (16 + stage + 2 * (size_t)rpw * b.words * 8 + (size_t)rpw * 4 + 15) & ~(size_t)15;
+    };
+    int rpw = 8;
+    if (const char *e = experiment_knob("GKI_HASH_RPW")) rpw = atoi(e) < 1 ? 1 : (atoi(e) > 32 ? 32 : atoi(e));
+    while (rpw > 1 && warp_bytes(rpw) * HASH_WARPS > 36 * 1024) rpw >>= 1;
+    b.rpw = rpw;
+    b.inv_halves = 65536u / (2u * (uint32_t)b.words) + 1u;
+    bool warp_ok = warp_bytes(rpw) * HASH_WARPS <= 64 * 1024;
+    for (uint32_t task = 0; warp_ok && task < (uint32_t)rpw * 2u * (uint32_t)b.words; task++)
+        warp_ok = ((task * b.inv_halves) >> 16) == task / (2u * (uint32_t)b.words);
+    if (warp_ok) {
+        b.stage_bytes = (uint32_t)((((size_t)rpw * read_len + 15) & ~(size_t)15) + 16);
+        b.warp_bytes = (uint32_t)warp_bytes(rpw);
+        b.n_wtiles = (n_reads + rpw - 1) / rpw;
+        b.bulk_ok = (row_stride == read_len) && (((uintptr_t)b.reads & 15) == 0) && (((int64_t)rpw * read_len) % 16 == 0);
+        const size_t smem = (size_t)b.warp_bytes * HASH_WARPS;
+        int ctas_per_sm = 4096;   // in effect one tile per warp; 6 CTAs are resident (40 registers), the rest of the grid arrives staggered (see the kernel)
+        if (const char *e = experiment_knob("GKI_HASH_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : ctas_per_sm;
+        const int grid = grid_for(b.n_wtiles, HASH_WARPS, device_info().sms * ctas_per_sm);
+        if (fwd && rc) {
+            GKI_CUDA(cudaFuncSetAttribute(hash_reads_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            hash_reads_kernel<true, true><<<grid, HASH_THREADS, smem, call.stream>>>(b, of.as<uint64_t>(), orc.as<uint64_t>());
+        } else if (fwd) {
+            GKI_CUDA(cudaFuncSetAttribute(hash_reads_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            hash_reads_kernel<true, false><<<grid, HASH_THREADS, smem, call.stream>>>(b, of.as<uint64_t>(), nullptr);
+        } else {
+            GKI_CUDA(cudaFuncSetAttribute(hash_reads_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            hash_reads_kernel<false, true><<<grid, HASH_THREADS, smem, call.stream>>>(b, nullptr, orc.as<uint64_t>());
         }
-        int ctas_per_sm = 8;   // measured: 4 -> 0.881 ms, 6 -> 0.844 ms, 8 -> 0.822 ms for 2 M x 150 bp reads (registers allow 8)
-        if (const char *e = experiment_knob("GKI_HASH_CTAS")) ctas_per_sm = atoi(e) > 0 ? atoi(e) : 8;
-        int grid = grid_for(b.n_tiles, 1, device_info().sms * ctas_per_sm);
-        hash_reads_kernel<<<grid, HASH_THREADS, smem, call.stream>>>(b, of.as<uint64_t>(), orc.as<uint64_t>());
         GKI_CHECK_LAUNCH();
     } else {  // very long rows: byte-stream path
         StreamBatch sb{in.as<uint8_t>(), nullptr, nullptr, n_reads, (int64_t)in_bytes, row_stride, read_len, k};
