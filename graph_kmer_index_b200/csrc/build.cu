@@ -1408,7 +1408,14 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
                 slab_sample_runs_kernel<<<1, 256, 0, s>>>(records ? (const uint64_t *)records : d_kmers.as<uint64_t>(), records ? 4 : 1, n, runs_flag);
                 GKI_CHECK_LAUNCH();
             }
-            const int sgrid = grid_for(n, 256 * 4, device_info().sms * 8);
+            // Both slab kernels get many more CTAs than are resident: what a CTA takes is then decided as slots free up, and SMs that
+            // run slower (the far die, a busy L2 slice) take less.  One resident wave with a static stride: 60 M entries 2.99 / 2.35 ms
+            // (shuffled rows / rows in finder order), 1 B 43.7 / 31.4 ms; with these grids 2.84 / 2.20 and 41.1 / 29.3 ms
+            // (profiles/r2/slab_grid_oversubscription.log).
+            int scatter_mult = 32, finish_mult = 32;
+            if (const char *e = experiment_knob("GKI_SLAB_SCATTER_MULT")) scatter_mult = atoi(e) > 0 ? atoi(e) : scatter_mult;
+            if (const char *e = experiment_knob("GKI_SLAB_FINISH_MULT")) finish_mult = atoi(e) > 0 ? atoi(e) : finish_mult;
+            const int sgrid = grid_for(n, 256 * 4, device_info().sms * 8 * scatter_mult);
             if (records) {
                 slab_scatter_records_kernel<4, 5, false><<<sgrid, 256, 0, s>>>(n, (const BinRecord *)records, sp, counts.as<uint32_t>(), slab.as<BinRecord>(), flag.as<uint32_t>(), runs_flag);
                 GKI_CHECK_LAUNCH();
@@ -1423,7 +1430,7 @@ static int build_range(const uint64_t *kmers, const uint32_t *nodes, const uint6
             // the finish pass is queued behind the scatter without a host round trip: it looks at the overflow flag itself and
             // leaves at once when a slab overflowed (the fallback paths below then write every output)
             GKI_CUDA(cudaFuncSetAttribute(slab_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const int grid = (int)std::min<uint64_t>(n_bins, (uint64_t)device_info().sms * 2);
+            const int grid = (int)std::min<uint64_t>(n_bins, (uint64_t)device_info().sms * 2 * finish_mult);
             slab_finish_kernel<<<grid, SLAB_THREADS, smem, s>>>(sp, counts.as<uint32_t>(), starts.as<uint32_t>(), slab.as<BinRecord>(), so, flag.as<uint32_t>());
             GKI_CHECK_LAUNCH();
             uint32_t overflow = 0;
