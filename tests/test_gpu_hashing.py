@@ -130,6 +130,33 @@ def test_hash_layout_variants(gki):
     assert np.array_equal(dfwd.cpu().numpy(), want_f) and np.array_equal(drc.cpu().numpy(), want_r)
 
 
+@pytest.mark.parametrize("n,L,k", [(1003, 150, 31), (77, 150, 30), (500, 101, 17), (300, 75, 16), (64, 40, 5), (200, 150, 29)])
+def test_single_strand_kernels_and_unaligned_outputs(gki, n, L, k):
+    """the three instantiations of the hashing kernel (both strands, forward only, reverse complement only) through the C ABI, with
+    output rows that do and do not start on 32-byte boundaries (256-bit stores vs the scalar tail), reads with non-ACGT bytes among them"""
+    import torch
+    from graph_kmer_index_b200 import _lib
+    rng = np.random.default_rng(n + L + k)
+    reads = random_reads(rng, n, L, dirty=False).copy()     # most reads take the four-windows-per-lane path, one in seven the masked one
+    reads[rng.integers(0, n, max(n // 7, 1)), rng.integers(0, L, max(n // 7, 1))] = ord("N")
+    want_f, want_r = c_oracle.hash_reads(reads, k)
+    nk = L - k + 1
+    d = torch.from_numpy(reads).cuda()
+    for shift in (0, 1, 3):                                  # uint64 elements: 0 keeps the rows 32-byte aligned when nk % 4 == 0
+        f = torch.zeros(n * nk + 4, dtype=torch.int64, device="cuda")
+        r = torch.zeros(n * nk + 4, dtype=torch.int64, device="cuda")
+        fv, rv = f[shift:shift + n * nk], r[shift:shift + n * nk]
+        for use_f, use_r in ((True, True), (True, False), (False, True)):
+            f.zero_(), r.zero_()
+            _lib.call("gki_hash_reads", _lib.ptr(d), n, L, L, k, _lib.ptr(fv) if use_f else None, _lib.ptr(rv) if use_r else None, None)
+            torch.cuda.synchronize()
+            got_f, got_r = fv.cpu().numpy().view(np.uint64).reshape(n, nk), rv.cpu().numpy().view(np.uint64).reshape(n, nk)
+            assert np.array_equal(got_f, want_f) if use_f else not got_f.any(), (shift, use_f, use_r)
+            assert np.array_equal(got_r, want_r) if use_r else not got_r.any(), (shift, use_f, use_r)
+            assert int(f[:shift].abs().sum()) == 0 and int(f[shift + n * nk:].abs().sum()) == 0          # nothing outside the rows
+            assert int(r[:shift].abs().sum()) == 0 and int(r[shift + n * nk:].abs().sum()) == 0
+
+
 def test_long_rows_take_the_stream_path(gki):
     from graph_kmer_index_b200.read_kmers import hash_read_matrix
     rng = np.random.default_rng(9)
