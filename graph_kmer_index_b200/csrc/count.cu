@@ -614,22 +614,23 @@ __global__ void __launch_bounds__(COUNT_THREADS, MINB) count_reads_kernel(TableV
                         mz[2] = min(common, min(v[2], min(v[MZ_W], v[MZ_W + 1])));
                         mz[3] = min(common, min(v[MZ_W], min(v[MZ_W + 1], v[MZ_W + 2])));
                     }
-                    uint64_t x = 0, rc = 0;
-                    uint32_t nxt = 0;
-                    if (i0 < b.nk) {
-                        x = extract_window(cw, i0, mask);
-                        nxt = (uint32_t)extract_window(cw, i0 + b.k, 0x3Full);
-                        rc = revcomp_hash(x, b.k);
-                    }
+                    // the lane's first window starts on a byte boundary of the packed read (i0 is a multiple of 4 bases): three byte
+                    // permutes bring 96 bits from there into place, window u is those bits shifted by the constant 2u (as in K1, hash.cu);
+                    // the reverse-complement hash of the first window is a bit reversal and rolls on with the base that enters on top
+                    const uint32_t *cw32 = (const uint32_t *)cw;
+                    const int wi = i0 >> 4;
+                    const uint32_t sel = 0x3210u + 0x1111u * (((uint32_t)i0 >> 2) & 3u);
+                    const uint32_t w0 = cw32[wi], w1 = cw32[wi + 1], w2 = cw32[wi + 2], w3 = cw32[wi + 3];   // (beyond the read: pad word, next read, the arrays behind)
+                    const uint32_t a0 = __byte_perm(w0, w1, sel), a1 = __byte_perm(w1, w2, sel), a2 = __byte_perm(w2, w3, sel);
+                    uint64_t x = (((uint64_t)a1 << 32) | a0) & mask, rc = revcomp_hash(x, b.k);
                     unsigned long long c[WPL];
                     uint32_t home[WPL], fw[WPL], fm[WPL];
                     uint32_t live = 0, pal = 0;
 #pragma unroll
                     for (int u = 0; u < WPL; u++) {
                         if (u) {
-                            uint64_t nb = (nxt >> (2 * (u - 1))) & 3u;
-                            x = (x >> 2) | (nb << (2 * (b.k - 1)));
-                            rc = ((rc << 2) | (3u - nb)) & mask;
+                            x = (((uint64_t)__funnelshift_r(a1, a2, 2 * u) << 32) | __funnelshift_r(a0, a1, 2 * u)) & mask;
+                            rc = ((rc << 2) | (3u - ((x >> (2 * (b.k - 1))) & 3u))) & mask;
                         }
                         bool ok = i0 + u < b.nk;
                         c[u] = x < rc ? x : rc;
