@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <sys/mman.h>
 #include <thread>
 #include <vector>
 #include "common.cuh"
@@ -166,6 +167,13 @@ int parallel_host_copy(void *dev, void *host, size_t bytes, bool to_device, cuda
     std::lock_guard<std::mutex> lock(pool.mu);
     GKI_TRY(ensure_copy_pool(pool));
     GKI_CUDA(cudaEventRecord(pool.ready, s));
+    if (!to_device && env_i64("GKI_HOST_COPY_HUGEPAGES", 1)) {
+        // the destination is usually a fresh allocation that the copy threads fault in page by page: ask for 2 MB pages on its aligned
+        // interior (transparent huge pages in `madvise` mode; a refusal costs nothing)
+        const uintptr_t two_mb = (uintptr_t)2 << 20;
+        const uintptr_t lo = ((uintptr_t)host + two_mb - 1) & ~(two_mb - 1), hi = ((uintptr_t)host + bytes) & ~(two_mb - 1);
+        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+    }
     const size_t chunk = pool.chunk;
     const int64_t n_chunks = (int64_t)((bytes + chunk - 1) / chunk);
     std::atomic<int64_t> next{0};

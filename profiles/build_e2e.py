@@ -19,8 +19,9 @@ def main():
     flat = gki.FlatKmers(hashes, nodes, ref, af)
     modulo = 452930477
     first = None
-    for threads in ("0", "4", "8", "14"):
+    for threads, huge in (("0", "1"), ("8", "0"), ("8", "1"), ("14", "0"), ("14", "1"), ("8", "0"), ("8", "1")):
         os.environ["GKI_HOST_COPY_THREADS"] = threads
+        os.environ["GKI_HOST_COPY_HUGEPAGES"] = huge      # MADV_HUGEPAGE on the fresh destination arrays
         secs = []
         for _ in range(3):
             t0 = time.perf_counter()
@@ -30,7 +31,7 @@ def main():
             first = index
         else:
             assert np.array_equal(index._hashes_to_index, first._hashes_to_index) and np.array_equal(index._nodes, first._nodes)
-        print(json.dumps({"entries": n, "modulo": modulo, "host_copy_threads": int(threads), "seconds": secs, "entries_per_s": n / min(secs),
+        print(json.dumps({"entries": n, "modulo": modulo, "host_copy_threads": int(threads), "madvise_hugepage": int(huge), "seconds": secs, "entries_per_s": n / min(secs),
                           "host_bytes": 24 * n + 26 * n + 8 * modulo, "cpus": os.cpu_count()}), flush=True)
 
 
