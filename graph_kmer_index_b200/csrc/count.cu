@@ -782,6 +782,115 @@ __global__ void node_counts_slice_kernel(const uint32_t *__restrict__ packed, in
     }
 }
 
+// The passes above stream ALL (node, weight) words once per node range (c3: 9 passes of 4 GB).  Which range a word belongs to depends
+// only on the entry's node, so every tile of NB_TILE entries can write its words grouped by range, at places that are the same in
+// every call (nb_seg, built once: per-tile histogram of the ranges + one exclusive scan in range-major order); each range is then
+// read once.  A tile is ordered in shared memory (slot = the range's first place in the tile + a shared-memory atomic) and leaves with
+// coalesced stores.  Ranges are 2^nb_shift nodes (32 MB of counts).  c3 (1 B entries, 50 M nodes; ncu, profiles/r2/node_counts_ranged_launches.txt):
+// 60 GB -> 32 GB per call, 10.4 -> 9.6 ms: the words pass 6.6 ms (24 GB of table + entry list read, 4 GB written), the twelve ranges
+// 0.25 ms each, which is the rate of float64 REDs on L2-resident lines (49 M additions per range = 196 G/s).
+constexpr int NB_TILE = 8192, NB_THREADS = 256, NB_MAX_RANGES = 64;   // (gki_index::nb_bounds holds NB_MAX_RANGES + 1 values)
+__global__ void __launch_bounds__(NB_THREADS) node_range_hist_kernel(const uint32_t *__restrict__ cs_node, int64_t n, int shift, int ranges, int64_t n_tiles,
+                                                                     uint32_t *__restrict__ hist) {
+    __shared__ uint32_t h[NB_MAX_RANGES];
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        if (threadIdx.x < NB_MAX_RANGES) h[threadIdx.x] = 0;
+        __syncthreads();
+        const int64_t e0 = tile * NB_TILE, e1 = min(n, e0 + NB_TILE);
+        for (int64_t e = e0 + threadIdx.x; e < e1; e += NB_THREADS) atomicAdd(&h[(__ldg(cs_node + e) & 0x7fffffffu) >> shift], 1u);
+        __syncthreads();
+        if ((int)threadIdx.x < ranges) hist[(int64_t)threadIdx.x * n_tiles + tile] = h[threadIdx.x];
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(NB_THREADS) entry_weights_ranged_kernel(TableView t, const uint32_t *__restrict__ cs_slot, const uint32_t *__restrict__ cs_node,
+                                                                          int64_t n, const uint32_t *__restrict__ seg, int shift, int ranges, int64_t n_tiles,
+                                                                          uint32_t *__restrict__ packed, int node_bits, double *__restrict__ out, int64_t n_out,
+                                                                          bool wrap16) {
+    __shared__ uint32_t stage[NB_TILE];
+    __shared__ uint32_t first[NB_MAX_RANGES + 1], cursor[NB_MAX_RANGES], dst[NB_MAX_RANGES], len[NB_MAX_RANGES];
+    constexpr int U = 8;                 // entries per thread in flight: loads of a batch are issued before the first is used
+    const uint32_t w_limit = 1u << (32 - node_bits);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t e0 = tile * NB_TILE, e1 = min(n, e0 + NB_TILE);
+        if ((int)threadIdx.x < ranges) {
+            const int64_t at = (int64_t)threadIdx.x * n_tiles + tile;
+            const uint32_t a = __ldg(seg + at);
+            dst[threadIdx.x] = a;
+            len[threadIdx.x] = __ldg(seg + at + 1) - a;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {          // where each range starts inside the tile (a few dozen values)
+            uint32_t run = 0;
+            for (int r = 0; r < ranges; r++) {
+                first[r] = run;
+                cursor[r] = run;
+                run += len[r];
+            }
+            first[ranges] = run;
+        }
+        __syncthreads();
+        for (int64_t base = e0 + threadIdx.x; base < e1; base += NB_THREADS * U) {
+            uint32_t nd[U], sl[U], v[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int64_t e = base + (int64_t)u * NB_THREADS;
+                nd[u] = e < e1 ? __ldg(cs_node + e) : 0u;
+                sl[u] = e < e1 ? __ldg(cs_slot + e) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) v[u] = base + (int64_t)u * NB_THREADS < e1 ? read_orientation(slot_counters(t, sl[u]), nd[u] >> 31) : 0u;
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                if (base + (int64_t)u * NB_THREADS >= e1) continue;
+                uint32_t w = wrap16 ? (v[u] & 0xFFFFu) : v[u];
+                const uint32_t node = nd[u] & 0x7fffffffu;
+                if (w >= w_limit) {
+                    if ((int64_t)node < n_out) atomicAdd(out + node, (double)w);
+                    w = 0;
+                }
+                stage[atomicAdd(&cursor[node >> shift], 1u)] = node | (w << node_bits);
+            }
+        }
+        __syncthreads();
+        for (int r = 0; r < ranges; r++) {
+            const uint32_t lo = first[r], n_r = len[r], to = dst[r];
+            for (uint32_t j = threadIdx.x; j < n_r; j += NB_THREADS) packed[(size_t)to + j] = stage[lo + j];
+        }
+        __syncthreads();
+    }
+}
+// the words of one node range: packed[lo .. hi)
+__global__ void node_counts_range_kernel(const uint32_t *__restrict__ packed, int64_t lo, int64_t hi, int node_bits, double *__restrict__ out) {
+    const uint32_t node_mask = (1u << node_bits) - 1u;
+    const int64_t a = (lo + 7) & ~(int64_t)7, b = hi & ~(int64_t)7;       // 32-byte aligned interior, 256-bit streaming loads
+    if (a >= b) {
+        for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+            const uint32_t v = __ldg(packed + i);
+            if (v >> node_bits) atomicAdd(out + (v & node_mask), (double)(v >> node_bits));
+        }
+        return;
+    }
+    for (int64_t q = (a >> 3) + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < (b >> 3); q += (int64_t)gridDim.x * blockDim.x) {
+        const U32x8 p = ld_stream_256(packed + 8 * q);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t w = p.v[j] >> node_bits;
+            if (w) atomicAdd(out + (p.v[j] & node_mask), (double)w);
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (int64_t i = lo + threadIdx.x; i < a; i += blockDim.x) {
+            const uint32_t v = __ldg(packed + i);
+            if (v >> node_bits) atomicAdd(out + (v & node_mask), (double)(v >> node_bits));
+        }
+        for (int64_t i = b + threadIdx.x; i < hi; i += blockDim.x) {
+            const uint32_t v = __ldg(packed + i);
+            if (v >> node_bits) atomicAdd(out + (v & node_mask), (double)(v >> node_bits));
+        }
+    }
+}
+
 __global__ void query_counts_kernel(TableView t, const uint64_t *__restrict__ queries, int64_t nq, uint32_t *__restrict__ out) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nq; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = kmer_count(t, __ldg(queries + i), false);
@@ -796,7 +905,9 @@ void destroy_count_table(gki_index *ix) {
     cudaFree((void *)ix->table.filter);
     cudaFree(ix->cs_slot);
     cudaFree(ix->cs_node);
-    ix->cs_slot = ix->cs_node = nullptr;
+    cudaFree(ix->nb_seg);
+    ix->cs_slot = ix->cs_node = ix->nb_seg = nullptr;
+    ix->nb_ranges = 0;
     ix->table = TableView{};
     ix->table_bytes = ix->filter_bytes = 0;
 }
@@ -1621,6 +1732,42 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
             while ((1ll << node_bits) <= ix->max_node) node_bits++;
             Scratch w;
             GKI_TRY(w.alloc((size_t)ix->n * 4, call.stream));
+            // ranges of 2^22 nodes (32 MB of counts), words grouped by range tile by tile (GKI_NODE_RANGED=0: the passes over all words)
+            const int shift = 22;
+            const int ranges = (int)(ix->max_node >> shift) + 1;
+            const char *ranged_env = getenv("GKI_NODE_RANGED");
+            if (ranges <= NB_MAX_RANGES && (int64_t)ix->n < (1ll << 32) && !(ranged_env && ranged_env[0] == '0')) {
+                const int64_t n_tiles = (ix->n + NB_TILE - 1) / NB_TILE;
+                const int tgrid = (int)std::min<int64_t>(n_tiles, (int64_t)device_info().sms * 8 * node_grid_mult);
+                if (!ix->nb_seg || ix->nb_ranges != ranges || ix->nb_shift != shift || ix->nb_tiles != n_tiles) {
+                    cudaFree(ix->nb_seg);
+                    ix->nb_seg = nullptr;
+                    const size_t cells = (size_t)ranges * n_tiles + 1;
+                    Scratch hist;
+                    GKI_TRY(hist.alloc(cells * 4, call.stream));
+                    GKI_CUDA(cudaMemsetAsync(hist.ptr, 0, cells * 4, call.stream));
+                    node_range_hist_kernel<<<tgrid, NB_THREADS, 0, call.stream>>>(ix->cs_node, ix->n, shift, ranges, n_tiles, hist.as<uint32_t>());
+                    GKI_CHECK_LAUNCH();
+                    GKI_CUDA(cudaMalloc((void **)&ix->nb_seg, cells * 4));
+                    GKI_TRY(exclusive_scan_u32(hist.as<uint32_t>(), ix->nb_seg, (int64_t)cells, nullptr, call.stream));
+                    // first word of every range: ranges + 1 values of nb_seg, n_tiles apart
+                    GKI_CUDA(cudaMemcpy2DAsync(ix->nb_bounds, 4, ix->nb_seg, (size_t)n_tiles * 4, 4, ranges + 1, cudaMemcpyDeviceToHost, call.stream));
+                    GKI_CUDA(cudaStreamSynchronize(call.stream));
+                    ix->nb_ranges = ranges;
+                    ix->nb_shift = shift;
+                    ix->nb_tiles = n_tiles;
+                }
+                entry_weights_ranged_kernel<<<tgrid, NB_THREADS, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, ix->nb_seg, shift, ranges, n_tiles,
+                                                                                     w.as<uint32_t>(), node_bits, o.as<double>(), n_out, wrap);
+                GKI_CHECK_LAUNCH();
+                for (int r = 0; r < ranges; r++) {
+                    const int64_t lo = ix->nb_bounds[r], hi = ix->nb_bounds[r + 1];
+                    if (lo >= hi) continue;
+                    const int rgrid = grid_for((hi - lo) / 8 + 1, 256, device_info().sms * 16 * node_grid_mult);
+                    node_counts_range_kernel<<<rgrid, 256, 0, call.stream>>>(w.as<uint32_t>(), lo, hi, node_bits, o.as<double>());
+                    GKI_CHECK_LAUNCH();
+                }
+            } else {
             entry_weights_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, w.as<uint32_t>(), node_bits, o.as<double>(), n_out, wrap);
             GKI_CHECK_LAUNCH();
             const int64_t passes = ((int64_t)n_out * 8 + (int64_t)slice_bytes - 1) / (int64_t)slice_bytes;
@@ -1631,6 +1778,7 @@ int gki_node_counts(gki_index_t *ix, double *out, int64_t n_out, int32_t flags, 
                 if (lo >= hi) break;
                 node_counts_slice_kernel<<<grid8, 256, 0, call.stream>>>(w.as<uint32_t>(), ix->n, node_bits, o.as<double>(), (uint32_t)lo, (uint32_t)hi);
                 GKI_CHECK_LAUNCH();
+            }
             }
         } else if (ix->cs_slot) node_counts_csr_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->cs_slot, ix->cs_node, ix->n, o.as<double>(), n_out, wrap);
         else node_counts_kernel<<<grid, 256, 0, call.stream>>>(ix->table, ix->kmers, ix->nodes, ix->n, o.as<double>(), n_out, wrap);

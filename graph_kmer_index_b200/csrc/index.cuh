@@ -61,6 +61,12 @@ struct gki_index {
     // entries regrouped by count-table slot (count.cu): slot index and node | orientation << 31, so that get_node_counts
     // streams the table instead of looking every entry up
     uint32_t *cs_slot = nullptr, *cs_node = nullptr;
+    // get_node_counts with more nodes than L2 keeps (count.cu): where every tile of entries writes its (node, weight) words, grouped
+    // by node range (nb_seg[range * nb_tiles + tile], one more element at the end); built by the first such call
+    uint32_t *nb_seg = nullptr;
+    uint32_t nb_bounds[65] = {};       // first word of every range, and the total
+    int32_t nb_ranges = 0, nb_shift = 0;
+    int64_t nb_tiles = 0;
     int64_t n_distinct = 0;
     size_t table_bytes = 0, filter_bytes = 0;
     // host-buffer streaming (gki_count_reads / gki_count_kmers with host pointers)

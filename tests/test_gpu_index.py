@@ -585,13 +585,16 @@ def test_partitioned_build_with_packed_records_emulated_on_one_gpu(gki, monkeypa
     assert np.array_equal(cat["freq"].view(np.uint16), want["_frequencies"])
 
 
-@pytest.mark.parametrize("slice_mb", [None, "16", "1", "0"])
-def test_node_counts_with_more_nodes_than_l2(gki, monkeypatch, slice_mb):
-    """node ids spread over 12 M (96 MB of float64 counts, more than L2 keeps): same counts as the oracle, in one pass and in
-    passes over node ranges (gki_node_counts: weights materialised once, one pass per range of GKI_NODE_SLICE_MB of counts)"""
+@pytest.mark.parametrize("slice_mb,ranged", [(None, None), ("16", None), ("16", "0"), ("1", "0"), (None, "0"), ("0", None)])
+def test_node_counts_with_more_nodes_than_l2(gki, monkeypatch, slice_mb, ranged):
+    """node ids spread over 12 M (96 MB of float64 counts, more than L2 keeps): same counts as the oracle, in one pass ("0"), with the
+    (node, weight) words grouped by node range tile by tile (the default for such vectors), and in passes over all words per node range
+    (GKI_NODE_RANGED=0: one pass per GKI_NODE_SLICE_MB of counts)"""
     from graph_kmer_index_b200 import synthetic
     if slice_mb is not None:
         monkeypatch.setenv("GKI_NODE_SLICE_MB", slice_mb)
+    if ranged is not None:
+        monkeypatch.setenv("GKI_NODE_RANGED", ranged)
     n, k, modulo, n_nodes = 300000, 31, 1000003, 12_000_000
     hashes, _, ref, af = synthetic.flat_kmers(n, 1000, k)
     rng = np.random.default_rng(8)
