@@ -787,9 +787,9 @@ __global__ void node_counts_slice_kernel(const uint32_t *__restrict__ packed, in
 // every call (nb_seg, built once: per-tile histogram of the ranges + one exclusive scan in range-major order); each range is then
 // read once.  A tile is ordered in shared memory (slot = the range's first place in the tile + a shared-memory atomic) and leaves with
 // coalesced stores.  Ranges are 2^nb_shift nodes (32 MB of counts).  c3 (1 B entries, 50 M nodes; ncu, profiles/r2/node_counts_ranged_launches.txt):
-// 60 GB -> 32 GB per call, 10.4 -> 9.6 ms: the words pass 6.6 ms (24 GB of table + entry list read, 4 GB written), the twelve ranges
+// 60 GB -> 32 GB per call, 10.4 -> 9.1 ms: the words pass 6.1 ms (24 GB of table + entry list read, 4 GB written; 6.6 ms with 256 threads per tile), the twelve ranges
 // 0.25 ms each, which is the rate of float64 REDs on L2-resident lines (49 M additions per range = 196 G/s).
-constexpr int NB_TILE = 8192, NB_THREADS = 256, NB_MAX_RANGES = 64;   // (gki_index::nb_bounds holds NB_MAX_RANGES + 1 values)
+constexpr int NB_TILE = 8192, NB_THREADS = 512, NB_MAX_RANGES = 64;   // (gki_index::nb_bounds holds NB_MAX_RANGES + 1 values)
 __global__ void __launch_bounds__(NB_THREADS) node_range_hist_kernel(const uint32_t *__restrict__ cs_node, int64_t n, int shift, int ranges, int64_t n_tiles,
                                                                      uint32_t *__restrict__ hist) {
     __shared__ uint32_t h[NB_MAX_RANGES];
