@@ -28,6 +28,17 @@ if os.environ.get("GKI_SYNTH_ORDER") == "finder":      # rows of a k-mer adjacen
     hashes, nodes, ref, af = (c[order] for c in (hashes, nodes, ref, af))
     del order
     torch.cuda.empty_cache()
+if os.environ.get("GKI_SYNTH_ORDER") == "finder4":     # four adjacent rows per k-mer (a k-mer whose path covers four nodes): every second k-mer of the finder order, twice
+    j = torch.arange(n, dtype=torch.int64, device=dev)
+    pos = (j * synthetic.PERM_MULT + synthetic.PERM_ADD) % n
+    order = torch.empty_like(j)
+    order[pos] = j
+    del j, pos
+    pick = order.view(-1, 4)[:, :2].repeat_interleave(2, dim=0).reshape(-1)[:n] if n % 4 == 0 else order
+    hashes, ref, af = hashes[pick], ref[pick], af[pick]
+    nodes = nodes[order]
+    del order, pick
+    torch.cuda.empty_cache()
 h2i = torch.empty(modulo, dtype=torch.int32, device=dev)
 nkm = torch.empty(modulo, dtype=torch.int32, device=dev)
 o_k, o_r, o_n, o_a = torch.empty_like(hashes), torch.empty_like(ref), torch.empty_like(nodes), torch.empty_like(af)
