@@ -1,11 +1,14 @@
 """Seeded random shapes through the fused counting path (ASCII, packed, host and device buffers, every filter addressing) against
 the C oracle: read lengths from k up to a few hundred bases, every k, odd batch sizes, N / lower-case rates from 0 to 30 %."""
+import os
+
 import numpy as np
 import pytest
 
 from oracle import c_oracle
 
 pytestmark = pytest.mark.gpu
+EXTRA = int(os.environ.get("GKI_FUZZ_EXTRA", "0"))       # more seeds for a one-off longer run
 
 
 def random_case(seed):
@@ -19,7 +22,7 @@ def random_case(seed):
     return k, L, n_reads, n, modulo, int(rng.choice([0, 10, 300])), bool(rng.integers(0, 2)), int(rng.integers(0, 3))
 
 
-@pytest.mark.parametrize("seed", range(48))
+@pytest.mark.parametrize("seed", range(48 + EXTRA))
 def test_random_shapes(monkeypatch, seed):
     import torch
     import graph_kmer_index_b200 as gki
@@ -52,7 +55,7 @@ def test_random_shapes(monkeypatch, seed):
     dev.close()
 
 
-@pytest.mark.parametrize("seed", range(20))
+@pytest.mark.parametrize("seed", range(20 + EXTRA // 4))
 def test_random_builds(seed):
     """gki_index_build on random sizes / table sizes / repeat patterns (binned path, its big-bin variant and the radix fallback are
     all reached) against the C oracle"""
