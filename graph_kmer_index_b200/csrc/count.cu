@@ -1109,6 +1109,12 @@ template <bool PACKED> static int launch_paired(gki_index *ix, const WarpBatch &
     if (ix->table.filter && ix->table.filter_m) {   // minimizer-addressed filter: odd k in 27..31 by construction (ensure_table)
         return fk3 ? launch_count_reads_t<true, true, 4, 0, PACKED, true, 3, true>(ix, b, s) : launch_count_reads_t<true, true, 4, 0, PACKED, true, 0, true>(ix, b, s);
     }
+#ifdef GKI_EXPERIMENT_KNOBS   // 3 or 5 resident CTAs per SM with the register budget that goes with them (85 / 48 instead of 64)
+    if (const char *e = experiment_knob("GKI_COUNT_MINB")) {
+        if (!PACKED && (b.k & 1) && fk3 && atoi(e) == 3) return launch_count_reads_t<true, true, 3, 0, false, true, 3>(ix, b, s);
+        if (!PACKED && (b.k & 1) && fk3 && atoi(e) == 5) return launch_count_reads_t<true, true, 5, 0, false, true, 3>(ix, b, s);
+    }
+#endif
     if (b.k & 1) return fk3 ? launch_count_reads_t<true, true, 4, 0, PACKED, true, 3>(ix, b, s) : launch_count_reads_t<true, true, 4, 0, PACKED, true, 0>(ix, b, s);
     return launch_count_reads_t<true, true, 4, 0, PACKED, false, 0>(ix, b, s);
 }

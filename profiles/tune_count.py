@@ -34,7 +34,7 @@ torch.cuda.synchronize()
 counts = torch.zeros(n_nodes, dtype=torch.float64, device=dev)
 ref_sum = None
 results = []
-KNOBS = ("GKI_COUNT_GRID_MULT", "GKI_COUNT_CTAS", "GKI_FILTER_MZ", "GKI_FILTER_MAX_MB", "GKI_FILTER_K", "GKI_TABLE_RAW", "GKI_RPW", "GKI_HINTS", "GKI_L2_FETCH")
+KNOBS = ("GKI_COUNT_MINB", "GKI_COUNT_GRID_MULT", "GKI_COUNT_CTAS", "GKI_FILTER_MZ", "GKI_FILTER_MAX_MB", "GKI_FILTER_K", "GKI_TABLE_RAW", "GKI_RPW", "GKI_HINTS", "GKI_L2_FETCH")
 combos = json.loads(sys.argv[3]) if len(sys.argv) > 3 else [{"GKI_FILTER_MAX_MB": mb} for mb in (0, 16, 32, 48, 64)]
 for env in combos:
     for key in KNOBS:
